@@ -1,0 +1,175 @@
+"""Seeded synthetic inputs for every BASELINE.json config.
+
+No dataset or checkpoint ships with the reference (README.md:63-84 are Google
+Drive links), so weights, frames and solver problems are generated here.  All
+generators are pure numpy / torch-CPU and deterministic in ``seed``; the same
+functions feed the CUDA path, the oracle and the golden-fixture scripts.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import torch
+
+from . import arch
+
+# YCB-Video intrinsics used by the reference's data
+K_YCBV = np.array([[1066.778, 0.0, 312.9869], [0.0, 1067.487, 241.3109], [0.0, 0.0, 1.0]])
+
+
+def make_synthetic_state_dict(seed: int = 0, num_kp: int = arch.NUM_KP, peaky: float = 1.0):
+    """A state dict with the reference's key names/shapes (arch.state_dict_spec).
+
+    Each tensor is drawn from its own generator keyed by (seed, crc32(key)), so
+    the values do not depend on construction order or on torch's module-init
+    code.  Convs: U(-b, b) with b = sqrt(2 / fan_in) (measured: final logits of O(1-10),
+    so 59 residual blocks neither explode nor vanish); BN running stats / affine
+    are randomised so that BN folding is exercised.
+    ``peaky`` scales the last tmpOut conv so heat-maps get an unambiguous peak.
+    """
+    sd = {}
+    for key, shape in arch.state_dict_spec(num_kp):
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        leaf = key.rsplit(".", 1)[1]
+        if leaf == "num_batches_tracked":
+            sd[key] = torch.tensor(100, dtype=torch.long)
+            continue
+        is_bn = len(shape) == 1 and (".bn" in key or key.startswith("backbone.bn1.")
+                                     or (".lin_." in key and key.split(".")[3] == "1"))
+        if is_bn:
+            if leaf == "running_mean":
+                t = torch.randn(shape, generator=g) * 0.1
+            elif leaf == "running_var":
+                t = torch.rand(shape, generator=g) + 0.5
+            elif leaf == "weight":
+                t = torch.rand(shape, generator=g) + 0.5
+            else:  # bias
+                t = torch.randn(shape, generator=g) * 0.1
+        elif leaf == "weight":
+            fan_in = int(np.prod(shape[1:]))
+            b = (2.0 / fan_in) ** 0.5
+            t = (torch.rand(shape, generator=g) * 2 - 1) * b
+        else:  # conv / linear bias
+            t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+        sd[key] = t.to(torch.float32)
+    last = f"backbone.tmpOut.{arch.N_STACK - 1}"
+    sd[last + ".weight"] = sd[last + ".weight"] * peaky
+    sd[last + ".bias"] = sd[last + ".bias"] * peaky
+    return sd
+
+
+def random_rotation(rng: np.random.Generator) -> np.ndarray:
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def so3_exp(w: np.ndarray) -> np.ndarray:
+    th = np.linalg.norm(w)
+    W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    if th < 1e-12:
+        return np.eye(3) + W
+    return np.eye(3) + np.sin(th) / th * W + (1 - np.cos(th)) / th ** 2 * (W @ W)
+
+
+def fix_K_for_bbox_ndc(K: np.ndarray, bbox) -> np.ndarray:
+    """K_bbox = S·T·K: camera matrix projecting into the bbox's NDC square
+    [-1,1]² with *negative* fy (reference lib/utils/utils.py:416-429)."""
+    x1, y1, x2, y2 = [float(v) for v in bbox]
+    w, h = x2 - x1, y2 - y1
+    T = np.eye(3)
+    T[0, 2], T[1, 2] = -x1, -y1
+    S = np.eye(3)
+    S[0, :] *= 2.0 / w
+    S[1, :] *= -2.0 / h
+    S[0, 2] -= 1.0
+    S[1, 2] += 1.0
+    return S @ T @ np.asarray(K, dtype=np.float64)
+
+
+def make_frame(seed: int, n_obj: int = 8, H: int = 480, W: int = 640, num_kp: int = arch.NUM_KP,
+               K: np.ndarray = K_YCBV, uv_noise: float = 0.01, outlier_frac: float = 0.1):
+    """One synthetic YCBV-shape frame (SURVEY.md §8d "Frame")."""
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    objs = []
+    for o in range(n_obj):
+        model_kps = rng.uniform(-60, 60, size=(num_kp, 3))
+        n_valid = int(rng.integers(8, 23))
+        mask = np.zeros(num_kp, dtype=bool)
+        mask[rng.choice(num_kp, size=n_valid, replace=False)] = True
+        for _ in range(50):
+            R = random_rotation(rng)
+            t = np.array([rng.uniform(-150, 150), rng.uniform(-100, 100), rng.uniform(600, 1200)])
+            pc = model_kps @ R.T + t
+            px = pc @ K.T
+            px = px[:, :2] / px[:, 2:3]
+            lo, hi = px[mask].min(0), px[mask].max(0)
+            ctr, half = (lo + hi) / 2, (hi - lo) / 2 * 1.1
+            box = np.array([ctr[0] - half[0], ctr[1] - half[1], ctr[0] + half[0], ctr[1] + half[1]])
+            box[[0, 2]] = np.clip(box[[0, 2]], 0, W - 1)
+            box[[1, 3]] = np.clip(box[[1, 3]], 0, H - 1)
+            if box[2] - box[0] >= 10 and box[3] - box[1] >= 10:
+                break
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = R, t
+        Kb = fix_K_for_bbox_ndc(K, box)
+        uv = pc @ Kb.T
+        uv = uv[:, :2] / uv[:, 2:3]
+        uv_meas = uv + rng.normal(scale=uv_noise, size=uv.shape)
+        n_out = int(round(outlier_frac * n_valid))
+        if n_out:
+            idx = rng.choice(np.nonzero(mask)[0], size=n_out, replace=False)
+            uv_meas[idx] = rng.uniform(-0.9, 0.9, size=(n_out, 2))
+        sig = rng.uniform(0.005, 0.05, size=(num_kp, 2))
+        rho = rng.uniform(-0.5, 0.5, size=num_kp)
+        cov = np.zeros((num_kp, 2, 2))
+        cov[:, 0, 0], cov[:, 1, 1] = sig[:, 0] ** 2, sig[:, 1] ** 2
+        cov[:, 0, 1] = cov[:, 1, 0] = rho * sig[:, 0] * sig[:, 1]
+        objs.append(dict(T_OtoC=T, model_kps=model_kps, model_kps_mask=mask, bbox=box.astype(np.float32),
+                         K_bbox=Kb, uv_gt=uv, uv_meas=uv_meas, cov=cov, diameter=150.0))
+    return dict(img=img, K=K.copy(), objs=objs)
+
+
+def make_ba_problem(seed: int, n_obj: int = 512, n_kp: int = 12, noise_px: float = 1.0,
+                    outlier_frac: float = 0.0):
+    """BASELINE config 3: objects x keypoints seen by one fixed camera, object
+    poses perturbed by exp(N(0,(5°,5°,5°,10,10,20mm))) (SURVEY.md §8d "C3";
+    generator modelled on thirdparty/g2opy/python/examples/object_slam_demo.py:54-150,
+    cam_k=[320,320,320,240])."""
+    rng = np.random.default_rng(seed)
+    cam_k = np.array([320.0, 320.0, 320.0, 240.0])
+    p_O = rng.uniform(-60, 60, size=(n_obj, n_kp, 3))
+    T_gt = np.zeros((n_obj, 3, 4))
+    T_init = np.zeros((n_obj, 3, 4))
+    uv = np.zeros((n_obj, n_kp, 2))
+    info = np.zeros((n_obj, n_kp, 2, 2))
+    for o in range(n_obj):
+        R = random_rotation(rng)
+        t = np.array([rng.uniform(-200, 200), rng.uniform(-150, 150), rng.uniform(600, 1200)])
+        T_gt[o, :, :3], T_gt[o, :, 3] = R, t
+        pc = p_O[o] @ R.T + t
+        uv[o, :, 0] = cam_k[0] * pc[:, 0] / pc[:, 2] + cam_k[2]
+        uv[o, :, 1] = cam_k[1] * pc[:, 1] / pc[:, 2] + cam_k[3]
+        uv[o] += rng.normal(scale=noise_px, size=(n_kp, 2))
+        n_out = int(round(outlier_frac * n_kp))
+        if n_out:
+            idx = rng.choice(n_kp, size=n_out, replace=False)
+            uv[o, idx] += rng.uniform(-60, 60, size=(n_out, 2))
+        sig = rng.uniform(0.5, 2.0, size=(n_kp, 2)) * noise_px
+        rho = rng.uniform(-0.5, 0.5, size=n_kp)
+        cov = np.zeros((n_kp, 2, 2))
+        cov[:, 0, 0], cov[:, 1, 1] = sig[:, 0] ** 2, sig[:, 1] ** 2
+        cov[:, 0, 1] = cov[:, 1, 0] = rho * sig[:, 0] * sig[:, 1]
+        info[o] = np.linalg.inv(cov)
+        dw = np.deg2rad(rng.normal(scale=5.0, size=3))
+        dt = rng.normal(size=3) * np.array([10.0, 10.0, 20.0])
+        dR = so3_exp(dw)
+        T_init[o, :, :3] = R @ dR          # perturb in the object frame: T_gt * exp(delta)
+        T_init[o, :, 3] = R @ dt + t
+    return dict(cam_k=cam_k, p_O=p_O, uv=uv, info=info, T_gt=T_gt, T_init=T_init)
