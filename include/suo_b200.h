@@ -1,0 +1,176 @@
+/* libsuo_b200 — C ABI of the B200-native SUO-SLAM per-frame hot path.
+ *
+ * Plain C: pointers + sizes, no torch / C++ types.  Every entry point returns 0 on
+ * success and a negative SUO_E_* code on failure (suo_last_error() gives the text);
+ * nothing throws across the boundary.  One suo_ctx per GPU; a ctx is not thread
+ * safe, different ctxs are.  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  `on_device` != 0 means every data pointer of the call is
+ * a device pointer on the ctx's GPU and the call only enqueues work on `stream`;
+ * `on_device` == 0 means host pointers: the call stages them through pinned memory,
+ * runs, copies results back and synchronises the stream before returning (this is
+ * the reference-facing form: the reference's pybind entry points take/return numpy).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference checkout, rpng/suo_slam @ 5de01433).
+ */
+#ifndef SUO_B200_H_
+#define SUO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct suo_ctx suo_ctx;
+
+enum {
+  SUO_OK = 0,
+  SUO_E_INVALID = -1,   /* bad argument / shape */
+  SUO_E_CUDA = -2,      /* CUDA runtime error (text in suo_last_error) */
+  SUO_E_STATE = -3,     /* e.g. forward before load_weights */
+  SUO_E_NOMEM = -4
+};
+
+/* Options for suo_set_option */
+enum {
+  SUO_OPT_CONV_BACKEND = 1, /* 0 = FP32 SIMT implicit GEMM, 1 = tcgen05 TF32 tensor cores (default) */
+  SUO_OPT_TF32_PASSES = 2,  /* 3 = 3xTF32 split (FP32-equivalent, default), 1 = single-pass TF32 */
+  SUO_OPT_USE_GRAPH = 3     /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
+};
+
+/* BA vertex/edge conventions (see suo_ba_batch) */
+enum { SUO_BA_EDGE_UNARY = -1 };
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* max_crops: largest crop batch one forward will see; crop_res: network input side
+ * (256 -> 64x64 heat-maps, lib/models/pkpnet.py:67 input_res); num_kp: 41
+ * (lib/labeling/kp_config.py:93-94). */
+int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** out);
+void suo_destroy(suo_ctx* ctx);
+const char* suo_last_error(const suo_ctx* ctx);
+int suo_set_option(suo_ctx* ctx, int option, int value);
+/* Number of this library's kernels launched since ctx creation (bench.py gpu_launches). */
+long long suo_kernel_launches(const suo_ctx* ctx);
+
+/* ---- weights ------------------------------------------------------------------- */
+/* Replaces PkpNet.load_state_dict(checkpoint['model']) (lib/object_slam.py:92-97).
+ * `blob` is the packed, BN-folded image produced by suo_slam_b200.weights.pack_state_dict
+ * (host pointer, copied). */
+int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes);
+
+/* ---- network forward ----------------------------------------------------------- */
+/* Replaces PkpNet.forward(images, boxes, prior_kp) (lib/models/pkpnet.py:80-119):
+ * roi_align crop + prior concat -> 2-stack hourglass -> spatial softmax ->
+ * soft-argmax / 2x2 covariance -> keypoint-present classifier.
+ *   images   [n_img,3,H,W] f32 in [0,1] (NCHW, as the reference passes them)
+ *   boxes    [L,4] xyxy f32, box_img[L] = image index of each box
+ *   priors   [L,num_kp,R,R] f32 or NULL (NULL == all-zero prior planes)
+ * Outputs (any may be NULL to skip): uv[L,K,2], cov[L,K,2,2], logits[L,K,R/4,R/4],
+ * prob (same shape), mask_logits[L,K], mask[L,K], argmax[L,K] (flat h*W+w of the max
+ * logit, first occurrence). */
+int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W,
+                const float* boxes, const int32_t* box_img, int L, const float* priors,
+                float* uv, float* cov, float* logits, float* prob,
+                float* mask_logits, float* mask, int32_t* argmax,
+                int on_device, void* stream);
+
+/* Stand-alone heat-map reduction (spatial_softmax + post_process_kp + classifier,
+ * lib/models/pkpnet.py:13-63,74-78,106-118).  logits [B,K,H,W] f32; cls_w [K,K],
+ * cls_b [K] may be NULL (then mask outputs are skipped). */
+int suo_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W,
+                       const float* cls_w, const float* cls_b,
+                       float* uv, float* cov, float* prob, float* mask_logits, float* mask,
+                       int32_t* argmax, int on_device, void* stream);
+
+/* roi_align crop + prior concat alone (lib/models/pkpnet.py:91-101); out is the NHWC
+ * tensor the network consumes: [L,R,R,out_c] with out_c = 4 (priors == NULL: RGB + one
+ * zero plane) or 48 (RGB, num_kp prior planes, zero padding). */
+int suo_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W,
+                    const float* boxes, const int32_t* box_img, int L, const float* priors,
+                    int R, float* out, int out_c, int on_device, void* stream);
+
+/* One convolution layer through the library's conv engine — test/bench hook for the
+ * dense-contraction kernels (no reference counterpart; the reference calls cuDNN/MKL-DNN
+ * through torch.nn.Conv2d, lib/models/layers/Residual.py:9-18).
+ *   in  [B,H,W,Cin] NHWC f32;  w [Cout,kh,kw,Cin] f32;  bias [Cout] or NULL
+ *   pre_scale/pre_shift [Cin] or NULL: input prologue relu(x*s+t) (pre-activation BN)
+ *   residual [B,Ho,Wo,Cout] or NULL; relu: apply ReLU after bias (before residual is
+ *   never needed by the network; residual layers have relu == 0)
+ *   ksize in {1,3,7}; stride 1 (ksize 1,3; pad (ksize-1)/2) or 2 (ksize 7, pad 3)
+ *   backend: 0 SIMT FP32, 1 tcgen05; tf32_passes as SUO_OPT_TF32_PASSES. */
+int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin,
+               const float* w, const float* bias, int Cout, int ksize, int stride,
+               const float* pre_scale, const float* pre_shift, const float* residual, int relu,
+               float* out, int backend, int tf32_passes, int on_device, void* stream);
+
+/* ---- PnP ----------------------------------------------------------------------- */
+/* Replaces lambdatwist.pnp(xs, ys, threshold) (thirdparty/lambdatwist/pnp_python_binding.cpp:32-62
+ * -> PNP::compute / refine, pnp_ransac.cpp:188-326) for a BATCH of objects.
+ *   xs [N,3] f64 model points, ys [N,2] f64 pinhole-normalised image points,
+ *   offsets[n_obj+1] row ranges per object (object o owns rows offsets[o]..offsets[o+1])
+ *   seed / obj_keys[n_obj] (NULL -> key = object index): counter-based RANSAC sampling
+ *   T_out [n_obj,16] row-major 4x4; identity == failure, exactly like the reference
+ *   stats [n_obj,5] i32 or NULL: best_inliers, best_iter, total_iters, refine1_its, refine2_its */
+int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj,
+                  double threshold, uint64_t seed, const uint64_t* obj_keys,
+                  double* T_out, int32_t* stats, int on_device, void* stream);
+
+/* ---- bundle adjustment --------------------------------------------------------- */
+/* Replaces the g2o solve inside ObjectSLAM.optimize() (lib/object_slam.py:842-896 driving
+ * SparseOptimizer::optimize / OptimizationAlgorithmLevenberg::solve with
+ * EdgeSE3ProjectFromObject / EdgeSE3ProjectFromFixedObject,
+ * thirdparty/g2opy/g2o/types/object_slam/types_object_slam.cpp:45-201) for a BATCH of
+ * independent problems (one LM lambda / accept test per problem, as g2o has per graph).
+ *   poses     [n_vert,12] f64 row-major [R|t], in/out (all problems' vertices concatenated)
+ *   fixed     [n_vert] u8
+ *   prob_vert [n_prob+1], prob_edge[n_prob+1]: vertex / edge ranges of each problem
+ *   e_obj     [n_edges] object vertex (global index) or SUO_BA_EDGE_UNARY (p is then p_inG)
+ *   e_cam     [n_edges] camera vertex (global index)
+ *   cam_k [n_edges,4] fx fy cx cy; p [n_edges,3]; uv [n_edges,2]; info [n_edges,4]
+ *   inliers   [n_edges] u8 in/out
+ *   its[n_rounds] LM iterations per round; huber_delta; chi2_gate; init_with_outliers
+ *   stats     [n_prob,3] i32 or NULL: rounds run, outer iterations, LM trials
+ * Every edge must touch exactly one non-fixed vertex (single-view mode: camera fixed;
+ * curr_only mode: objects folded into p_inG) — the camera+object coupled global graph
+ * is SURVEY.md §8 row f3 and returns SUO_E_INVALID here. */
+int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge,
+                 double* poses, const uint8_t* fixed, int n_vert,
+                 const int32_t* e_obj, const int32_t* e_cam, const double* cam_k, const double* p,
+                 const double* uv, const double* info, uint8_t* inliers, int n_edges,
+                 const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
+                 int init_with_outliers, int32_t* stats, int on_device, void* stream);
+
+/* ---- keypoints -> poses ---------------------------------------------------------- */
+/* Everything ObjectSLAM does with the network output of single-view frames, device resident:
+ * keypoint gating (lib/object_slam.py:1100-1115), per-object PnP (:1123-1165 -> lambdatwist.pnp)
+ * and the single-view optimize() (:703-930, camera fixed at identity, its=[10]*4).
+ *   uv [L,K,2] f32, cov [L,K,4] f32, kp_mask [L,K] f32 (sigmoid output); box_img [L] sorted:
+ *   crops of one image form one BA graph (one LM lambda per image, as g2o has per optimizer).
+ * Other arguments / outputs as suo_frames. */
+int suo_solve_keypoints(suo_ctx* ctx, const float* uv, const float* cov, const float* kp_mask, const int32_t* box_img,
+                        int n_img, int L, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                        const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+                        double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, int on_device, void* stream);
+
+/* ---- fused per-frame pipeline -------------------------------------------------- */
+/* One call for a batch of single-view frames: forward -> keypoint gating
+ * (lib/object_slam.py:1100-1115) -> per-object PnP (:1123-1165) -> single-view BA
+ * (optimize(), :703-930, camera fixed at identity) with everything resident on the GPU.
+ *   model_kps [L,K,3] f64, model_mask [L,K] u8, K_bbox [L,9] f64 (fix_K_for_bbox_ndc),
+ *   diameter [L] f64; thresholds as ObjectSLAM.__init__ (kp_var_thresh, bbox_thresh)
+ * Outputs: T_pnp [L,16] f64 (identity = rejected), T_ba [L,12] f64, kp_used [L,K] u8,
+ * ba_inliers [L,K] u8, uv [L,K,2] f32, cov [L,K,4] f32 (any may be NULL). */
+int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W,
+               const float* boxes, const int32_t* box_img, int L, const float* priors,
+               const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+               const double* diameter, double kp_var_thresh, double bbox_thresh,
+               uint64_t seed, int run_ba,
+               double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
+               float* uv, float* cov, int on_device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUO_B200_H_ */

@@ -677,7 +677,10 @@ struct LMState { double lambda; double ni; };
 static int g2o_optimize(Graph& G, int iterations, int* lm_trials_total) {
   // initializeOptimization(0): active edges = level 0; active vertices = non-fixed vertices touched by them
   std::vector<int> active;
-  for (int e = 0; e < G.n_edges; ++e) if (G.level[e] == 0) active.push_back(e);
+  // edges whose vertices are all fixed never enter the active set (SparseOptimizer::initializeOptimization,
+  // sparse_optimizer.cpp:201-272 skips e->allVerticesFixed())
+  for (int e = 0; e < G.n_edges; ++e)
+    if (G.level[e] == 0 && (!G.fixed[G.e_cam[e]] || (G.e_obj[e] >= 0 && !G.fixed[G.e_obj[e]]))) active.push_back(e);
   std::vector<int> col(G.n_vert, -1);
   int nfree = 0;
   {

@@ -1,0 +1,734 @@
+// C-ABI entry points of libsuo_b200 (include/suo_b200.h) and the network executor.
+//
+// The network topology is not hard-coded here: suo_load_weights() receives a packed blob
+// (suo_slam_b200/weights.py) holding a buffer table, an op list ("program") and a float pool
+// with BN-folded weights.  The executor owns the activation buffers (NHWC FP32 in HBM, one
+// buffer per op output: 180 GB of HBM make liveness-based reuse unnecessary at these sizes),
+// packs the weights for the tensor-core kernel once, and replays the op list — as a CUDA
+// graph per (crop count, variant) — on the caller's stream.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <memory>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int32_t kMagic = 0x574F5553;  // 'SUOW'
+enum OpType : int32_t { OP_CONV = 0, OP_MAXPOOL = 1, OP_UPADD = 2 };
+
+struct BlobHeader {
+  int32_t magic, version, num_kp, n_bufs, n_ops, n_floats;
+  int32_t in_buf_noprior, in_buf_prior, logits_buf, cls_w_off, cls_b_off, heat_div;
+  int32_t reserved[4];
+};
+struct BufDesc { int32_t div, C; };
+struct OpDesc {
+  int32_t type, variant, in, out, res, mode, Cin, Cout, Cout_pad, K, cpr, relu, out_nchw, w_off, b_off, pre_off;
+};
+
+struct NetState {
+  BlobHeader h{};
+  std::vector<BufDesc> bufs;
+  std::vector<OpDesc> ops;
+  float* pool = nullptr;                     // device float pool (canonical weights, biases, prologues)
+  std::vector<float*> packed;                // per op: tcgen05 weight images (device) or nullptr
+  std::vector<float*> act;                   // per buffer: device activation tensor
+  float* pooled = nullptr;                   // [max_crops, K] channel means
+  float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
+  int32_t* d_argmax = nullptr;
+  struct GraphKey { int L, variant, backend, passes; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes) < std::tie(o.L, o.variant, o.backend, o.passes); } };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+};
+
+struct DevScratch {   // growable device + pinned staging for host-pointer calls
+  void* d = nullptr; size_t dn = 0;
+  int grow(suo_ctx* ctx, size_t n) {
+    if (n <= dn) return SUO_OK;
+    if (d) cudaFree(d);
+    dn = 0; d = nullptr;
+    SUO_CUDA_TRY(ctx, cudaMalloc(&d, n));
+    dn = n;
+    return SUO_OK;
+  }
+};
+
+struct CtxExtra {
+  NetState net;
+  DevScratch io;        // staged inputs/outputs of host-pointer calls
+  DevScratch ba;        // BA err/level/fv scratch
+  DevScratch fr;        // suo_frames workspace
+  bool loaded = false;
+};
+
+CtxExtra* X(suo_ctx* c) { return reinterpret_cast<CtxExtra*>(c->net); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// bump allocator over one device scratch block
+struct Bump {
+  uint8_t* base; size_t off = 0;
+  template <typename T> T* take(size_t n) { off = align_up(off, 256); T* p = reinterpret_cast<T*>(base + off); off += n * sizeof(T); return p; }
+};
+
+int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
+  NetState& N = X(ctx)->net;
+  const int R = ctx->crop_res;
+  for (size_t i = 0; i < N.ops.size(); ++i) {
+    const OpDesc& o = N.ops[i];
+    if (o.variant != 2 && o.variant != variant) continue;
+    const BufDesc& bi = N.bufs[o.in];
+    const BufDesc& bo = N.bufs[o.out];
+    int rc = SUO_OK;
+    if (o.type == OP_CONV) {
+      ConvParams p{};
+      p.in = N.act[o.in];
+      p.w = N.pool + o.w_off;
+      p.w_packed = N.packed[i];
+      p.bias = N.pool + o.b_off;
+      p.pre_scale = o.pre_off >= 0 ? N.pool + o.pre_off : nullptr;
+      p.pre_shift = o.pre_off >= 0 ? N.pool + o.pre_off + o.Cin : nullptr;
+      p.residual = o.res >= 0 ? N.act[o.res] : nullptr;
+      p.out = N.act[o.out];
+      p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin;
+      p.Ho = R / bo.div; p.Wo = R / bo.div;
+      p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
+      p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
+      rc = backend == 1 ? launch_conv_tc(ctx, p, passes, s) : launch_conv_simt(ctx, p, s);
+    } else if (o.type == OP_MAXPOOL) {
+      rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);
+    } else if (o.type == OP_UPADD) {
+      rc = launch_upsample_add(ctx, N.act[o.in], N.act[o.res], L, R / bo.div, R / bo.div, bo.C, N.act[o.out], s);
+    } else {
+      ctx->set_error("unknown op type in program", __FILE__, __LINE__);
+      return SUO_E_INVALID;
+    }
+    if (rc != SUO_OK) return rc;
+  }
+  return SUO_OK;
+}
+
+int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
+  NetState& N = X(ctx)->net;
+  const int backend = ctx->opt_backend, passes = ctx->opt_passes;
+  if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
+  NetState::GraphKey key{L, variant, backend, passes};
+  auto it = N.graphs.find(key);
+  if (it == N.graphs.end()) {
+    // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
+    int rc = run_program(ctx, L, variant, backend, passes, s);
+    if (rc != SUO_OK) return rc;
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    cudaStream_t cs;
+    SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    SUO_CUDA_TRY(ctx, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const long long before = ctx->launches;
+    rc = run_program(ctx, L, variant, backend, passes, cs);
+    ctx->launches = before;   // captured, not launched
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    if (rc != SUO_OK || e != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaStreamDestroy(cs);
+      if (rc == SUO_OK) { ctx->set_error(std::string("graph capture: ") + cudaGetErrorString(e), __FILE__, __LINE__); rc = SUO_E_CUDA; }
+      return rc;
+    }
+    cudaGraphExec_t ge;
+    SUO_CUDA_TRY(ctx, cudaGraphInstantiate(&ge, g, 0));
+    cudaGraphDestroy(g);
+    cudaStreamDestroy(cs);
+    it = N.graphs.emplace(key, ge).first;
+    return SUO_OK;   // the warm-up run above already produced this call's result
+  }
+  SUO_CUDA_TRY(ctx, cudaGraphLaunch(it->second, s));
+  // count the kernels the graph replays
+  long long n = 0;
+  for (const OpDesc& o : N.ops) if (o.variant == 2 || o.variant == variant) ++n;
+  ctx->launches += n;
+  return SUO_OK;
+}
+
+int check_ctx(suo_ctx* ctx) {
+  if (!ctx) return SUO_E_INVALID;
+  cudaError_t e = cudaSetDevice(ctx->device);
+  if (e != cudaSuccess) { ctx->set_error(cudaGetErrorString(e), __FILE__, __LINE__); return SUO_E_CUDA; }
+  return SUO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** out) {
+  if (!out || max_crops <= 0 || crop_res < 64 || (crop_res & (crop_res - 1)) || num_kp <= 0 || num_kp > 45) return SUO_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SUO_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return SUO_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SUO_E_CUDA;
+  if (prop.major != 10) return SUO_E_CUDA;   // sm_100a only: there is no fallback path
+  suo_ctx* c = new suo_ctx();
+  c->device = device; c->max_crops = max_crops; c->crop_res = crop_res; c->num_kp = num_kp;
+  c->net = new CtxExtra();
+  *out = c;
+  return SUO_OK;
+}
+
+void suo_destroy(suo_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  CtxExtra* x = X(ctx);
+  if (x) {
+    NetState& N = x->net;
+    for (auto& kv : N.graphs) cudaGraphExecDestroy(kv.second);
+    for (float* p : N.packed) if (p) cudaFree(p);
+    for (float* p : N.act) if (p) cudaFree(p);
+    if (N.pool) cudaFree(N.pool);
+    if (N.pooled) cudaFree(N.pooled);
+    if (N.d_uv) cudaFree(N.d_uv);
+    if (x->io.d) cudaFree(x->io.d);
+    if (x->ba.d) cudaFree(x->ba.d);
+    if (x->fr.d) cudaFree(x->fr.d);
+    delete x;
+  }
+  delete ctx;
+}
+
+const char* suo_last_error(const suo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+long long suo_kernel_launches(const suo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int suo_set_option(suo_ctx* ctx, int option, int value) {
+  if (!ctx) return SUO_E_INVALID;
+  switch (option) {
+    case SUO_OPT_CONV_BACKEND: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_backend = value; return SUO_OK;
+    case SUO_OPT_TF32_PASSES: if (value != 1 && value != 3) return SUO_E_INVALID; ctx->opt_passes = value; return SUO_OK;
+    case SUO_OPT_USE_GRAPH: ctx->opt_graph = value ? 1 : 0; return SUO_OK;
+    default: return SUO_E_INVALID;
+  }
+}
+
+int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (x->loaded) { ctx->set_error("weights already loaded (create a new ctx)", __FILE__, __LINE__); return SUO_E_STATE; }
+  const uint8_t* b = static_cast<const uint8_t*>(blob);
+  if (nbytes < sizeof(BlobHeader)) return SUO_E_INVALID;
+  NetState& N = x->net;
+  memcpy(&N.h, b, sizeof(BlobHeader));
+  if (N.h.magic != kMagic || N.h.version != 1 || N.h.num_kp != ctx->num_kp) {
+    ctx->set_error("bad weight blob header", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  size_t off = sizeof(BlobHeader);
+  const size_t need = off + sizeof(BufDesc) * N.h.n_bufs + sizeof(OpDesc) * N.h.n_ops + sizeof(float) * (size_t)N.h.n_floats;
+  if (nbytes < need) { ctx->set_error("weight blob truncated", __FILE__, __LINE__); return SUO_E_INVALID; }
+  N.bufs.resize(N.h.n_bufs);
+  memcpy(N.bufs.data(), b + off, sizeof(BufDesc) * N.h.n_bufs); off += sizeof(BufDesc) * N.h.n_bufs;
+  N.ops.resize(N.h.n_ops);
+  memcpy(N.ops.data(), b + off, sizeof(OpDesc) * N.h.n_ops); off += sizeof(OpDesc) * N.h.n_ops;
+  const float* pool_h = reinterpret_cast<const float*>(b + off);
+  SUO_CUDA_TRY(ctx, cudaMalloc(&N.pool, sizeof(float) * (size_t)N.h.n_floats));
+  SUO_CUDA_TRY(ctx, cudaMemcpy(N.pool, pool_h, sizeof(float) * (size_t)N.h.n_floats, cudaMemcpyHostToDevice));
+  // tensor-core weight images
+  N.packed.assign(N.ops.size(), nullptr);
+  std::vector<float> tmp;
+  for (size_t i = 0; i < N.ops.size(); ++i) {
+    const OpDesc& o = N.ops[i];
+    if (o.type != OP_CONV) continue;
+    const size_t nf = conv_tc_packed_floats(o.Cout_pad, o.K);
+    tmp.resize(nf);
+    conv_tc_pack_weights(pool_h + o.w_off, o.Cout_pad, o.K, tmp.data());
+    SUO_CUDA_TRY(ctx, cudaMalloc(&N.packed[i], nf * sizeof(float)));
+    SUO_CUDA_TRY(ctx, cudaMemcpy(N.packed[i], tmp.data(), nf * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // activation buffers
+  N.act.assign(N.bufs.size(), nullptr);
+  const int R = ctx->crop_res;
+  for (size_t i = 0; i < N.bufs.size(); ++i) {
+    const size_t side = R / N.bufs[i].div;
+    const size_t n = (size_t)ctx->max_crops * side * side * N.bufs[i].C;
+    SUO_CUDA_TRY(ctx, cudaMalloc(&N.act[i], n * sizeof(float)));
+    SUO_CUDA_TRY(ctx, cudaMemset(N.act[i], 0, n * sizeof(float)));
+  }
+  const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
+  SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
+  SUO_CUDA_TRY(ctx, cudaMalloc(&N.d_uv, LK * (2 + 4 + 1 + 1 + 1) * sizeof(float)));
+  N.d_cov = N.d_uv + LK * 2; N.d_mask = N.d_cov + LK * 4; N.d_mask_logits = N.d_mask + LK;
+  N.d_argmax = reinterpret_cast<int32_t*>(N.d_mask_logits + LK);
+  x->loaded = true;
+  return SUO_OK;
+}
+
+int suo_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
+                       const float* cls_b, float* uv, float* cov, float* prob, float* mask_logits, float* mask,
+                       int32_t* argmax, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (B <= 0 || K <= 0 || !logits) return SUO_E_INVALID;
+  CtxExtra* x = X(ctx);
+  const size_t n = (size_t)B * K * H * W, BK = (size_t)B * K;
+  if (on_device) {
+    // pooled scratch
+    rc = x->ba.grow(ctx, BK * sizeof(float));
+    if (rc) return rc;
+    return launch_heatmap_reduce(ctx, logits, B, K, H, W, cls_w, cls_b, static_cast<float*>(x->ba.d), uv, cov, prob,
+                                 mask_logits, mask, argmax, s);
+  }
+  size_t bytes = (n * (prob ? 2 : 1) + BK * 16 + (size_t)K * K + K) * sizeof(float) + 4096;
+  rc = x->io.grow(ctx, bytes);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  float* d_log = bp.take<float>(n);
+  float* d_prob = prob ? bp.take<float>(n) : nullptr;
+  float* d_pooled = bp.take<float>(BK);
+  float* d_uv = bp.take<float>(BK * 2);
+  float* d_cov = bp.take<float>(BK * 4);
+  float* d_ml = bp.take<float>(BK);
+  float* d_m = bp.take<float>(BK);
+  int32_t* d_am = bp.take<int32_t>(BK);
+  float* d_w = cls_w ? bp.take<float>((size_t)K * K) : nullptr;
+  float* d_b = cls_b ? bp.take<float>(K) : nullptr;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_log, logits, n * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (d_w) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_w, cls_w, (size_t)K * K * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (d_b) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_b, cls_b, K * sizeof(float), cudaMemcpyHostToDevice, s));
+  rc = launch_heatmap_reduce(ctx, d_log, B, K, H, W, d_w, d_b, d_pooled, d_uv, d_cov, d_prob, d_ml, d_m, d_am, s);
+  if (rc) return rc;
+  if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(uv, d_uv, BK * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(cov, d_cov, BK * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (prob) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(prob, d_prob, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (mask_logits && d_w) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(mask_logits, d_ml, BK * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (mask && d_w) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(mask, d_m, BK * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (argmax) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(argmax, d_am, BK * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes,
+                    const int32_t* box_img, int L, const float* priors, int R, float* out, int out_c, int on_device,
+                    void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (L <= 0 || n_img <= 0 || !images || !boxes || !box_img || !out) return SUO_E_INVALID;
+  if (on_device) return launch_crop_concat(ctx, images, n_img, H, W, boxes, box_img, L, priors, ctx->num_kp, R, out, out_c, s);
+  CtxExtra* x = X(ctx);
+  const size_t n_im = (size_t)n_img * 3 * H * W, n_out = (size_t)L * R * R * out_c, n_pr = priors ? (size_t)L * ctx->num_kp * R * R : 0;
+  rc = x->io.grow(ctx, (n_im + n_out + n_pr + 8 * (size_t)L) * sizeof(float) + 4096);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  float* d_im = bp.take<float>(n_im);
+  float* d_box = bp.take<float>(4 * (size_t)L);
+  int32_t* d_bi = bp.take<int32_t>(L);
+  float* d_pr = priors ? bp.take<float>(n_pr) : nullptr;
+  float* d_out = bp.take<float>(n_out);
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_im, images, n_im * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_box, boxes, 4 * (size_t)L * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_bi, box_img, L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (d_pr) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_pr, priors, n_pr * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, n_out * sizeof(float), s));
+  rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, ctx->num_kp, R, d_out, out_c, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, const float* w, const float* bias,
+               int Cout, int ksize, int stride, const float* pre_scale, const float* pre_shift,
+               const float* residual, int relu, float* out, int backend, int tf32_passes, int on_device, void* stream) {
+  // Test / bench hook: host pointers only (packs weights on the fly).
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (on_device) { ctx->set_error("suo_conv2d takes host pointers", __FILE__, __LINE__); return SUO_E_INVALID; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  ConvParams p{};
+  if (ksize == 1 && stride == 1) p.mode = CONV_1x1;
+  else if (ksize == 3 && stride == 1) p.mode = CONV_3x3;
+  else if (ksize == 7 && stride == 2) p.mode = CONV_STEM7;
+  else return SUO_E_INVALID;
+  if (Cin % 4 || (p.mode != CONV_STEM7 && Cin % 32)) return SUO_E_INVALID;
+  const int Ho = stride == 2 ? H / 2 : H, Wo = stride == 2 ? W / 2 : W;
+  const int Cout_pad = (int)align_up(Cout, 64);
+  int K, cpr = 0;
+  if (p.mode == CONV_1x1) K = Cin;
+  else if (p.mode == CONV_3x3) K = 9 * Cin;
+  else { cpr = (7 * Cin + 31) / 32; K = 7 * cpr * 32; }
+  // canonical weights [Cout_pad][K] in gather order from [Cout][kh][kw][Cin]
+  std::vector<float> wc((size_t)Cout_pad * K, 0.f), bc(Cout_pad, 0.f);
+  for (int co = 0; co < Cout; ++co) {
+    if (bias) bc[co] = bias[co];
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx)
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float v = w[(((size_t)co * ksize + ky) * ksize + kx) * Cin + ci];
+          size_t k;
+          if (p.mode == CONV_STEM7) k = (size_t)ky * cpr * 32 + (size_t)kx * Cin + ci;
+          else k = (size_t)(ky * ksize + kx) * Cin + ci;
+          wc[(size_t)co * K + k] = v;
+        }
+  }
+  std::vector<float> wp(conv_tc_packed_floats(Cout_pad, K));
+  conv_tc_pack_weights(wc.data(), Cout_pad, K, wp.data());
+  const size_t n_in = (size_t)B * H * W * Cin, n_out = (size_t)B * Ho * Wo * Cout;
+  CtxExtra* x = X(ctx);
+  rc = x->io.grow(ctx, (n_in + 2 * n_out + wc.size() + wp.size() + bc.size() + 2 * (size_t)Cin) * sizeof(float) + 8192);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  float* d_in = bp.take<float>(n_in);
+  float* d_out = bp.take<float>(n_out);
+  float* d_res = residual ? bp.take<float>(n_out) : nullptr;
+  float* d_w = bp.take<float>(wc.size());
+  float* d_wp = bp.take<float>(wp.size());
+  float* d_b = bp.take<float>(bc.size());
+  float* d_ps = pre_scale ? bp.take<float>(Cin) : nullptr;
+  float* d_pt = pre_scale ? bp.take<float>(Cin) : nullptr;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, n_in * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (d_res) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_res, residual, n_out * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_w, wc.data(), wc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_b, bc.data(), bc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (d_ps) {
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_ps, pre_scale, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_pt, pre_shift, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, n_out * sizeof(float), s));
+  p.in = d_in; p.w = d_w; p.w_packed = d_wp; p.bias = d_b; p.pre_scale = d_ps; p.pre_shift = d_pt; p.residual = d_res;
+  p.out = d_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cout_pad = Cout_pad;
+  p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
+  rc = backend == 1 ? launch_conv_tc(ctx, p, tf32_passes, s) : launch_conv_simt(ctx, p, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                int L, const float* priors, float* uv, float* cov, float* logits, float* prob, float* mask_logits,
+                float* mask, int32_t* argmax, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!x->loaded) { ctx->set_error("suo_forward before suo_load_weights", __FILE__, __LINE__); return SUO_E_STATE; }
+  if (L <= 0 || L > ctx->max_crops || n_img <= 0 || !images || !boxes || !box_img) {
+    ctx->set_error("suo_forward: bad crop count / null input", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NetState& N = x->net;
+  const int R = ctx->crop_res, K = ctx->num_kp, HM = R / N.h.heat_div;
+  const int variant = priors ? 1 : 0;
+  const int in_buf = priors ? N.h.in_buf_prior : N.h.in_buf_noprior;
+  const size_t n_im = (size_t)n_img * 3 * H * W, n_pr = priors ? (size_t)L * K * R * R : 0;
+  const size_t n_hm = (size_t)L * K * HM * HM, LK = (size_t)L * K;
+  const float *d_im = images, *d_box = boxes, *d_pr = priors;
+  const int32_t* d_bi = box_img;
+  float* d_prob = prob;
+  if (!on_device) {
+    rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0)) * sizeof(float) + 4096);
+    if (rc) return rc;
+    Bump bp{static_cast<uint8_t*>(x->io.d)};
+    float* a = bp.take<float>(n_im);
+    float* b = bp.take<float>(4 * (size_t)L);
+    int32_t* c = bp.take<int32_t>(L);
+    float* d = priors ? bp.take<float>(n_pr) : nullptr;
+    d_prob = prob ? bp.take<float>(n_hm) : nullptr;
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(a, images, n_im * sizeof(float), cudaMemcpyHostToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b, boxes, 4 * (size_t)L * sizeof(float), cudaMemcpyHostToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(c, box_img, L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (d) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d, priors, n_pr * sizeof(float), cudaMemcpyHostToDevice, s));
+    d_im = a; d_box = b; d_bi = c; d_pr = d;
+  }
+  rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
+  if (rc) return rc;
+  rc = run_network(ctx, L, variant, s);
+  if (rc) return rc;
+  const float* d_logits = N.act[N.h.logits_buf];
+  if (on_device) {
+    rc = launch_heatmap_reduce(ctx, d_logits, L, K, HM, HM, N.pool + N.h.cls_w_off, N.pool + N.h.cls_b_off, N.pooled, uv, cov,
+                               d_prob, mask_logits, mask, argmax, s);
+    if (rc) return rc;
+    if (logits) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(logits, d_logits, n_hm * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return SUO_OK;
+  }
+  rc = launch_heatmap_reduce(ctx, d_logits, L, K, HM, HM, N.pool + N.h.cls_w_off, N.pool + N.h.cls_b_off, N.pooled, N.d_uv,
+                             N.d_cov, d_prob, N.d_mask_logits, N.d_mask, N.d_argmax, s);
+  if (rc) return rc;
+  if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(uv, N.d_uv, LK * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(cov, N.d_cov, LK * 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (mask) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(mask, N.d_mask, LK * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (mask_logits) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(mask_logits, N.d_mask_logits, LK * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (argmax) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(argmax, N.d_argmax, LK * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (logits) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(logits, d_logits, n_hm * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (prob) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(prob, d_prob, n_hm * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj, double threshold,
+                  uint64_t seed, const uint64_t* obj_keys, double* T_out, int32_t* stats, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (n_obj <= 0 || !xs || !ys || !offsets || !T_out) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (on_device) return launch_pnp_batch(ctx, xs, ys, offsets, n_obj, threshold, seed, obj_keys, T_out, stats, s);
+  const int N = offsets[n_obj];
+  for (int o = 0; o < n_obj; ++o)
+    if (offsets[o + 1] - offsets[o] > 64 || offsets[o + 1] < offsets[o]) {
+      ctx->set_error("suo_pnp_batch: at most 64 points per object", __FILE__, __LINE__);
+      return SUO_E_INVALID;
+    }
+  CtxExtra* x = X(ctx);
+  rc = x->io.grow(ctx, (size_t)N * 5 * 8 + (size_t)n_obj * (16 * 8 + 5 * 4 + 8 + 4) + 8192);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  double* d_xs = bp.take<double>(3 * (size_t)N);
+  double* d_ys = bp.take<double>(2 * (size_t)N);
+  int32_t* d_off = bp.take<int32_t>(n_obj + 1);
+  uint64_t* d_keys = obj_keys ? bp.take<uint64_t>(n_obj) : nullptr;
+  double* d_T = bp.take<double>(16 * (size_t)n_obj);
+  int32_t* d_st = bp.take<int32_t>(5 * (size_t)n_obj);
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_xs, xs, 3 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_ys, ys, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (n_obj + 1) * 4, cudaMemcpyHostToDevice, s));
+  if (d_keys) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, obj_keys, n_obj * 8, cudaMemcpyHostToDevice, s));
+  rc = launch_pnp_batch(ctx, d_xs, d_ys, d_off, n_obj, threshold, seed, d_keys, d_T, d_st, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(T_out, d_T, 16 * (size_t)n_obj * 8, cudaMemcpyDeviceToHost, s));
+  if (stats) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(stats, d_st, 5 * (size_t)n_obj * 4, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, double* poses,
+                 const uint8_t* fixed, int n_vert, const int32_t* e_obj, const int32_t* e_cam, const double* cam_k,
+                 const double* p, const double* uv, const double* info, uint8_t* inliers, int n_edges,
+                 const int32_t* its, int n_rounds, double huber_delta, double chi2_gate, int init_with_outliers,
+                 int32_t* stats, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (n_prob <= 0 || n_vert <= 0 || n_edges < 0 || n_rounds <= 0 || n_rounds > 16) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CtxExtra* x = X(ctx);
+  const size_t scratch = align_up((size_t)n_edges * 16, 256) + align_up(n_edges, 256) * 2 + 1024;
+  rc = x->ba.grow(ctx, scratch);
+  if (rc) return rc;
+  Bump sb{static_cast<uint8_t*>(x->ba.d)};
+  double* d_err = sb.take<double>(2 * (size_t)n_edges);
+  uint8_t* d_level = sb.take<uint8_t>(n_edges);
+  int8_t* d_fv = sb.take<int8_t>(n_edges);
+  if (on_device) {
+    return launch_ba_batch_scratch(ctx, n_prob, prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers,
+                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s);
+  }
+  // host-side validation (the kernel reports the same conditions through stats)
+  for (int pr = 0; pr < n_prob; ++pr) {
+    if (prob_vert[pr + 1] - prob_vert[pr] > 64) { ctx->set_error("suo_ba_batch: > 64 vertices in one problem", __FILE__, __LINE__); return SUO_E_INVALID; }
+    for (int e = prob_edge[pr]; e < prob_edge[pr + 1]; ++e) {
+      const bool fo = e_obj[e] >= 0 && !fixed[e_obj[e]], fc = !fixed[e_cam[e]];
+      if (fo && fc) { ctx->set_error("suo_ba_batch: edge with free camera AND free object (global graph, SURVEY f3) not supported", __FILE__, __LINE__); return SUO_E_INVALID; }
+      if (e_cam[e] < prob_vert[pr] || e_cam[e] >= prob_vert[pr + 1] || (e_obj[e] >= 0 && (e_obj[e] < prob_vert[pr] || e_obj[e] >= prob_vert[pr + 1]))) {
+        ctx->set_error("suo_ba_batch: edge references a vertex outside its problem", __FILE__, __LINE__); return SUO_E_INVALID;
+      }
+    }
+  }
+  rc = x->io.grow(ctx, (size_t)n_vert * (12 * 8 + 1) + (size_t)n_edges * (4 + 4 + (4 + 3 + 2 + 4) * 8 + 1) + (size_t)n_prob * (8 + 12) + 16 * 4 + 16384);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  int32_t* d_pv = bp.take<int32_t>(n_prob + 1);
+  int32_t* d_pe = bp.take<int32_t>(n_prob + 1);
+  double* d_poses = bp.take<double>(12 * (size_t)n_vert);
+  uint8_t* d_fixed = bp.take<uint8_t>(n_vert);
+  int32_t* d_eo = bp.take<int32_t>(n_edges);
+  int32_t* d_ec = bp.take<int32_t>(n_edges);
+  double* d_k = bp.take<double>(4 * (size_t)n_edges);
+  double* d_p = bp.take<double>(3 * (size_t)n_edges);
+  double* d_uv = bp.take<double>(2 * (size_t)n_edges);
+  double* d_info = bp.take<double>(4 * (size_t)n_edges);
+  uint8_t* d_inl = bp.take<uint8_t>(n_edges);
+  int32_t* d_its = bp.take<int32_t>(n_rounds);
+  int32_t* d_st = bp.take<int32_t>(3 * (size_t)n_prob);
+#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+  H2D(d_pv, prob_vert, (n_prob + 1) * 4); H2D(d_pe, prob_edge, (n_prob + 1) * 4);
+  H2D(d_poses, poses, 12 * (size_t)n_vert * 8); H2D(d_fixed, fixed, n_vert);
+  H2D(d_eo, e_obj, (size_t)n_edges * 4); H2D(d_ec, e_cam, (size_t)n_edges * 4);
+  H2D(d_k, cam_k, 4 * (size_t)n_edges * 8); H2D(d_p, p, 3 * (size_t)n_edges * 8);
+  H2D(d_uv, uv, 2 * (size_t)n_edges * 8); H2D(d_info, info, 4 * (size_t)n_edges * 8);
+  H2D(d_inl, inliers, n_edges); H2D(d_its, its, n_rounds * 4);
+#undef H2D
+  rc = launch_ba_batch_scratch(ctx, n_prob, d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its,
+                               n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(poses, d_poses, 12 * (size_t)n_vert * 8, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(inliers, d_inl, n_edges, cudaMemcpyDeviceToHost, s));
+  if (stats) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(stats, d_st, 3 * (size_t)n_prob * 4, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+// Device-resident part after the network: gating -> PnP -> single-view BA.  All pointers are device
+// pointers; d_uv/d_cov/d_mask are the network outputs (or caller-provided keypoints).
+static int solve_keypoints_device(suo_ctx* ctx, Bump& bp, const float* d_uv, const float* d_cov, const float* d_mask,
+                                  const int32_t* d_bi, int n_img, int L, const double* d_mk, const uint8_t* d_mm,
+                                  const double* d_kb, const double* d_diam, double kp_var_thresh, double bbox_thresh,
+                                  uint64_t seed, int run_ba, double* d_Tpnp, double* d_Tba, uint8_t* d_used,
+                                  uint8_t* d_bain, cudaStream_t s) {
+  const int K = ctx->num_kp;
+  const size_t LK = (size_t)L * K, NV = (size_t)L + n_img;
+  double* d_xs = bp.take<double>(3 * LK); double* d_ys = bp.take<double>(2 * LK);
+  int32_t* d_cnt = bp.take<int32_t>(L); int32_t* d_kpi = bp.take<int32_t>(LK);
+  int32_t* d_pst = bp.take<int32_t>(5 * (size_t)L);
+  int32_t* d_fs = bp.take<int32_t>(n_img + 1);
+  int rc = launch_gate_compact(ctx, d_uv, d_cov, d_mask, d_mm, d_mk, d_kb, L, K, (float)kp_var_thresh, (float)bbox_thresh, d_xs,
+                               d_ys, d_cnt, d_kpi, d_used, s);
+  if (rc) return rc;
+  // PnP: object c owns rows [c*K, c*K + count[c])
+  int32_t* d_off = bp.take<int32_t>(L);
+  {
+    std::vector<int32_t> off(L);
+    for (int c = 0; c < L; ++c) off[c] = c * K;
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, off.data(), L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // `off` goes out of scope
+  }
+  rc = launch_pnp_batch_counts(ctx, d_xs, d_ys, d_off, d_cnt, L, 0.001, seed, nullptr, d_Tpnp, d_pst, s);
+  if (rc) return rc;
+  if (!run_ba) return SUO_OK;
+  rc = launch_frame_ranges(ctx, d_bi, L, n_img, d_fs, s);
+  if (rc) return rc;
+  double* d_poses = bp.take<double>(12 * NV); uint8_t* d_fixed = bp.take<uint8_t>(NV);
+  int32_t* d_pv = bp.take<int32_t>(n_img); int32_t* d_vc = bp.take<int32_t>(n_img);
+  int32_t* d_pe = bp.take<int32_t>(n_img); int32_t* d_ecnt = bp.take<int32_t>(n_img);
+  int32_t* d_eo = bp.take<int32_t>(LK); int32_t* d_ec = bp.take<int32_t>(LK);
+  double* d_ck = bp.take<double>(4 * LK); double* d_p = bp.take<double>(3 * LK); double* d_uvd = bp.take<double>(2 * LK);
+  double* d_info = bp.take<double>(4 * LK); uint8_t* d_inl = bp.take<uint8_t>(LK); int32_t* d_esrc = bp.take<int32_t>(LK);
+  uint8_t* d_acc = bp.take<uint8_t>(L);
+  double* d_err = bp.take<double>(2 * LK); uint8_t* d_lvl = bp.take<uint8_t>(LK); int8_t* d_fv = bp.take<int8_t>(LK);
+  int32_t* d_its = bp.take<int32_t>(4); int32_t* d_bst = bp.take<int32_t>(3 * (size_t)n_img);
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_fixed, 0, NV, s));
+  rc = launch_ba_assemble(ctx, n_img, d_fs, d_cnt, d_kpi, d_xs, d_uv, d_cov, d_kb, d_diam, d_Tpnp, K, d_poses, d_fixed, d_pv,
+                          d_vc, d_pe, d_ecnt, d_eo, d_ec, d_ck, d_p, d_uvd, d_info, d_inl, d_esrc, d_acc, s);
+  if (rc) return rc;
+  static const int32_t its_host[4] = {10, 10, 10, 10};   // single-view mode (object_slam.py:843-846)
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_its, its_host, sizeof(its_host), cudaMemcpyHostToDevice, s));
+  rc = launch_ba_batch_scratch(ctx, n_img, d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_ck, d_p, d_uvd, d_info, d_inl, d_its, 4,
+                               2.4476519768340177 /* sqrt(5.991) */, 5.991, 0, d_bst, d_err, d_lvl, d_fv, s, d_vc, d_ecnt);
+  if (rc) return rc;
+  return launch_ba_scatter(ctx, n_img, d_fs, d_ecnt, d_esrc, d_inl, d_poses, d_acc, K, d_Tba, d_bain, s);
+}
+
+static size_t solve_workspace_bytes(int L, int K, int n_img) {
+  const size_t LK = (size_t)L * K, NV = (size_t)L + n_img;
+  return 64 * 256 + LK * (3 + 2 + 4 + 3 + 2 + 4 + 2 + 3) * 8 + LK * (4 + 4 + 4 + 4 + 8) + (size_t)L * (16 * 8 + 5 * 4 + 4 * 3 + 1 + 9 * 8 + 8 + 12 * 8) +
+         NV * (12 * 8 + 1) + (size_t)n_img * (4 * 6 + 12) + 4096;
+}
+
+int suo_solve_keypoints(suo_ctx* ctx, const float* uv, const float* cov, const float* kp_mask, const int32_t* box_img,
+                        int n_img, int L, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                        const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+                        double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (L <= 0 || n_img <= 0 || !uv || !cov || !kp_mask || !box_img || !model_kps || !model_mask || !K_bbox || !diameter) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CtxExtra* x = X(ctx);
+  const int K = ctx->num_kp;
+  const size_t LK = (size_t)L * K;
+  rc = x->fr.grow(ctx, solve_workspace_bytes(L, K, n_img) + LK * 64);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->fr.d)};
+  const float *d_uv = uv, *d_cov = cov, *d_km = kp_mask;
+  const int32_t* d_bi = box_img;
+  const double *d_mk = model_kps, *d_kb = K_bbox, *d_diam = diameter;
+  const uint8_t* d_mm = model_mask;
+  if (!on_device) {
+    for (int c = 1; c < L; ++c) if (box_img[c] < box_img[c - 1]) { ctx->set_error("box_img must be sorted", __FILE__, __LINE__); return SUO_E_INVALID; }
+    float* a = bp.take<float>(2 * LK); float* b = bp.take<float>(4 * LK); float* c = bp.take<float>(LK); int32_t* d = bp.take<int32_t>(L);
+    double* e = bp.take<double>(3 * LK); uint8_t* f = bp.take<uint8_t>(LK); double* g = bp.take<double>(9 * (size_t)L); double* h = bp.take<double>(L);
+#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+    H2D(a, uv, 8 * LK); H2D(b, cov, 16 * LK); H2D(c, kp_mask, 4 * LK); H2D(d, box_img, 4 * (size_t)L);
+    H2D(e, model_kps, 24 * LK); H2D(f, model_mask, LK); H2D(g, K_bbox, 72 * (size_t)L); H2D(h, diameter, 8 * (size_t)L);
+#undef H2D
+    d_uv = a; d_cov = b; d_km = c; d_bi = d; d_mk = e; d_mm = f; d_kb = g; d_diam = h;
+  }
+  double* d_Tpnp = (on_device && T_pnp) ? T_pnp : bp.take<double>(16 * (size_t)L);
+  double* d_Tba = (on_device && T_ba) ? T_ba : bp.take<double>(12 * (size_t)L);
+  uint8_t* d_used = (on_device && kp_used) ? kp_used : bp.take<uint8_t>(LK);
+  uint8_t* d_bain = (on_device && ba_inliers) ? ba_inliers : bp.take<uint8_t>(LK);
+  rc = solve_keypoints_device(ctx, bp, d_uv, d_cov, d_km, d_bi, n_img, L, d_mk, d_mm, d_kb, d_diam, kp_var_thresh, bbox_thresh, seed,
+                              run_ba, d_Tpnp, d_Tba, d_used, d_bain, s);
+  if (rc || on_device) return rc;
+#define D2H(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, s))
+  D2H(T_pnp, d_Tpnp, 128 * (size_t)L); D2H(kp_used, d_used, LK);
+  if (run_ba) { D2H(T_ba, d_Tba, 96 * (size_t)L); D2H(ba_inliers, d_bain, LK); }
+#undef D2H
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+               int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+               const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+               double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
+               int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!x->loaded) { ctx->set_error("suo_frames before suo_load_weights", __FILE__, __LINE__); return SUO_E_STATE; }
+  if (L <= 0 || L > ctx->max_crops || n_img <= 0 || !images || !boxes || !box_img || !model_kps || !model_mask || !K_bbox || !diameter) {
+    ctx->set_error("suo_frames: bad crop count / null input", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NetState& N = x->net;
+  const int K = ctx->num_kp, R = ctx->crop_res;
+  const size_t LK = (size_t)L * K, n_im = (size_t)n_img * 3 * H * W, n_pr = priors ? LK * R * R : 0;
+  size_t bytes = solve_workspace_bytes(L, K, n_img) + LK * 64;
+  if (!on_device) bytes += (n_im + n_pr) * sizeof(float) + 4096;
+  rc = x->fr.grow(ctx, bytes);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->fr.d)};
+  const float *d_im = images, *d_box = boxes, *d_pr = priors;
+  const int32_t* d_bi = box_img;
+  const double *d_mk = model_kps, *d_kb = K_bbox, *d_diam = diameter;
+  const uint8_t* d_mm = model_mask;
+  if (!on_device) {
+    for (int c = 1; c < L; ++c) if (box_img[c] < box_img[c - 1]) { ctx->set_error("suo_frames: box_img must be sorted", __FILE__, __LINE__); return SUO_E_INVALID; }
+    float* a = bp.take<float>(n_im); float* b = bp.take<float>(4 * (size_t)L); int32_t* c = bp.take<int32_t>(L);
+    float* d = priors ? bp.take<float>(n_pr) : nullptr;
+    double* e = bp.take<double>(3 * LK); uint8_t* f = bp.take<uint8_t>(LK); double* g = bp.take<double>(9 * (size_t)L); double* h = bp.take<double>(L);
+#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+    H2D(a, images, n_im * 4); H2D(b, boxes, 16 * (size_t)L); H2D(c, box_img, 4 * (size_t)L);
+    if (d) H2D(d, priors, n_pr * 4);
+    H2D(e, model_kps, 24 * LK); H2D(f, model_mask, LK); H2D(g, K_bbox, 72 * (size_t)L); H2D(h, diameter, 8 * (size_t)L);
+#undef H2D
+    d_im = a; d_box = b; d_bi = c; d_pr = d; d_mk = e; d_mm = f; d_kb = g; d_diam = h;
+  }
+  // forward (device path): results land in the executor's own uv / cov / mask buffers
+  rc = suo_forward(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, N.d_uv, N.d_cov, nullptr, nullptr, N.d_mask_logits, N.d_mask,
+                   N.d_argmax, 1, stream);
+  if (rc) return rc;
+  double* d_Tpnp = (on_device && T_pnp) ? T_pnp : bp.take<double>(16 * (size_t)L);
+  double* d_Tba = (on_device && T_ba) ? T_ba : bp.take<double>(12 * (size_t)L);
+  uint8_t* d_used = (on_device && kp_used) ? kp_used : bp.take<uint8_t>(LK);
+  uint8_t* d_bain = (on_device && ba_inliers) ? ba_inliers : bp.take<uint8_t>(LK);
+  rc = solve_keypoints_device(ctx, bp, N.d_uv, N.d_cov, N.d_mask, d_bi, n_img, L, d_mk, d_mm, d_kb, d_diam, kp_var_thresh,
+                              bbox_thresh, seed, run_ba, d_Tpnp, d_Tba, d_used, d_bain, s);
+  if (rc) return rc;
+  if (on_device) {
+    if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(uv, N.d_uv, LK * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(cov, N.d_cov, LK * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return SUO_OK;
+  }
+#define D2H(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, s))
+  D2H(T_pnp, d_Tpnp, 128 * (size_t)L); D2H(kp_used, d_used, LK);
+  D2H(uv, N.d_uv, LK * 8); D2H(cov, N.d_cov, LK * 16);
+  if (run_ba) { D2H(T_ba, d_Tba, 96 * (size_t)L); D2H(ba_inliers, d_bain, LK); }
+#undef D2H
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+}  // extern "C"

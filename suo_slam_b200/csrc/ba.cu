@@ -1,0 +1,437 @@
+// Batched Levenberg-Marquardt object-pose bundle adjustment, FP64.
+//
+// Replaces, for a BATCH of independent graphs in one launch, what the reference does through
+// thousands of pybind calls per frame in ObjectSLAM.optimize() (lib/object_slam.py:842-896):
+//   * EdgeSE3ProjectFromObject / EdgeSE3ProjectFromFixedObject computeError + linearizeOplus
+//     (thirdparty/g2opy/g2o/types/object_slam/types_object_slam.cpp:45-60,70-123,156-169,177-201)
+//   * BaseBinaryEdge/BaseUnaryEdge::constructQuadraticForm with RobustKernelHuber
+//     (g2o/core/base_binary_edge.hpp:64-127, base_unary_edge.hpp:52-78, robust_kernel_impl.cpp:65-78)
+//   * OptimizationAlgorithmLevenberg::solve (g2o/core/optimization_algorithm_levenberg.cpp:58-175):
+//     lambda0 = 1e-5 max diag(H); (H + lambda I) dx = b; T <- exp(dx) T; rho test with one lambda and
+//     one accept/reject per graph; <= 10 trials per iteration
+//   * VertexSE3Expmap::oplusImpl / SE3Quat::exp (types/sba/types_six_dof_expmap.h:100-103,
+//     types/slam3d/se3quat.h:220-254) and the dense LDLT solve (solvers/dense/linear_solver_dense.h:65-113)
+//   * the 4-round chi2 re-classification / Huber-stripping schedule of optimize() itself.
+//
+// One CTA per graph; the graph's vertex states, 6x6 Hessian blocks and LM scalars live in shared
+// memory; edges are streamed from global memory.  Every edge has exactly one free vertex here
+// (single-view mode: camera fixed; curr_only: objects folded into p_inG), so H is block-diagonal.
+// Hessian blocks are accumulated by one warp per vertex in a fixed order (lane-strided partial sums
+// + shuffle tree): results are deterministic run to run, as the reference insists on
+// (lib/object_slam.py:440-442).  Latency / FP64-issue bound; no bandwidth claim.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BA_THREADS = 128;
+constexpr int BA_WARPS = BA_THREADS / 32;
+constexpr int BA_MAXV = 64;     // vertices per graph held in shared memory
+
+struct SE3q { double qx, qy, qz, qw, t[3]; };
+
+__device__ void se3_from_Rt(const double* R, const double* t, SE3q& o) {   // Eigen::Quaterniond(R) + normalizeRotation (se3quat.h:55-57,277-282)
+  double q[4];
+  const double tr = R[0] + R[4] + R[8];
+  if (tr > 0) {
+    double s = sqrt(tr + 1.0);
+    q[3] = 0.5 * s; s = 0.5 / s;
+    q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double s = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+    q[i] = 0.5 * s; s = 0.5 / s;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * s; q[j] = (R[3 * j + i] + R[3 * i + j]) * s; q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+  }
+  if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  o.qx = q[0] / n; o.qy = q[1] / n; o.qz = q[2] / n; o.qw = q[3] / n;
+  o.t[0] = t[0]; o.t[1] = t[1]; o.t[2] = t[2];
+}
+__device__ __forceinline__ void se3_R(const SE3q& T, double* R) {          // Eigen toRotationMatrix
+  const double tx = 2 * T.qx, ty = 2 * T.qy, tz = 2 * T.qz;
+  const double twx = tx * T.qw, twy = ty * T.qw, twz = tz * T.qw;
+  const double txx = tx * T.qx, txy = ty * T.qx, txz = tz * T.qx, tyy = ty * T.qy, tyz = tz * T.qy, tzz = tz * T.qz;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ __forceinline__ void se3_map(const SE3q& T, const double* p, double* o) {
+  double R[9];
+  se3_R(T, R);
+  o[0] = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + T.t[0];
+  o[1] = R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + T.t[1];
+  o[2] = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + T.t[2];
+}
+__device__ void se3_oplus(const SE3q& T, const double* u, SE3q& out) {     // exp(u) * T
+  const double theta = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  const double Om[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
+  double Om2[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Om2[3 * i + j] = Om[3 * i] * Om[j] + Om[3 * i + 1] * Om[3 + j] + Om[3 * i + 2] * Om[6 + j];
+  double R[9], V[9];
+  if (theta < 0.00001) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
+  } else {
+    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const double I = (i % 4 == 0 ? 1.0 : 0.0); R[i] = I + a * Om[i] + b * Om2[i]; V[i] = I + b * Om[i] + c * Om2[i]; }
+  }
+  const double td[3] = {V[0] * u[3] + V[1] * u[4] + V[2] * u[5], V[3] * u[3] + V[4] * u[4] + V[5] * u[5], V[6] * u[3] + V[7] * u[4] + V[8] * u[5]};
+  SE3q E;
+  se3_from_Rt(R, td, E);
+  double RE[9];
+  se3_R(E, RE);
+  out.t[0] = E.t[0] + RE[0] * T.t[0] + RE[1] * T.t[1] + RE[2] * T.t[2];
+  out.t[1] = E.t[1] + RE[3] * T.t[0] + RE[4] * T.t[1] + RE[5] * T.t[2];
+  out.t[2] = E.t[2] + RE[6] * T.t[0] + RE[7] * T.t[1] + RE[8] * T.t[2];
+  double w = E.qw * T.qw - E.qx * T.qx - E.qy * T.qy - E.qz * T.qz;
+  double x = E.qw * T.qx + E.qx * T.qw + E.qy * T.qz - E.qz * T.qy;
+  double y = E.qw * T.qy - E.qx * T.qz + E.qy * T.qw + E.qz * T.qx;
+  double z = E.qw * T.qz + E.qx * T.qy - E.qy * T.qx + E.qz * T.qw;
+  if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
+  const double n = sqrt(x * x + y * y + z * z + w * w);
+  out.qx = x / n; out.qy = y / n; out.qz = z / n; out.qw = w / n;
+}
+
+__device__ __forceinline__ void huber(double e, double delta, double& rho0, double& rho1) {
+  const double dsqr = delta * delta;
+  if (e <= dsqr) { rho0 = e; rho1 = 1.0; }
+  else { const double sq = sqrt(e); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
+}
+
+__device__ bool chol6(double* A, double* b) {   // in place, row-major lower
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j * 6 + j];
+    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
+    if (!(d > 0) || !isfinite(d)) return false;
+    d = sqrt(d);
+    A[j * 6 + j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double s = A[i * 6 + j];
+      for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = s / d;
+    }
+  }
+  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * b[k]; b[i] = s / A[i * 6 + i]; }
+  for (int i = 5; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * b[k]; b[i] = s / A[i * 6 + i]; }
+  return true;
+}
+
+struct BaArgs {
+  const int32_t* prob_vert; const int32_t* prob_edge;
+  const int32_t* vert_cnt; const int32_t* edge_cnt;   // optional explicit counts (else next offset - offset)
+  double* poses; const uint8_t* fixed;
+  const int32_t* e_obj; const int32_t* e_cam;
+  const double* cam_k; const double* p; const double* uv; const double* info;
+  uint8_t* inliers;
+  const int32_t* its; int n_rounds;
+  double huber_delta, chi2_gate; int init_with_outliers;
+  int32_t* stats;
+  double* err;        // scratch [n_edges,2]: the edge's _error as last computed (g2o keeps it in the edge)
+  uint8_t* level;     // scratch [n_edges]
+  int8_t* fv_kind;    // scratch [n_edges]: 0 = free vertex is the object, 1 = the camera, -1 = none / invalid
+};
+
+__device__ double block_sum_d(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0;
+#pragma unroll
+  for (int w = 0; w < BA_WARPS; ++w) r += sh[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(BA_THREADS)
+ba_kernel(const BaArgs a) {
+  __shared__ SE3q est[BA_MAXV], bak[BA_MAXV];
+  __shared__ double Hs[BA_MAXV][36], bs[BA_MAXV][6], xsol[BA_MAXV][6];
+  __shared__ uint8_t vact[BA_MAXV], vok[BA_MAXV];
+  __shared__ double red[BA_WARPS];
+  __shared__ double s_lambda, s_ni, s_cur, s_rho;
+  __shared__ int s_flag, s_bad;
+
+  const int prob = blockIdx.x;
+  const int v0 = a.prob_vert[prob], nv = a.vert_cnt ? a.vert_cnt[prob] : a.prob_vert[prob + 1] - v0;
+  const int e0 = a.prob_edge[prob], ne = a.edge_cnt ? a.edge_cnt[prob] : a.prob_edge[prob + 1] - e0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  if (nv > BA_MAXV) { if (tid == 0 && a.stats) { a.stats[3 * prob] = -1; a.stats[3 * prob + 1] = 0; a.stats[3 * prob + 2] = 0; } return; }
+
+  for (int v = tid; v < nv; v += BA_THREADS) {
+    const double* T = a.poses + 12 * (size_t)(v0 + v);
+    const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+    const double t[3] = {T[3], T[7], T[11]};
+    se3_from_Rt(R, t, est[v]);
+  }
+  // which vertex of each edge is free
+  for (int e = tid; e < ne; e += BA_THREADS) {
+    const int ge = e0 + e;
+    const int vo = a.e_obj[ge], vc = a.e_cam[ge];
+    const bool fo = vo >= 0 && !a.fixed[vo], fc = !a.fixed[vc];
+    int8_t k = -1;
+    if (fo && fc) { k = -1; atomicExch(&s_bad, 1); }      // coupled camera+object graph: SURVEY §8 f3, not handled here
+    else if (fo) k = 0;
+    else if (fc) k = 1;
+    a.fv_kind[ge] = k;
+  }
+  __syncthreads();
+  if (s_bad) { if (tid == 0 && a.stats) { a.stats[3 * prob] = -2; a.stats[3 * prob + 1] = 0; a.stats[3 * prob + 2] = 0; } return; }
+
+  auto edge_error = [&](int ge) {   // computeError
+    double pw[3] = {a.p[3 * ge], a.p[3 * ge + 1], a.p[3 * ge + 2]}, pc[3];
+    if (a.e_obj[ge] >= 0) { double tmp[3]; se3_map(est[a.e_obj[ge] - v0], pw, tmp); pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; }
+    se3_map(est[a.e_cam[ge] - v0], pw, pc);
+    const double* k = a.cam_k + 4 * ge;
+    a.err[2 * ge] = a.uv[2 * ge] - (k[0] * pc[0] / pc[2] + k[2]);
+    a.err[2 * ge + 1] = a.uv[2 * ge + 1] - (k[1] * pc[1] / pc[2] + k[3]);
+  };
+  auto edge_chi2 = [&](int ge) {
+    const double* O = a.info + 4 * ge;
+    const double r0 = a.err[2 * ge], r1 = a.err[2 * ge + 1];
+    return r0 * (O[0] * r0 + O[1] * r1) + r1 * (O[2] * r0 + O[3] * r1);
+  };
+  // active = level 0 and has a free vertex (edges whose vertices are all fixed are dropped by
+  // SparseOptimizer::initializeOptimization)
+  auto is_active = [&](int ge) { return a.level[ge] == 0 && a.fv_kind[ge] >= 0; };
+
+  // ---- initial chi2 classification (object_slam.py:848-866) ----
+  int my_good = 0;
+  for (int e = tid; e < ne; e += BA_THREADS) {
+    const int ge = e0 + e;
+    if (a.init_with_outliers) { a.level[ge] = 0; my_good++; }
+    else {
+      edge_error(ge);
+      if (edge_chi2(ge) > a.chi2_gate) { a.level[ge] = 1; a.inliers[ge] = 0; }
+      else { a.level[ge] = 0; a.inliers[ge] = 1; my_good++; }
+    }
+  }
+  int num_good = (int)(block_sum_d((double)my_good, red) + 0.5);
+  int robust = 1;
+  int rounds = 0, outer_total = 0, trials_total = 0;
+
+  for (int round = 0; round < a.n_rounds; ++round) {
+    if (ne < 4 || num_good < 4) break;
+    // ---------------- initializeOptimization(0) ----------------
+    for (int v = tid; v < nv; v += BA_THREADS) vact[v] = 0;
+    __syncthreads();
+    for (int e = tid; e < ne; e += BA_THREADS) {
+      const int ge = e0 + e;
+      if (is_active(ge)) vact[(a.fv_kind[ge] == 0 ? a.e_obj[ge] : a.e_cam[ge]) - v0] = 1;   // benign race: all write 1
+    }
+    __syncthreads();
+    int any = 0;
+    for (int v = 0; v < nv; ++v) any |= vact[v];
+    ++rounds;
+    if (any) {
+      // ---------------- optimize(its[round]) ----------------
+      bool ok = true;
+      const int iters = a.its[round];
+      for (int it = 0; it < iters && ok; ++it) {
+        // computeActiveErrors + activeRobustChi2
+        double part = 0;
+        for (int e = tid; e < ne; e += BA_THREADS) {
+          const int ge = e0 + e;
+          if (!is_active(ge)) continue;
+          edge_error(ge);
+          const double c = edge_chi2(ge);
+          if (robust) { double r0, r1; huber(c, a.huber_delta, r0, r1); part += r0; } else part += c;
+        }
+        const double currentChi0 = block_sum_d(part, red);
+        // buildSystem: one warp per vertex, fixed summation order
+        for (int v = warp; v < nv; v += BA_WARPS) {
+          double acc[27];
+#pragma unroll
+          for (int k = 0; k < 27; ++k) acc[k] = 0;
+          if (vact[v]) {
+            for (int e = lane; e < ne; e += 32) {
+              const int ge = e0 + e;
+              if (!is_active(ge)) continue;
+              const int fvert = (a.fv_kind[ge] == 0 ? a.e_obj[ge] : a.e_cam[ge]) - v0;
+              if (fvert != v) continue;
+              // linearizeOplus
+              double pw[3] = {a.p[3 * ge], a.p[3 * ge + 1], a.p[3 * ge + 2]}, pc[3];
+              if (a.e_obj[ge] >= 0) { double tmp[3]; se3_map(est[a.e_obj[ge] - v0], pw, tmp); pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; }
+              const SE3q& Tcw = est[a.e_cam[ge] - v0];
+              se3_map(Tcw, pw, pc);
+              const double* k = a.cam_k + 4 * ge;
+              const double iz = 1.0 / pc[2];
+              double pj[6] = {-(k[0] * iz), 0.0, k[0] * pc[0] * iz * iz, 0.0, -(k[1] * iz), k[1] * pc[1] * iz * iz};
+              double J[12];
+              const double* q = pc;
+              if (a.fv_kind[ge] == 0) {   // Jacobian wrt the object: projectJac * R_cw * [-[p_W]x | I]
+                double Rcw[9];
+                se3_R(Tcw, Rcw);
+                double pr[6];
+#pragma unroll
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                  for (int c = 0; c < 3; ++c) pr[3 * r + c] = pj[3 * r] * Rcw[c] + pj[3 * r + 1] * Rcw[3 + c] + pj[3 * r + 2] * Rcw[6 + c];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pj[c] = pr[c];
+                q = pw;
+              }
+              // [ -[q]x | I ] = [[0, z, -y, 1,0,0],[-z, 0, x, 0,1,0],[y, -x, 0, 0,0,1]]
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const double p0 = pj[3 * r], p1 = pj[3 * r + 1], p2 = pj[3 * r + 2];
+                J[6 * r + 0] = -p1 * q[2] + p2 * q[1];
+                J[6 * r + 1] = p0 * q[2] - p2 * q[0];
+                J[6 * r + 2] = -p0 * q[1] + p1 * q[0];
+                J[6 * r + 3] = p0; J[6 * r + 4] = p1; J[6 * r + 5] = p2;
+              }
+              const double* O = a.info + 4 * ge;
+              const double r0 = a.err[2 * ge], r1 = a.err[2 * ge + 1];
+              double w = 1.0;
+              if (robust) { double h0; huber(r0 * (O[0] * r0 + O[1] * r1) + r1 * (O[2] * r0 + O[3] * r1), a.huber_delta, h0, w); }
+              const double or0 = -(O[0] * r0 + O[1] * r1) * w, or1 = -(O[2] * r0 + O[3] * r1) * w;
+              const double w00 = O[0] * w, w01 = O[1] * w, w10 = O[2] * w, w11 = O[3] * w;
+              int idx = 6;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                acc[c] += J[c] * or0 + J[6 + c] * or1;
+                const double a0 = J[c] * w00 + J[6 + c] * w10, a1 = J[c] * w01 + J[6 + c] * w11;   // row c of J^T W
+#pragma unroll
+                for (int d = c; d < 6; ++d) acc[idx++] += a0 * J[d] + a1 * J[6 + d];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
+          }
+          if (lane == 0) {
+            int idx = 6;
+            for (int c = 0; c < 6; ++c) {
+              bs[v][c] = acc[c];
+              for (int d = c; d < 6; ++d) { Hs[v][6 * c + d] = acc[idx]; Hs[v][6 * d + c] = acc[idx]; ++idx; }
+            }
+          }
+        }
+        __syncthreads();
+        if (tid == 0) {
+          s_cur = currentChi0;
+          if (it == 0) {   // computeLambdaInit
+            double mx = 0;
+            for (int v = 0; v < nv; ++v) if (vact[v]) for (int j = 0; j < 6; ++j) mx = fmax(fabs(Hs[v][7 * j]), mx);
+            s_lambda = 1e-5 * mx; s_ni = 2.0;
+          }
+        }
+        __syncthreads();
+        double rho = 0;
+        int qmax = 0;
+        bool lam_bad = false;
+        do {
+          // push + solve (H + lambda I) x = b per active vertex, update
+          for (int v = tid; v < nv; v += BA_THREADS) {
+            bak[v] = est[v];
+            vok[v] = 1;
+            if (vact[v]) {
+              double A[36], rhs[6];
+              for (int k = 0; k < 36; ++k) A[k] = Hs[v][k];
+              for (int j = 0; j < 6; ++j) { A[7 * j] += s_lambda; rhs[j] = bs[v][j]; }
+              const bool okv = chol6(A, rhs);
+              vok[v] = okv;
+              for (int j = 0; j < 6; ++j) xsol[v][j] = okv ? rhs[j] : 0.0;
+              SE3q nw;
+              se3_oplus(est[v], xsol[v], nw);
+              est[v] = nw;
+            }
+          }
+          __syncthreads();
+          double part2 = 0;
+          for (int e = tid; e < ne; e += BA_THREADS) {
+            const int ge = e0 + e;
+            if (!is_active(ge)) continue;
+            edge_error(ge);
+            const double c = edge_chi2(ge);
+            if (robust) { double h0, h1; huber(c, a.huber_delta, h0, h1); part2 += h0; } else part2 += c;
+          }
+          double tempChi = block_sum_d(part2, red);
+          if (tid == 0) {
+            bool ok2 = true;
+            double scale = 0;
+            for (int v = 0; v < nv; ++v) if (vact[v]) {
+              ok2 = ok2 && vok[v];
+              for (int j = 0; j < 6; ++j) scale += xsol[v][j] * (s_lambda * xsol[v][j] + bs[v][j]);   // computeScale
+            }
+            if (!ok2) tempChi = 1.7976931348623157e308;
+            double r = (s_cur - tempChi) / (scale + 1e-3);
+            int flag;
+            if (r > 0 && isfinite(tempChi)) {
+              double alpha = 1. - pow(2 * r - 1, 3.0);
+              alpha = fmin(alpha, 2. / 3.);
+              s_lambda *= fmax(1. / 3., alpha);
+              s_ni = 2; s_cur = tempChi; flag = 1;
+            } else {
+              s_lambda *= s_ni; s_ni *= 2; flag = 0;
+              if (!isfinite(s_lambda)) flag = 2;
+            }
+            s_rho = r; s_flag = flag;
+          }
+          __syncthreads();
+          rho = s_rho;
+          const int flag = s_flag;
+          if (flag != 1) {      // pop(): restore vertices; edge errors stay those of the rejected trial
+            for (int v = tid; v < nv; v += BA_THREADS) est[v] = bak[v];
+          }
+          __syncthreads();
+          ++trials_total;
+          if (flag == 2) { lam_bad = true; break; }
+          qmax++;
+        } while (rho < 0 && qmax < 10);
+        ++outer_total;
+        if (qmax == 10 || rho == 0 || lam_bad) ok = false;   // Terminate
+      }
+    }
+    // ---------------- chi2 re-classification (object_slam.py:878-896) ----------------
+    my_good = 0;
+    for (int e = tid; e < ne; e += BA_THREADS) {
+      const int ge = e0 + e;
+      if (!a.inliers[ge]) edge_error(ge);
+      if (edge_chi2(ge) > a.chi2_gate) { a.level[ge] = 1; a.inliers[ge] = 0; }
+      else { a.level[ge] = 0; a.inliers[ge] = 1; my_good++; }
+    }
+    num_good = (int)(block_sum_d((double)my_good, red) + 0.5);
+    if (round == max(1, a.n_rounds / 2)) robust = 0;
+  }
+  __syncthreads();
+  for (int v = tid; v < nv; v += BA_THREADS) {
+    double R[9];
+    se3_R(est[v], R);
+    double* T = a.poses + 12 * (size_t)(v0 + v);
+    for (int r = 0; r < 3; ++r) { T[4 * r] = R[3 * r]; T[4 * r + 1] = R[3 * r + 1]; T[4 * r + 2] = R[3 * r + 2]; T[4 * r + 3] = est[v].t[r]; }
+  }
+  if (tid == 0 && a.stats) { a.stats[3 * prob] = rounds; a.stats[3 * prob + 1] = outer_total; a.stats[3 * prob + 2] = trials_total; }
+}
+
+}  // namespace
+
+int launch_ba_kernel(suo_ctx* ctx, int n_prob, const BaArgs& args, cudaStream_t s) {
+  if (n_prob <= 0) return SUO_OK;
+  ba_kernel<<<n_prob, BA_THREADS, 0, s>>>(args);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
+}
+
+// Called by api.cu with scratch buffers sized for n_edges.
+int launch_ba_batch_scratch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, double* poses,
+                            const uint8_t* fixed, const int32_t* e_obj, const int32_t* e_cam, const double* cam_k,
+                            const double* p, const double* uv, const double* info, uint8_t* inliers,
+                            const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
+                            int init_with_outliers, int32_t* stats, double* err_scratch, uint8_t* level_scratch,
+                            int8_t* fv_scratch, cudaStream_t s, const int32_t* vert_cnt, const int32_t* edge_cnt) {
+  BaArgs a;
+  a.prob_vert = prob_vert; a.prob_edge = prob_edge; a.vert_cnt = vert_cnt; a.edge_cnt = edge_cnt; a.poses = poses; a.fixed = fixed; a.e_obj = e_obj; a.e_cam = e_cam;
+  a.cam_k = cam_k; a.p = p; a.uv = uv; a.info = info; a.inliers = inliers; a.its = its; a.n_rounds = n_rounds;
+  a.huber_delta = huber_delta; a.chi2_gate = chi2_gate; a.init_with_outliers = init_with_outliers; a.stats = stats;
+  a.err = err_scratch; a.level = level_scratch; a.fv_kind = fv_scratch;
+  return launch_ba_kernel(ctx, n_prob, a, s);
+}

@@ -1,0 +1,116 @@
+// Shared host/device helpers for libsuo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/suo_b200.h"
+
+#define SUO_CUDA_TRY(ctx, expr)                                                        \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SUO_E_CUDA;                                                               \
+    }                                                                                  \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- one conv layer as the engine sees it -----------------------------------------
+enum ConvMode : int { CONV_1x1 = 0, CONV_3x3 = 1, CONV_STEM7 = 2 };
+
+struct ConvParams {
+  const float* in;        // NHWC [B,H,W,Cin]  (Cin = floats per pixel as stored)
+  const float* w;         // SIMT: [Cout_pad][K] row-major, K in gather order
+  const float* w_packed;  // tcgen05: per (n_tile, k_chunk) SW128 images, hi then lo
+  const float* bias;      // [Cout_pad] (zeros where absent)
+  const float* pre_scale; // [Cin] or nullptr
+  const float* pre_shift; // [Cin] or nullptr
+  const float* residual;  // NHWC [B,Ho,Wo,Cout_store] or nullptr
+  float* out;             // NHWC [B,Ho,Wo,out_c] or NCHW [B,Cout,Ho,Wo] (out_nchw)
+  int B, H, W, Cin;       // input geometry
+  int Ho, Wo;             // output geometry
+  int Cout;               // real output channels written
+  int Cout_pad;           // padded to the MMA N granularity
+  int out_c;              // channel stride of the NHWC output / residual
+  int K;                  // GEMM K (multiple of 32), in gather order
+  int mode;               // ConvMode
+  int chunks_per_row;     // CONV_STEM7: 32-float chunks per kernel row (ceil(7*Cin/32))
+  int relu;               // ReLU after bias
+  int out_nchw;           // store NCHW planes instead of NHWC
+};
+
+struct suo_ctx;
+int launch_conv_simt(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
+int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s);
+// host-side packing of canonical [Cout_pad][K] weights into the tcgen05 smem images
+size_t conv_tc_packed_floats(int Cout_pad, int K);
+void conv_tc_pack_weights(const float* w, int Cout_pad, int K, float* dst);
+int conv_tc_block_n(int Cout_pad);
+
+int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
+                          const float* cls_b, float* pooled_scratch, float* uv, float* cov, float* prob,
+                          float* mask_logits, float* mask, int32_t* argmax, cudaStream_t s);
+int launch_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes,
+                       const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
+                       cudaStream_t s);
+int launch_maxpool2(suo_ctx* ctx, const float* in, int B, int H, int W, int C, float* out, cudaStream_t s);
+int launch_upsample_add(suo_ctx* ctx, const float* up1, const float* low, int B, int H, int W, int C, float* out,
+                        cudaStream_t s);
+int launch_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj,
+                     double threshold, uint64_t seed, const uint64_t* obj_keys, double* T_out, int32_t* stats,
+                     cudaStream_t s);
+int launch_pnp_batch_counts(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets,
+                            const int32_t* counts, int n_obj, double threshold, uint64_t seed, const uint64_t* obj_keys,
+                            double* T_out, int32_t* stats, cudaStream_t s);
+int launch_ba_batch_scratch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, double* poses,
+                            const uint8_t* fixed, const int32_t* e_obj, const int32_t* e_cam, const double* cam_k,
+                            const double* p, const double* uv, const double* info, uint8_t* inliers,
+                            const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
+                            int init_with_outliers, int32_t* stats, double* err_scratch, uint8_t* level_scratch,
+                            int8_t* fv_scratch, cudaStream_t s, const int32_t* vert_cnt = nullptr,
+                            const int32_t* edge_cnt = nullptr);
+
+int launch_gate_compact(suo_ctx* ctx, const float* uv, const float* cov, const float* kp_mask, const uint8_t* model_mask,
+                        const double* model_kps, const double* K_bbox, int L, int K, float kp_var_thresh, float bbox_thresh,
+                        double* xs, double* ys, int32_t* counts, int32_t* kp_index, uint8_t* kp_used, cudaStream_t s);
+int launch_frame_ranges(suo_ctx* ctx, const int32_t* box_img, int L, int n_img, int32_t* frame_start, cudaStream_t s);
+int launch_ba_assemble(suo_ctx* ctx, int n_img, const int32_t* frame_start, const int32_t* counts, const int32_t* kp_index,
+                       const double* xs, const float* uv, const float* cov, const double* K_bbox, const double* diameter,
+                       const double* T_pnp, int K, double* poses, uint8_t* fixed, int32_t* prob_vert, int32_t* vert_cnt,
+                       int32_t* prob_edge, int32_t* edge_cnt, int32_t* e_obj, int32_t* e_cam, double* cam_k, double* p,
+                       double* uvd, double* info, uint8_t* inliers, int32_t* edge_src, uint8_t* accepted, cudaStream_t s);
+int launch_ba_scatter(suo_ctx* ctx, int n_img, const int32_t* frame_start, const int32_t* edge_cnt, const int32_t* edge_src,
+                      const uint8_t* inliers, const double* poses, const uint8_t* accepted, int K, double* T_ba,
+                      uint8_t* ba_inliers, cudaStream_t s);
+
+struct suo_ctx {
+  int device = 0;
+  int max_crops = 0, crop_res = 0, num_kp = 0;
+  std::string err;
+  long long launches = 0;
+  int opt_backend = 1, opt_passes = 3, opt_graph = 1;
+  void* net = nullptr;  // NetState (net_exec.cu)
+  void* scratch = nullptr; size_t scratch_bytes = 0;        // device scratch for host-pointer calls
+  void* pinned = nullptr; size_t pinned_bytes = 0;          // pinned staging
+  void set_error(const std::string& m, const char* f, int l) {
+    err = m + " (" + f + ":" + std::to_string(l) + ")";
+  }
+};

@@ -1,0 +1,402 @@
+// tcgen05 tensor-core implicit-GEMM convolution for sm_100a (conv backend 1).
+//
+// Replaces the cuDNN/MKL-DNN convolutions the reference reaches through
+// torch.nn.Conv2d in lib/models/layers/Residual.py:9-18 and lib/models/hg.py:67,80-86
+// (1x1, 3x3 pad 1, 7x7 stride 2 pad 3) together with the BatchNorm/ReLU/residual-add
+// glue around them (Residual.py:20-35), which is fused here as a prologue/epilogue.
+//
+//   D[m, n] = sum_k A[m, k] * Wt[n, k]      m = output pixel, n = output channel
+//
+// Precision: the reference computes these convs in FP32.  tcgen05 has no FP32 MMA, so
+// every FP32 operand is split into two TF32 numbers, x = hi + lo (hi = rna_tf32(x),
+// lo = rna_tf32(x - hi)), and three kind::tf32 MMAs accumulate hi*hi + lo*hi + hi*lo into
+// the FP32 TMEM accumulator ("3xTF32", relative error ~2^-21 per product, i.e. FP32
+// grade).  tf32_passes == 1 issues only hi*hi (plain TF32, 2^-11).
+//
+// Per CTA: one 128 x BN output tile, K marched in 32-float chunks through a 3-stage
+// shared-memory ring.  Warp roles (10 warps):
+//   warp 0      : weight producer — one thread issues cp.async.bulk (TMA bulk copy, UBLKCP)
+//                 of the pre-swizzled hi/lo weight images of the chunk, completes on an mbarrier
+//   warp 1      : TMEM allocator + MMA issuer — one thread issues tcgen05.mma (UTCMMA),
+//                 tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2..9  : A producers — coalesced 128-bit global loads of the NHWC activations
+//                 (im2col addressing with zero fill for padding), optional pre-activation
+//                 BN affine + ReLU, TF32 hi/lo split, stores into the 128B-swizzled K-major
+//                 operand tiles, fence.proxy.async + mbarrier arrive;
+//                 afterwards the same warps run the epilogue: tcgen05.ld TMEM -> registers,
+//                 + bias, ReLU, + residual, 128-bit stores (NHWC) or coalesced plane stores (NCHW).
+#include <cstring>
+#include "conv_gather.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;          // floats per chunk = one 128-byte swizzle row
+constexpr int NUM_STAGES = 3;
+constexpr int NUM_PRODUCER_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_PRODUCER_WARPS;
+constexpr int PREFETCH = 2;          // chunks of A kept in flight in registers
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, single CTA
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B, dense 8-row groups (SBO = 1024 B),
+// descriptor version 1 (sm_100).  Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);          // start address | LBO = 1 (unused for swizzled K-major)
+  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO | version = 1 | layout = SWIZZLE_128B
+  return ((uint64_t)hi << 32) | lo;
+}
+// Instruction descriptor: D = F32, A = B = TF32, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN>
+struct Smem {
+  static constexpr int B_TILE_BYTES = BN * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int BAR_OFFSET = NUM_STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;   // + barriers + alignment slack
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const ConvParams p, const int passes) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using S = Smem<BN>;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  auto full_a = [&](int s) { return bar_base + 8 * s; };
+  auto full_b = [&](int s) { return bar_base + 8 * (NUM_STAGES + s); };
+  auto empty = [&](int s) { return bar_base + 8 * (2 * NUM_STAGES + s); };
+  const uint32_t tmem_full = bar_base + 8 * (3 * NUM_STAGES);
+  const uint32_t tmem_slot = bar_base + 8 * (3 * NUM_STAGES + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFFSET + 8 * (3 * NUM_STAGES + 1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = p.B * p.Ho * p.Wo;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n_tile = blockIdx.y;
+  const int nchunks = p.K / BLOCK_K;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(full_a(s), NUM_PRODUCER_WARPS);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== weight producer (TMA bulk copies) =====================
+    if (lane == 0) {
+      const uint32_t bytes_per_part = S::B_TILE_BYTES;
+      const float* src = p.w_packed + (size_t)n_tile * nchunks * 2 * (BN * BLOCK_K);
+      for (int j = 0; j < nchunks; ++j) {
+        const int s = j % NUM_STAGES;
+        const uint32_t ph = (j / NUM_STAGES) & 1;
+        mbar_wait(empty(s), ph ^ 1);
+        const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
+        const uint32_t nbytes = passes == 3 ? 2 * bytes_per_part : bytes_per_part;
+        mbar_arrive_expect_tx(full_b(s), nbytes);
+        bulk_g2s(dst, src + (size_t)j * 2 * (BN * BLOCK_K), nbytes, full_b(s));   // hi image (and lo image right behind it)
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN);
+    for (int j = 0; j < nchunks; ++j) {
+      const int s = j % NUM_STAGES;
+      const uint32_t ph = (j / NUM_STAGES) & 1;
+      mbar_wait(full_a(s), ph);
+      mbar_wait(full_b(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_base + s * S::STAGE_BYTES;
+        const uint32_t a_lo = a_hi + A_TILE_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+        const uint32_t b_lo = b_hi + S::B_TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
+          const uint64_t dah = make_sw128_desc(a_hi + kk * 32), dbh = make_sw128_desc(b_hi + kk * 32);
+          umma_tf32(tmem_acc, dah, dbh, idesc, (j | kk) != 0);
+          if (passes == 3) {
+            const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
+            umma_tf32(tmem_acc, dal, dbh, idesc, 1u);
+            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(empty(s));                       // frees the smem stage once these MMAs retire
+        if (j == nchunks - 1) umma_commit(tmem_full);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== A producers, then epilogue =====================
+    const int pt = threadIdx.x - 64;            // 0..255
+    const int g = pt & 7;                       // float4 group inside the 128-byte row
+    const int r0 = pt >> 3;                     // rows r0 + 32*i
+    PixelCoord pc[4];
+    bool rok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + r0 + 32 * i;
+      rok[i] = m < M;
+      pc[i] = decode_pixel(rok[i] ? m : 0, p.Ho, p.Wo);
+    }
+    float4 v[PREFETCH][4];
+    auto load_chunk = [&](int j, float4 (&dst)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t vm;
+        const float* ptr = chunk_ptr(p, pc[i], j, vm);
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rok[i] && ((vm >> g) & 1u)) dst[i] = __ldg(reinterpret_cast<const float4*>(ptr + 4 * g));
+      }
+    };
+#pragma unroll
+    for (int q = 0; q < PREFETCH; ++q)
+      if (q < nchunks) load_chunk(q, v[q]);
+
+    auto produce = [&](int j, float4 (&buf)[4]) {
+      const int s = j % NUM_STAGES;
+      const uint32_t ph = (j / NUM_STAGES) & 1;
+      float4 cur[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = buf[i];
+      if (p.pre_scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * j + 4 * g));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * j + 4 * g));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (rok[i]) {
+            cur[i].x = fmaxf(fmaf(cur[i].x, sc.x, sh.x), 0.f); cur[i].y = fmaxf(fmaf(cur[i].y, sc.y, sh.y), 0.f);
+            cur[i].z = fmaxf(fmaf(cur[i].z, sc.z, sh.z), 0.f); cur[i].w = fmaxf(fmaf(cur[i].w, sc.w, sh.w), 0.f);
+          }
+        }
+      }
+      if (j + PREFETCH < nchunks) load_chunk(j + PREFETCH, buf);   // keep PREFETCH chunks of loads in flight
+      mbar_wait(empty(s), ph ^ 1);
+      uint8_t* a_hi = smem_gen + s * S::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4);
+        float4 hi;
+        hi.x = tf32_rna(cur[i].x); hi.y = tf32_rna(cur[i].y); hi.z = tf32_rna(cur[i].z); hi.w = tf32_rna(cur[i].w);
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        if (passes == 3) {
+          float4 lo;
+          lo.x = tf32_rna(cur[i].x - hi.x); lo.y = tf32_rna(cur[i].y - hi.y);
+          lo.z = tf32_rna(cur[i].z - hi.z); lo.w = tf32_rna(cur[i].w - hi.w);
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_a(s));
+    };
+    static_assert(PREFETCH == 2, "producer loop is unrolled for two register buffers");
+    for (int j = 0; j < nchunks; j += 2) {
+      produce(j, v[0]);
+      if (j + 1 < nchunks) produce(j + 1, v[1]);
+    }
+
+    // ---- epilogue: TMEM -> registers -> global ----
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the BN columns
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const int HW = p.Ho * p.Wo;
+    constexpr int COLS_PER_WARP = BN / 2;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+      const int col = half * COLS_PER_WARP + c0;   // column inside the tile
+      uint32_t r[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+      tmem_ld_wait();
+      const int n_base = n_tile * BN + col;
+      if (m < M) {
+        if (!p.out_nchw) {
+          float* __restrict__ orow = p.out + (size_t)m * p.out_c + n_base;
+          const float* __restrict__ rrow = p.residual ? p.residual + (size_t)m * p.out_c + n_base : nullptr;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            if (n_base + c < p.Cout) {
+              const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c));
+              float4 o;
+              o.x = __uint_as_float(r[c]) + bq.x; o.y = __uint_as_float(r[c + 1]) + bq.y;
+              o.z = __uint_as_float(r[c + 2]) + bq.z; o.w = __uint_as_float(r[c + 3]) + bq.w;
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (rrow) {
+                const float4 rq = *reinterpret_cast<const float4*>(rrow + c);
+                o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+              }
+              *reinterpret_cast<float4*>(orow + c) = o;
+            }
+          }
+        } else {
+          const int b = m / HW, rem = m - b * HW;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int n = n_base + c;
+            if (n < p.Cout) {
+              float o = __uint_as_float(r[c]) + __ldg(p.bias + n);
+              if (p.relu) o = fmaxf(o, 0.f);
+              p.out[((size_t)b * p.Cout + n) * HW + rem] = o;   // lanes = consecutive pixels of plane n: coalesced
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+template <int BN>
+int launch_bn(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    configured = true;
+  }
+  const int M = p.B * p.Ho * p.Wo;
+  dim3 grid((M + BLOCK_M - 1) / BLOCK_M, p.Cout_pad / BN);
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
+}
+
+inline float host_tf32_rna(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u = (u + 0x1000u) & 0xFFFFE000u;     // round-to-nearest, ties away (cvt.rna.tf32.f32)
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+}  // namespace
+
+int conv_tc_block_n(int Cout_pad) { return Cout_pad % 128 == 0 ? 128 : 64; }
+
+size_t conv_tc_packed_floats(int Cout_pad, int K) { return (size_t)Cout_pad * K * 2; }
+
+// w: [Cout_pad][K] row-major -> per (n_tile, chunk): hi image then lo image, each BN rows x 128 B
+// in the 128B-swizzled K-major layout the UMMA descriptor above describes.
+void conv_tc_pack_weights(const float* w, int Cout_pad, int K, float* dst) {
+  const int BN = conv_tc_block_n(Cout_pad);
+  const int nchunks = K / BLOCK_K;
+  for (int nt = 0; nt < Cout_pad / BN; ++nt)
+    for (int j = 0; j < nchunks; ++j) {
+      float* img = dst + ((size_t)nt * nchunks + j) * 2 * (BN * BLOCK_K);
+      for (int r = 0; r < BN; ++r)
+        for (int g = 0; g < 8; ++g)
+          for (int e = 0; e < 4; ++e) {
+            const float x = w[(size_t)(nt * BN + r) * K + 32 * j + 4 * g + e];
+            const float hi = host_tf32_rna(x);
+            const float lo = host_tf32_rna(x - hi);
+            const int off = (r >> 3) * 256 + (r & 7) * 32 + ((g ^ (r & 7)) << 2) + e;
+            img[off] = hi;
+            img[BN * BLOCK_K + off] = lo;
+          }
+    }
+}
+
+int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s) {
+  if (p.K % BLOCK_K || p.Cin % 4 || p.Cout_pad % 64 || (!p.out_nchw && (p.Cout % 4 || p.out_c % 4)) ||
+      (p.mode != CONV_STEM7 && p.Cin % 32)) {
+    ctx->set_error("conv_tc: unsupported shape", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  const int passes = tf32_passes == 1 ? 1 : 3;
+  if (conv_tc_block_n(p.Cout_pad) == 128) return launch_bn<128>(ctx, p, passes, s);
+  return launch_bn<64>(ctx, p, passes, s);
+}

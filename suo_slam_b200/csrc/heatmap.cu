@@ -1,0 +1,153 @@
+// Heat-map reduction (SURVEY.md §8 rows a3 + a4): spatial softmax, soft-argmax,
+// 2x2 covariance, hard argmax, channel mean and the keypoint-present classifier.
+// Replaces reference lib/models/pkpnet.py:13-63 (spatial_softmax, mesh_grid,
+// post_process_kp) and :74-78,116-118 (classifier), which materialise
+// [B,K,H,W,2] and [B,K,H,W,2,2] temporaries; here one CTA owns one (b,k) map:
+//   pass 1 (HBM -> registers/L1): max, argmax, sum x           (float4 loads)
+//   pass 2 (L1):                  S = sum e, first moments, optional prob store
+//   pass 3 (L1):                  central second moments
+// The map (16 KB at 64x64) stays in L1 between passes, so DRAM traffic is the
+// algorithmic H*W*4 bytes per map.  HBM-bound: no tensor cores on purpose.
+//
+// Grid convention is the reference's TRANSPOSED mesh (pkpnet.py:19-26):
+//   xx[h,w] = r[h], yy[h,w] = -r[w], r[i] = (i + 0.5)/(H/2) - 1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  T r = (threadIdx.x < kThreads / 32) ? sh[threadIdx.x] : T(0);
+  if (wid == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+heatmap_reduce_kernel(const float* __restrict__ logits, int K, int H, int W, float* __restrict__ pooled,
+                      float* __restrict__ uv, float* __restrict__ cov, float* __restrict__ prob,
+                      int32_t* __restrict__ argmax) {
+  __shared__ float shf[kThreads / 32];
+  __shared__ float shmax[kThreads / 32];
+  __shared__ int shidx[kThreads / 32];
+  const int map = blockIdx.x;  // b*K + k
+  const int HW = H * W;
+  const float* __restrict__ x = logits + (size_t)map * HW;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  const int n4 = HW >> 2;  // H*W is a multiple of 4 (checked on the host)
+  const float inv_half = 1.0f / (0.5f * (float)H);
+
+  // ---- pass 1: max / first argmax / plain sum --------------------------------------
+  float m = -INFINITY, s = 0.f;
+  int mi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    float4 v = x4[i];
+    float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s += e[j];
+      if (e[j] > m) { m = e[j]; mi = 4 * i + j; }   // ascending index per thread => first occurrence
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float om = __shfl_xor_sync(0xffffffffu, m, o);
+    int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { shmax[threadIdx.x >> 5] = m; shidx[threadIdx.x >> 5] = mi; }
+  float total = block_sum(s, shf);  // contains the __syncthreads that publish shmax/shidx
+  m = shmax[0]; mi = shidx[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w)
+    if (shmax[w] > m || (shmax[w] == m && shidx[w] < mi)) { m = shmax[w]; mi = shidx[w]; }
+
+  // ---- pass 2: normaliser and first moments ----------------------------------------
+  float S = 0.f, sx = 0.f, sy = 0.f;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    float4 v = x4[i];
+    float e[4] = {expf(v.x - m), expf(v.y - m), expf(v.z - m), expf(v.w - m)};
+    const int idx = 4 * i;
+    const int h = idx / W, w0 = idx - h * W;      // W % 4 == 0 => the 4 elements share a row
+    const float gx = ((float)h + 0.5f) * inv_half - 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gy = -(((float)(w0 + j) + 0.5f) * inv_half - 1.0f);
+      S += e[j]; sx += e[j] * gx; sy += e[j] * gy;
+    }
+  }
+  S = block_sum(S, shf);
+  sx = block_sum(sx, shf);
+  sy = block_sum(sy, shf);
+  const float invS = 1.0f / S;
+  const float u = sx * invS, vv = sy * invS;
+
+  // ---- pass 3: central second moments (+ optional prob store) -----------------------
+  float cxx = 0.f, cxy = 0.f, cyy = 0.f;
+  float4* __restrict__ p4 = prob ? reinterpret_cast<float4*>(prob + (size_t)map * HW) : nullptr;
+  for (int i = threadIdx.x; i < n4; i += kThreads) {
+    float4 v = x4[i];
+    float e[4] = {expf(v.x - m) * invS, expf(v.y - m) * invS, expf(v.z - m) * invS, expf(v.w - m) * invS};
+    const int idx = 4 * i;
+    const int h = idx / W, w0 = idx - h * W;
+    const float dx = (((float)h + 0.5f) * inv_half - 1.0f) - u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dy = -(((float)(w0 + j) + 0.5f) * inv_half - 1.0f) - vv;
+      cxx += e[j] * dx * dx; cxy += e[j] * dx * dy; cyy += e[j] * dy * dy;
+    }
+    if (p4) p4[i] = make_float4(e[0], e[1], e[2], e[3]);
+  }
+  cxx = block_sum(cxx, shf);
+  cxy = block_sum(cxy, shf);
+  cyy = block_sum(cyy, shf);
+
+  if (threadIdx.x == 0) {
+    if (uv) { uv[2 * map] = u; uv[2 * map + 1] = vv; }
+    if (cov) { cov[4 * map] = cxx; cov[4 * map + 1] = cxy; cov[4 * map + 2] = cxy; cov[4 * map + 3] = cyy; }
+    if (argmax) argmax[map] = mi;
+    if (pooled) pooled[map] = total / (float)HW;
+  }
+}
+
+// kp_mask_logits = W * relu(mean_hw(raw)) + b ; kp_mask = sigmoid (pkpnet.py:74-78,116-118)
+__global__ void classifier_kernel(const float* __restrict__ pooled, const float* __restrict__ Wc,
+                                  const float* __restrict__ bc, int K, float* __restrict__ mask_logits,
+                                  float* __restrict__ mask) {
+  const int b = blockIdx.x;
+  for (int o = threadIdx.x; o < K; o += blockDim.x) {
+    float acc = bc[o];
+    for (int i = 0; i < K; ++i) acc += Wc[o * K + i] * fmaxf(pooled[b * K + i], 0.f);
+    if (mask_logits) mask_logits[b * K + o] = acc;
+    if (mask) mask[b * K + o] = 1.0f / (1.0f + expf(-acc));
+  }
+}
+
+}  // namespace
+
+int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
+                          const float* cls_b, float* pooled_scratch, float* uv, float* cov, float* prob,
+                          float* mask_logits, float* mask, int32_t* argmax, cudaStream_t s) {
+  if (H != W || (W & 3) || B <= 0 || K <= 0) {
+    ctx->set_error("heatmap_reduce: need square maps with W % 4 == 0", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  heatmap_reduce_kernel<<<B * K, kThreads, 0, s>>>(logits, K, H, W, pooled_scratch, uv, cov, prob, argmax);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  if (cls_w && cls_b && (mask_logits || mask)) {
+    classifier_kernel<<<B, 64, 0, s>>>(pooled_scratch, cls_w, cls_b, K, mask_logits, mask);
+    ctx->launches++;
+    SUO_CUDA_TRY(ctx, cudaGetLastError());
+  }
+  return SUO_OK;
+}

@@ -1,0 +1,73 @@
+"""Single-view frame pipeline (the path BASELINE config 2 times): the three downward calls
+ObjectSLAM makes per frame — model(...) (lib/object_slam.py:1099), pnp(...) per object (:1144)
+and optimize() (:443-451) — plus the NumPy glue between them (:1100-1165), executed for a BATCH
+of independent frames by one ``suo_frames`` call with everything resident on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, synth
+from .pkpnet import PkpNet
+
+
+def k_bbox_for(K, bboxes):
+    """utils.fix_K_for_bbox_ndc per box, rounded through float32 like the reference's
+    ``K_bbox_np`` (float32 array, lib/object_slam.py:1082,1086) before .astype(float64) (:1140)."""
+    out = np.zeros((len(bboxes), 3, 3), dtype=np.float32)
+    for i, bb in enumerate(bboxes):
+        out[i] = synth.fix_K_for_bbox_ndc(K, bb)
+    return out.astype(np.float64)
+
+
+class FramePipeline:
+    def __init__(self, model: PkpNet, kp_var_thresh: float = 0.2, bbox_thresh: float = 0.9, seed: int = 0):
+        self.model = model
+        self.kp_var_thresh, self.bbox_thresh, self.seed = kp_var_thresh, bbox_thresh, seed   # evaluate.py:58-76 (YCBV)
+
+    def run(self, images, boxes, box_img, model_kps, model_mask, K_bbox, diameter, priors=None, run_ba=True):
+        """Host arrays in (numpy or pinned torch CPU tensors), host numpy out.
+        images [n_img,3,H,W] f32 in [0,1]; boxes [L,4]; box_img [L] sorted; model_kps [L,K,3] f64;
+        model_mask [L,K] bool; K_bbox [L,3,3] f64; diameter [L]."""
+        ctx = self.model.context()
+        n_img, _, H, W = images.shape
+        L, K = model_mask.shape
+        c = lambda a, dt: a if (hasattr(a, "data_ptr") and not isinstance(a, np.ndarray)) else np.ascontiguousarray(a, dtype=dt)
+        images = c(images, np.float32)
+        boxes, box_img = c(boxes, np.float32), c(box_img, np.int32)
+        model_kps, K_bbox, diameter = c(model_kps, np.float64), c(K_bbox, np.float64), c(diameter, np.float64)
+        model_mask = np.ascontiguousarray(model_mask, dtype=np.uint8)
+        pri = None if priors is None else c(priors, np.float32)
+        out = dict(T_pnp=np.zeros((L, 4, 4)), T_ba=np.zeros((L, 3, 4)), kp_used=np.zeros((L, K), np.uint8),
+                   ba_inliers=np.zeros((L, K), np.uint8), uv=np.zeros((L, K, 2), np.float32),
+                   cov=np.zeros((L, K, 2, 2), np.float32))
+        ctx.check(_lib.lib().suo_frames(
+            ctx.handle, _lib.ptr(images), n_img, H, W, _lib.ptr(boxes), _lib.ptr(box_img), L, _lib.ptr(pri),
+            _lib.ptr(model_kps), _lib.ptr(model_mask), _lib.ptr(K_bbox), _lib.ptr(diameter),
+            float(self.kp_var_thresh), float(self.bbox_thresh), int(self.seed), int(run_ba),
+            _lib.ptr(out["T_pnp"]), _lib.ptr(out["T_ba"]), _lib.ptr(out["kp_used"]), _lib.ptr(out["ba_inliers"]),
+            _lib.ptr(out["uv"]), _lib.ptr(out["cov"]), 0, None))
+        out["kp_used"] = out["kp_used"].astype(bool)
+        out["ba_inliers"] = out["ba_inliers"].astype(bool)
+        return out
+
+
+def solve_keypoints(ctx, uv, cov, kp_mask, box_img, model_kps, model_mask, K_bbox, diameter, kp_var_thresh=0.2,
+                    bbox_thresh=0.9, seed=0, run_ba=True):
+    """Rows a4'..a8 on given keypoints (host numpy in/out): gating -> PnP -> single-view BA."""
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    uv, cov, kp_mask = c(uv, np.float32), c(cov, np.float32), c(kp_mask, np.float32)
+    box_img = c(box_img, np.int32)
+    L, K = kp_mask.shape
+    n_img = int(box_img.max()) + 1
+    model_kps, K_bbox, diameter = c(model_kps, np.float64), c(K_bbox, np.float64), c(diameter, np.float64)
+    model_mask = c(model_mask, np.uint8)
+    out = dict(T_pnp=np.zeros((L, 4, 4)), T_ba=np.zeros((L, 3, 4)), kp_used=np.zeros((L, K), np.uint8),
+               ba_inliers=np.zeros((L, K), np.uint8))
+    ctx.check(_lib.lib().suo_solve_keypoints(
+        ctx.handle, _lib.ptr(uv), _lib.ptr(cov), _lib.ptr(kp_mask), _lib.ptr(box_img), n_img, L, _lib.ptr(model_kps),
+        _lib.ptr(model_mask), _lib.ptr(K_bbox), _lib.ptr(diameter), float(kp_var_thresh), float(bbox_thresh), int(seed),
+        int(run_ba), _lib.ptr(out["T_pnp"]), _lib.ptr(out["T_ba"]), _lib.ptr(out["kp_used"]), _lib.ptr(out["ba_inliers"]),
+        0, None))
+    out["kp_used"] = out["kp_used"].astype(bool)
+    out["ba_inliers"] = out["ba_inliers"].astype(bool)
+    return out

@@ -1,0 +1,118 @@
+"""GPU parity: each CUDA kernel, through the C ABI, against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import net_oracle
+from suo_slam_b200 import _lib, pkpnet, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_ref(x_nhwc, w_ohwi, bias, ksize, stride, pre, residual, relu):
+    x = torch.from_numpy(x_nhwc).double().permute(0, 3, 1, 2)
+    if pre is not None:
+        x = F.relu(x * torch.from_numpy(pre[0]).double()[None, :, None, None] + torch.from_numpy(pre[1]).double()[None, :, None, None])
+    w = torch.from_numpy(w_ohwi).double().permute(0, 3, 1, 2)
+    y = F.conv2d(x, w, None if bias is None else torch.from_numpy(bias).double(), stride=stride, padding=(ksize - 1) // 2)
+    if relu:
+        y = F.relu(y)
+    y = y.permute(0, 2, 3, 1).numpy()
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, ksize, stride, pre, residual, relu
+    (2, 16, 16, 256, 128, 1, 1, True, False, True),     # conv1 of a bottleneck
+    (2, 16, 16, 128, 128, 3, 1, False, False, True),    # conv2
+    (2, 16, 16, 128, 256, 1, 1, False, True, False),    # conv3 + skip
+    (3, 4, 4, 256, 256, 1, 1, False, True, False),      # M = 48 < one tile
+    (1, 8, 8, 64, 64, 3, 1, False, False, True),        # r1.conv2
+    (2, 32, 32, 4, 64, 7, 2, False, False, True),       # stem, RGB-only layout
+    (1, 32, 32, 48, 64, 7, 2, False, False, True),      # stem, 44+4 channel layout
+    (2, 16, 16, 256, 41, 1, 1, False, False, False),    # tmpOut (N = 41 -> padded tile)
+    (2, 16, 16, 64, 256, 1, 1, False, True, False),     # tmpOut_ (K = 64)
+]
+
+
+@pytest.mark.parametrize("backend,passes,tol", [(0, 3, 2e-6), (1, 3, 4e-6), (1, 1, 3e-3)])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_engine_vs_fp64_reference(gpu_ctx, case, backend, passes, tol):
+    B, H, W, Cin, Cout, ks, st, use_pre, use_res, relu = case
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    x = rng.normal(size=(B, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(size=(Cout, ks, ks, Cin)) / np.sqrt(ks * ks * Cin)).astype(np.float32)
+    b = rng.normal(size=Cout).astype(np.float32)
+    pre = (rng.uniform(0.5, 1.5, Cin).astype(np.float32), rng.normal(scale=0.1, size=Cin).astype(np.float32)) if use_pre else None
+    Ho, Wo = (H // 2, W // 2) if st == 2 else (H, W)
+    res = rng.normal(size=(B, Ho, Wo, Cout)).astype(np.float32) if use_res else None
+    if Cout % 4:   # NHWC store needs Cout % 4 == 0: the network pads 41 -> 64 (zero weights); do the same here
+        pad = (-Cout) % 4
+        w = np.concatenate([w, np.zeros((pad,) + w.shape[1:], np.float32)])
+        b = np.concatenate([b, np.zeros(pad, np.float32)])
+        Cout += pad
+    got = pkpnet.conv2d(gpu_ctx, x, w, b, ks, st, pre, res, relu, backend=backend, tf32_passes=passes)
+    ref = _conv_ref(x, w, b, ks, st, pre, res, relu)
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max() / scale
+    assert err < tol, f"rel-to-max error {err:.3e} (backend {backend}, passes {passes})"
+
+
+def test_heatmap_reduce_vs_reference_golden(gpu_ctx, golden_dir):
+    g = np.load(f"{golden_dir}/reduce.npz")
+    out = pkpnet.heatmap_reduce(gpu_ctx, g["logits"])
+    assert np.array_equal(out["argmax"], g["logits"].reshape(2, 41, -1).argmax(-1))      # bit-exact indices
+    np.testing.assert_allclose(out["uv"], g["uv"], atol=1e-6)
+    np.testing.assert_allclose(out["cov"], g["cov"], atol=1e-6)
+    np.testing.assert_allclose(out["prob"], g["prob"], atol=1e-7, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(8, 41, 64, 64), (2, 41, 128, 128), (1, 3, 4, 4)])
+def test_heatmap_reduce_vs_oracle_shapes(gpu_ctx, shape):
+    rng = np.random.default_rng(shape[2])
+    logits = rng.normal(scale=2.0, size=shape).astype(np.float32)
+    K = shape[1]
+    cw, cb = rng.normal(size=(K, K)).astype(np.float32), rng.normal(size=K).astype(np.float32)
+    ctx = gpu_ctx if K == 41 else _lib.Context(0, 1, 64, K)
+    out = pkpnet.heatmap_reduce(ctx, logits, cw, cb)
+    ref = net_oracle.heatmap_reduce(torch.from_numpy(logits), torch.from_numpy(cw), torch.from_numpy(cb))
+    assert np.array_equal(out["argmax"], ref["argmax"].numpy())
+    np.testing.assert_allclose(out["uv"], ref["uv"].numpy(), atol=2e-6)
+    np.testing.assert_allclose(out["cov"], ref["cov"].numpy(), atol=2e-6)
+    np.testing.assert_allclose(out["kp_mask"], ref["kp_mask"].numpy(), atol=1e-5)
+    np.testing.assert_allclose(out["kp_mask_logits"], ref["kp_mask_logits"].numpy(), atol=1e-4)
+
+
+def test_heatmap_ties_pick_first_index(gpu_ctx):
+    logits = np.zeros((1, 41, 8, 8), np.float32)
+    logits[0, 3, 2, 5] = logits[0, 3, 6, 1] = 4.0
+    out = pkpnet.heatmap_reduce(gpu_ctx, logits)
+    assert out["argmax"][0, 3] == 2 * 8 + 5 and out["argmax"][0, 0] == 0
+
+
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_crop_concat_vs_torchvision(gpu_ctx, with_prior):
+    import torchvision
+    rng = np.random.default_rng(9)
+    H, W, R = 120, 160, 64
+    img = rng.random((2, 3, H, W), dtype=np.float32)
+    boxes = np.array([[10.0, 8.0, 90.0, 100.0], [40.5, 20.25, 150.0, 110.0], [100.0, 30.0, 112.0, 45.0],
+                      [-20.0, -10.0, 60.0, 50.0], [100.0, 60.0, 200.0, 140.0], [5.0, 5.0, 5.5, 5.5]], np.float32)
+    box_img = np.array([0, 0, 0, 1, 1, 1], np.int32)
+    L = len(boxes)
+    prior = rng.random((L, 41, R, R), dtype=np.float32) if with_prior else None
+    oc = 48 if with_prior else 4
+    out = np.zeros((L, R, R, oc), np.float32)
+    gpu_ctx.check(_lib.lib().suo_crop_concat(gpu_ctx.handle, _lib.ptr(img), 2, H, W, _lib.ptr(boxes), _lib.ptr(box_img), L,
+                                              _lib.ptr(prior), R, _lib.ptr(out), oc, 0, None))
+    bl = [torch.from_numpy(boxes[box_img == i]) for i in range(2)]
+    ref = torchvision.ops.roi_align(torch.from_numpy(img), bl, output_size=(R, R)).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(out[..., :3], ref, atol=2e-6)
+    if with_prior:
+        np.testing.assert_array_equal(out[..., 3:44], prior.transpose(0, 2, 3, 1))
+        assert not out[..., 44:].any()
+    else:
+        assert not out[..., 3].any()

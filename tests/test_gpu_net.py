@@ -1,0 +1,97 @@
+"""GPU parity of the whole network forward (rows a1-a4) through the reference call surface
+``model(images, boxes, prior_kp)``, against fixtures made by the UNMODIFIED reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle
+from suo_slam_b200 import _lib, synth
+from suo_slam_b200.pkpnet import PkpNet
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.make_synthetic_state_dict(seed=0, peaky=4.0)
+
+
+def _model(sd, backend, passes, res=64, max_crops=8):
+    m = PkpNet(input_res=(res, res), max_crops=max_crops)
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    m.context().set_option(_lib.SUO_OPT_CONV_BACKEND, backend)
+    m.context().set_option(_lib.SUO_OPT_TF32_PASSES, passes)
+    return m
+
+
+def _margin_ok(logits, argmax, err):
+    """indices must agree wherever the reference's top-2 margin exceeds the logit error bound"""
+    flat = logits.reshape(logits.shape[0], logits.shape[1], -1)
+    top2 = np.sort(flat, -1)[..., -2:]
+    ref_idx = flat.argmax(-1)
+    decisive = (top2[..., 1] - top2[..., 0]) > 4 * err
+    return decisive, ref_idx
+
+
+@pytest.mark.parametrize("backend,passes,tol_logit,tol_uv", [(0, 3, 2e-4, 2e-5), (1, 3, 3e-4, 2e-5), (1, 1, 0.3, 2e-2)])
+@pytest.mark.parametrize("name", ["net_small", "net_prior"])
+def test_forward_vs_reference_golden(golden_dir, sd, name, backend, passes, tol_logit, tol_uv):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    m = _model(sd, backend, passes)
+    prior = None if g["prior"].size == 0 else [torch.from_numpy(g["prior"]).cuda()]
+    out = m(torch.from_numpy(g["img"]).cuda(), [torch.from_numpy(g["boxes"]).cuda()], prior)
+    torch.cuda.synchronize()
+    logits = out["prob_logits"].cpu().numpy()
+    err = np.abs(logits - g["logits"]).max()
+    assert err < tol_logit * max(1.0, np.abs(g["logits"]).max() / 10), f"logit err {err}"
+    np.testing.assert_allclose(out["uv"].cpu().numpy(), g["uv"], atol=tol_uv)
+    np.testing.assert_allclose(out["cov"].cpu().numpy(), g["cov"], atol=tol_uv)
+    np.testing.assert_allclose(out["kp_mask"].cpu().numpy(), g["kp_mask"], atol=max(tol_uv, 1e-4))
+    decisive, ref_idx = _margin_ok(g["logits"], None, err)
+    got_idx = out["argmax"].cpu().numpy()
+    assert decisive.mean() > 0.5
+    assert np.array_equal(got_idx[decisive], ref_idx[decisive])          # bit-exact hard argmax where decisive
+    assert set(out.keys()) >= {"uv", "cov", "prob_logits", "prob", "kp_mask_logits", "kp_mask"}
+    assert out["uv"].shape == (3, 41, 2) and out["cov"].shape == (3, 41, 2, 2) and out["prob"].shape == (3, 41, 16, 16)
+
+
+def test_forward_host_tensors_and_graph_replay(sd, golden_dir):
+    """CPU tensors in -> CPU tensors out (host-pointer ABI path); second call replays the CUDA graph."""
+    g = np.load(f"{golden_dir}/net_small.npz")
+    m = _model(sd, 1, 3)
+    a = m(torch.from_numpy(g["img"]), [torch.from_numpy(g["boxes"])], None)
+    b = m(torch.from_numpy(g["img"]), [torch.from_numpy(g["boxes"])], None)
+    assert a["uv"].device.type == "cpu"
+    np.testing.assert_array_equal(a["prob_logits"].numpy(), b["prob_logits"].numpy())     # deterministic
+    np.testing.assert_allclose(a["uv"].numpy(), g["uv"], atol=2e-5)
+    assert m.context().kernel_launches() > 400
+
+
+def test_forward_256_vs_oracle(sd):
+    """BASELINE config-2 shape: 8 crops of a 640x480 frame at 256x256 -> 64x64 heat-maps."""
+    fr = synth.make_frame(1)
+    img = torch.from_numpy(fr["img"].transpose(2, 0, 1).astype(np.float32) / 255)[None]
+    boxes = torch.from_numpy(np.stack([o["bbox"] for o in fr["objs"]]))
+    m = _model(sd, 1, 3, res=256, max_crops=8)
+    out = m(img.cuda(), [boxes.cuda()], None)
+    torch.cuda.synchronize()
+    ref = net_oracle.pkpnet_forward(sd, img, [boxes], None, (256, 256))
+    lg, lr = out["prob_logits"].cpu().numpy(), ref["prob_logits"].numpy()
+    err = np.abs(lg - lr).max()
+    assert err < 5e-4 * max(1.0, np.abs(lr).max() / 10), err
+    np.testing.assert_allclose(out["uv"].cpu().numpy(), ref["uv"].numpy(), atol=3e-5)
+    np.testing.assert_allclose(out["cov"].cpu().numpy(), ref["cov"].numpy(), atol=3e-5)
+    decisive, ref_idx = _margin_ok(lr, None, err)
+    assert np.array_equal(out["argmax"].cpu().numpy()[decisive], ref_idx[decisive])
+
+
+def test_forward_errors(sd):
+    m = PkpNet(input_res=(64, 64), max_crops=2)
+    with pytest.raises(_lib.SuoError):
+        m(torch.zeros(1, 3, 32, 32), [torch.tensor([[0.0, 0.0, 8.0, 8.0]])])           # no weights loaded
+    m.load_state_dict(sd)
+    with pytest.raises(_lib.SuoError):
+        m(torch.zeros(1, 3, 32, 32), [torch.tensor([[0.0, 0.0, 8.0, 8.0]] * 3)])       # more crops than max_crops
+    with pytest.raises(AssertionError):
+        m(torch.zeros(2, 3, 32, 32), [torch.tensor([[0.0, 0.0, 8.0, 8.0]])])           # len(boxes) != batch (pkpnet.py:91)

@@ -1,0 +1,76 @@
+"""CPU: the net oracle (oracle/net_oracle.py) against fixtures produced by the UNMODIFIED
+reference modules (oracle/gen_golden_net.py), and live against the reference when mounted."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import net_oracle, ref_shims
+from suo_slam_b200 import arch, synth
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.make_synthetic_state_dict(seed=0, peaky=4.0)
+
+
+@pytest.mark.parametrize("name", ["net_small", "net_prior"])
+def test_oracle_reproduces_reference_golden(golden_dir, sd, name):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    prior = None if g["prior"].size == 0 else [torch.from_numpy(g["prior"])]
+    out = net_oracle.pkpnet_forward(sd, torch.from_numpy(g["img"]), [torch.from_numpy(g["boxes"])], prior, (64, 64))
+    # same torch ops in the same order as the reference => essentially bit-equal; allow thread-count reassociation
+    np.testing.assert_allclose(out["prob_logits"].numpy(), g["logits"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(out["uv"].numpy(), g["uv"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["cov"].numpy(), g["cov"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(out["kp_mask"].numpy(), g["kp_mask"], rtol=0, atol=1e-5)
+    assert np.array_equal(out["argmax"].numpy(), g["logits"].reshape(3, 41, -1).argmax(-1))
+
+
+def test_reduce_golden(golden_dir):
+    g = np.load(f"{golden_dir}/reduce.npz")
+    out = net_oracle.heatmap_reduce(torch.from_numpy(g["logits"]))
+    np.testing.assert_allclose(out["uv"].numpy(), g["uv"], atol=1e-6)
+    np.testing.assert_allclose(out["cov"].numpy(), g["cov"], atol=1e-6)
+    np.testing.assert_allclose(out["prob"].numpy(), g["prob"], atol=1e-7)
+    # the flat map: uv = 0 and cov = variance of the pixel-centre grid (1 - 1/H^2)/3
+    assert abs(out["uv"][1, 5]).max() < 1e-6
+    np.testing.assert_allclose(out["cov"][1, 5].numpy(), np.eye(2) * (1 - 1 / 32 ** 2) / 3, atol=1e-5)
+
+
+def test_grid_is_transposed():
+    """uv[...,0] varies along ROWS, uv[...,1] = -(column coordinate)."""
+    raw = torch.full((1, 1, 8, 8), -50.0)
+    raw[0, 0, 1, 6] = 50.0   # row 1, col 6
+    out = net_oracle.heatmap_reduce(raw)
+    r = (np.arange(0.5, 8, 1) / 4 - 1)
+    np.testing.assert_allclose(out["uv"][0, 0].numpy(), [r[1], -r[6]], atol=1e-6)
+    assert int(out["argmax"][0, 0]) == 1 * 8 + 6
+
+
+def test_kbbox_golden(golden_dir):
+    g = np.load(f"{golden_dir}/kbbox.npz")
+    for K, bb, ref in zip(g["K"], g["bbox"], g["K_bbox"]):
+        np.testing.assert_allclose(synth.fix_K_for_bbox_ndc(K, bb), ref, rtol=1e-14, atol=1e-12)
+
+
+def test_state_dict_spec_counts():
+    spec = arch.state_dict_spec()
+    assert len(spec) == 1274                         # reference PkpNet().state_dict() (SURVEY §2.2 probe)
+    n_param = sum(int(np.prod(s)) for k, s in spec if not k.endswith(("running_mean", "running_var", "num_batches_tracked")))
+    assert n_param == 12_726_732
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not mounted")
+def test_oracle_vs_live_reference(sd):
+    ref = ref_shims.import_reference_pkpnet()
+    net = ref.PkpNet(input_res=(64, 64))
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    rng = np.random.default_rng(3)
+    img = torch.from_numpy(rng.random((2, 3, 96, 128), dtype=np.float32))
+    boxes = [torch.tensor([[5.0, 6.0, 70.0, 80.0]]), torch.tensor([[20.0, 10.0, 100.0, 90.0], [0.0, 0.0, 127.0, 95.0]])]
+    with torch.no_grad():
+        a = net(img, boxes, None)
+    b = net_oracle.pkpnet_forward(sd, img, boxes, None, (64, 64))
+    for k in ("uv", "cov", "kp_mask", "prob_logits"):
+        np.testing.assert_allclose(b[k].numpy(), a[k].numpy(), atol=2e-4 if k == "prob_logits" else 1e-5)
