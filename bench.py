@@ -1,0 +1,289 @@
+"""bench.py — frames/s of the SUO-SLAM per-frame hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+Workload = BASELINE.json configs[1]: synthetic YCBV-shape stream, 640x480 frames, 8 object
+crops per frame, 256x256 crops -> 41-channel 64x64 heat-maps; one *step* is one pass of the
+whole single-view frame path (crop -> hourglass -> soft-argmax/cov -> gating -> per-object PnP
+-> single-view LM-BA) over a batch of `--frames-per-step` independent frames per GPU.
+Frames of a single-view stream are independent, so ranks take disjoint
+frames (weak scaling) and exchange the per-crop pose records with ONE NCCL all-gather per step.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with inputs resident in HBM; `e2e` = the same
+path through the host-pointer C ABI (pinned host buffers in, host results out, copies inside the
+timed region).  Timing: CUDA events on the launching stream, barrier + synchronize on both
+sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, CROPS, RES, NUM_KP = 480, 640, 8, 256, 41
+GFLOP_PER_CROP = 31.495          # 15.7475 GMAC per 256x256 crop (convs only)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--input-sets", type=int, default=3, help="distinct input batches rotated between steps")
+    ap.add_argument("--tf32-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_batch(seed0, n_frames):
+    """n_frames synthetic frames -> flat per-crop arrays (host)."""
+    from suo_slam_b200 import frames, synth
+    imgs, boxes, bi, mk, mm, kb, diam = [], [], [], [], [], [], []
+    for f in range(n_frames):
+        fr = synth.make_frame(seed0 + f, n_obj=CROPS, H=H, W=W)
+        imgs.append(fr["img"].transpose(2, 0, 1).astype(np.float32) / 255.0)     # object_slam.py:1092
+        bb = [o["bbox"] for o in fr["objs"]]
+        boxes += bb
+        bi += [f] * CROPS
+        mk += [o["model_kps"] for o in fr["objs"]]
+        mm += [o["model_kps_mask"] for o in fr["objs"]]
+        diam += [o["diameter"] for o in fr["objs"]]
+        kb.append(frames.k_bbox_for(fr["K"], bb))
+    return dict(images=np.stack(imgs), boxes=np.stack(boxes).astype(np.float32), box_img=np.asarray(bi, np.int32),
+                model_kps=np.stack(mk), model_mask=np.stack(mm).astype(np.uint8), K_bbox=np.concatenate(kb),
+                diameter=np.asarray(diam, np.float64))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_frames_per_s(seconds, steps=None, warmup=1):
+    """The reference's CPU path (oracle port: torch-CPU net + restated Lambda-Twist/Ceres PnP + g2o BA)
+    on this box's host cores, one 8-crop frame per step."""
+    import torch
+    from oracle import frame_oracle
+    from suo_slam_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_synthetic_state_dict(0, peaky=4.0)
+    b = make_batch(1000, 1)
+    times = []
+    t_end = time.perf_counter() + seconds
+    i = 0
+    while True:
+        t0 = time.perf_counter()
+        frame_oracle.run_frames(sd, b["images"], b["boxes"], b["box_img"], b["model_kps"], b["model_mask"].astype(bool),
+                                b["K_bbox"], b["diameter"], input_res=(RES, RES))
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        i += 1
+        if steps is not None:
+            if len(times) >= steps:
+                break
+        elif time.perf_counter() > t_end and len(times) >= 2:
+            break
+    return 1.0 / float(np.median(times)), len(times), torch.get_num_threads(), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fps, n, cores, times = cpu_reference_frames_per_s(0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    ms = 1e3 / fps
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/sec (8 obj-crops/frame, 640x480)", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 net / f64 solvers", "data": "synthetic",
+        "config": {"workload": "configs[1]: 640x480 frame, 8 crops, 256x256 -> 41x64x64, net+reduce+gating+PnP+single-view BA",
+                   "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} steps of 1 frame (8 crops) each, oracle/ (reference g2o/Ceres/lambdatwist do not build here)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from suo_slam_b200 import _lib, dist as sdist, synth
+    from suo_slam_b200.pkpnet import PkpNet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    F = args.frames_per_step
+    L = F * CROPS
+    dev = torch.device("cuda", local)
+
+    model = PkpNet(input_res=(RES, RES), max_crops=L)
+    model.load_state_dict(synth.make_synthetic_state_dict(0, peaky=4.0))
+    model.cuda(local)
+    ctx = model.context()
+    ctx.set_option(_lib.SUO_OPT_TF32_PASSES, args.tf32_passes)
+    lib, hdl = _lib.lib(), ctx.handle
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    # distinct input sets per rank (disjoint frames of the stream), rotated between steps
+    sets_h = [make_batch(10_000 * rank + 100 * s, F) for s in range(args.input_sets)]
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    sets_pin = [{k: pin(v) for k, v in b.items()} for b in sets_h]
+    sets_dev = [{k: v.to(dev) for k, v in b.items()} for b in sets_pin]
+    f64 = dict(dtype=torch.float64, device=dev)
+    outs_dev = dict(T_pnp=torch.zeros((L, 16), **f64), T_ba=torch.zeros((L, 12), **f64),
+                    used=torch.zeros((L, NUM_KP), dtype=torch.uint8, device=dev),
+                    bain=torch.zeros((L, NUM_KP), dtype=torch.uint8, device=dev))
+    outs_host = dict(T_pnp=torch.zeros((L, 16), dtype=torch.float64).pin_memory(), T_ba=torch.zeros((L, 12), dtype=torch.float64).pin_memory(),
+                     used=torch.zeros((L, NUM_KP), dtype=torch.uint8).pin_memory(), bain=torch.zeros((L, NUM_KP), dtype=torch.uint8).pin_memory(),
+                     uv=torch.zeros((L, NUM_KP, 2)).pin_memory(), cov=torch.zeros((L, NUM_KP, 4)).pin_memory())
+    rec = torch.zeros((L, sdist.RECORD_WORDS), **f64)
+    gathered = torch.zeros((world * L, sdist.RECORD_WORDS), **f64)
+
+    def step(b, on_device, o):
+        p = _lib.ptr
+        ctx.check(lib.suo_frames(hdl, p(b["images"]), F, H, W, p(b["boxes"]), p(b["box_img"]), L, None, p(b["model_kps"]),
+                                 p(b["model_mask"]), p(b["K_bbox"]), p(b["diameter"]), 0.2, 0.9, 0, 1,
+                                 p(o["T_pnp"]), p(o["T_ba"]), p(o["used"]), p(o["bain"]),
+                                 p(o.get("uv")), p(o.get("cov")), 1 if on_device else 0, sp))
+        if world > 1:   # the single exchange of the step: fixed-size pose records of every rank's crops
+            if on_device:
+                rec[:, :12] = o["T_pnp"][:, :12]
+                rec[:, 12:24] = o["T_ba"]
+            else:
+                rec[:, :12].copy_(o["T_pnp"][:, :12], non_blocking=True)
+                rec[:, 12:24].copy_(o["T_ba"], non_blocking=True)
+            dist.all_gather_into_tensor(gathered, rec)
+
+    def timed(on_device, sets, o, steps, warm):
+        for i in range(warm):
+            step(sets[i % len(sets)], on_device, o)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.kernel_launches()
+        e0.record(stream)
+        for i in range(steps):
+            step(sets[i % len(sets)], on_device, o)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), ctx.kernel_launches() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(True, sets_dev, outs_dev, args.steps, max(3, args.warmup))
+    ms_e2e, _ = timed(False, sets_pin, outs_host, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline of the dominant kernel (tcgen05 conv engine): per-op events over the network program
+    import ctypes as C
+    conv_ms, other_ms = C.c_float(0), C.c_float(0)
+    ctx.check(lib.suo_profile_network(hdl, L, 0, 2, C.byref(conv_ms), C.byref(other_ms), sp))
+    torch.cuda.synchronize(dev)
+
+    if rank == 0:
+        frames_total = F * world * args.steps
+        fps = frames_total / (ms_dev * 1e-3)
+        fps_e2e = frames_total / (ms_e2e * 1e-3)
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
+        h2d = sum(v.numel() * v.element_size() for v in sets_pin[0].values())
+        d2h = sum(v.numel() * v.element_size() for v in outs_host.values())
+        out = {
+            "metric": "frames/sec (8 obj-crops/frame, 640x480)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32x3 (3xTF32 split, fp32-equivalent) convs + f32 reductions + f64 solvers" if args.tf32_passes == 3 else "tf32 convs + f32 reductions + f64 solvers",
+            "data": "synthetic (seeded random-init weights, uniform-noise frames)",
+            "config": {"workload": "configs[1]: 640x480 frame, 8 crops, 256x256 -> 41x64x64, net+reduce+gating+PnP+single-view BA",
+                       "frames_per_step_per_gpu": F, "crops_per_step_per_gpu": L, "parallelism": f"frames sharded over {world} GPU(s), 1 all-gather of pose records/step",
+                       "l2": f"{args.input_sets} input sets rotated; per-step activation working set ({L} crops) >> 126 MB L2",
+                       "conv_backend": "tcgen05", "tf32_passes": args.tf32_passes},
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                         "traffic": None, "kernel": "conv_tc_kernel (all conv layers of one forward)",
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                         "note": "algorithmic 31.495 GFLOP/crop x crops / summed conv-kernel time (CUDA events per launch, eager pass after the timed region); "
+                                 "3xTF32 issues 3 tf32 MMAs per product, so the hardware ceiling for this kernel is peak/6",
+                         "conv_ms_per_step": conv_ms.value, "other_net_ms_per_step": other_ms.value},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cfps, n, cores, _ = cpu_reference_frames_per_s(args.cpu_baseline_seconds)
+            out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                   "sample": f"{n} timed frames (8 crops each) of the same workload through oracle/ on the host cores"}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (N>1 or --no-cpu-baseline)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -37,7 +37,8 @@ enum {
 enum {
   SUO_OPT_CONV_BACKEND = 1, /* 0 = FP32 SIMT implicit GEMM, 1 = tcgen05 TF32 tensor cores (default) */
   SUO_OPT_TF32_PASSES = 2,  /* 3 = 3xTF32 split (FP32-equivalent, default), 1 = single-pass TF32 */
-  SUO_OPT_USE_GRAPH = 3     /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
+  SUO_OPT_USE_GRAPH = 3,    /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
+  SUO_OPT_CONV_PERSISTENT = 4 /* 1 = persistent tcgen05 conv kernel with overlapped epilogue (default), 0 = one tile per CTA */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */
@@ -169,6 +170,13 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W,
                uint64_t seed, int run_ba,
                double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
                float* uv, float* cov, int on_device, void* stream);
+
+/* ---- measurement ----------------------------------------------------------------- */
+/* Per-op CUDA-event timing of the network program on the current input buffer (eager launches):
+ * average ms per forward in the conv kernels and in the pool / up-sample kernels.  bench.py uses it
+ * for the roofline block; it has no reference counterpart (the reference times with time.time(),
+ * lib/utils/utils.py:20-23). */
+int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* conv_ms, float* other_ms, void* stream);
 
 #ifdef __cplusplus
 }

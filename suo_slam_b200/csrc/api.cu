@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -38,8 +39,8 @@ struct NetState {
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes) < std::tie(o.L, o.variant, o.backend, o.passes); } };
+  struct GraphKey { int L, variant, backend, passes, persistent; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
 };
 
@@ -114,7 +115,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -205,6 +206,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_BACKEND: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_backend = value; return SUO_OK;
     case SUO_OPT_TF32_PASSES: if (value != 1 && value != 3) return SUO_E_INVALID; ctx->opt_passes = value; return SUO_OK;
     case SUO_OPT_USE_GRAPH: ctx->opt_graph = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -728,6 +730,62 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const
   if (run_ba) { D2H(T_ba, d_Tba, 96 * (size_t)L); D2H(ba_inliers, d_bain, LK); }
 #undef D2H
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+// Per-op device timing of the network program (eager launches, one CUDA event pair per op) on
+// whatever the input buffer currently holds: average milliseconds per forward spent in conv
+// kernels and in the other (pool / up-sample) kernels.  Used by bench.py for the roofline block.
+int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* conv_ms, float* other_ms, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!x->loaded || L <= 0 || L > ctx->max_crops || iters <= 0) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NetState& N = x->net;
+  const int variant = with_priors ? 1 : 0;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < N.ops.size(); ++i) if (N.ops[i].variant == 2 || N.ops[i].variant == variant) idx.push_back(i);
+  std::vector<cudaEvent_t> ev(idx.size() + 1);
+  for (auto& e : ev) SUO_CUDA_TRY(ctx, cudaEventCreate(&e));
+  double conv = 0, other = 0;
+  const int R = ctx->crop_res;
+  for (int it = 0; it < iters; ++it) {
+    SUO_CUDA_TRY(ctx, cudaEventRecord(ev[0], s));
+    for (size_t q = 0; q < idx.size(); ++q) {
+      // run exactly one op by temporarily restricting the program
+      const OpDesc& o = N.ops[idx[q]];
+      const BufDesc& bi = N.bufs[o.in];
+      const BufDesc& bo = N.bufs[o.out];
+      if (o.type == OP_CONV) {
+        ConvParams p{};
+        p.in = N.act[o.in]; p.w = N.pool + o.w_off; p.w_packed = N.packed[idx[q]]; p.bias = N.pool + o.b_off;
+        p.pre_scale = o.pre_off >= 0 ? N.pool + o.pre_off : nullptr;
+        p.pre_shift = o.pre_off >= 0 ? N.pool + o.pre_off + o.Cin : nullptr;
+        p.residual = o.res >= 0 ? N.act[o.res] : nullptr;
+        p.out = N.act[o.out];
+        p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin; p.Ho = R / bo.div; p.Wo = R / bo.div;
+        p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode; p.chunks_per_row = o.cpr;
+        p.relu = o.relu; p.out_nchw = o.out_nchw;
+        rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
+      } else if (o.type == OP_MAXPOOL) {
+        rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);
+      } else {
+        rc = launch_upsample_add(ctx, N.act[o.in], N.act[o.res], L, R / bo.div, R / bo.div, bo.C, N.act[o.out], s);
+      }
+      if (rc) return rc;
+      SUO_CUDA_TRY(ctx, cudaEventRecord(ev[q + 1], s));
+    }
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    for (size_t q = 0; q < idx.size(); ++q) {
+      float ms = 0;
+      SUO_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev[q], ev[q + 1]));
+      (N.ops[idx[q]].type == OP_CONV ? conv : other) += ms;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (conv_ms) *conv_ms = (float)(conv / iters);
+  if (other_ms) *other_ms = (float)(other / iters);
   return SUO_OK;
 }
 

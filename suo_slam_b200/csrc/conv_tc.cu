@@ -25,6 +25,7 @@
 //                 operand tiles, fence.proxy.async + mbarrier arrive;
 //                 afterwards the same warps run the epilogue: tcgen05.ld TMEM -> registers,
 //                 + bias, ReLU, + residual, 128-bit stores (NHWC) or coalesced plane stores (NCHW).
+#include <algorithm>
 #include <cstring>
 #include "conv_gather.cuh"
 
@@ -158,7 +159,7 @@ conv_tc_kernel(const ConvParams p, const int passes) {
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);   // [0,BN): hi*hi accumulator, [BN,2BN): correction terms
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -198,9 +199,13 @@ conv_tc_kernel(const ConvParams p, const int passes) {
           const uint64_t dah = make_sw128_desc(a_hi + kk * 32), dbh = make_sw128_desc(b_hi + kk * 32);
           umma_tf32(tmem_acc, dah, dbh, idesc, (j | kk) != 0);
           if (passes == 3) {
+            // The tensor core's FP32 accumulate truncates: measured error grows linearly with the number of
+            // accumulation steps into one accumulator (~1.4e-8 of max per step).  The small lo*hi + hi*lo
+            // terms therefore go to their own accumulator (their truncation error is 2^-11 smaller) and are
+            // added in FP32 by the epilogue; the main accumulator sees only K/8 steps.
             const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
-            umma_tf32(tmem_acc, dal, dbh, idesc, 1u);
-            umma_tf32(tmem_acc, dah, dbl, idesc, 1u);
+            umma_tf32(tmem_acc + BN, dal, dbh, idesc, (j | kk) != 0);
+            umma_tf32(tmem_acc + BN, dah, dbl, idesc, 1u);
           }
         }
         umma_commit(empty(s));                       // frees the smem stage once these MMAs retire
@@ -295,6 +300,13 @@ conv_tc_kernel(const ConvParams p, const int passes) {
       uint32_t r[32];
       tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
       tmem_ld_wait();
+      if (passes == 3) {
+        uint32_t rc[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + col), rc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(rc[c]));
+      }
       const int n_base = n_tile * BN + col;
       if (m < M) {
         if (!p.out_nchw) {
@@ -334,8 +346,284 @@ conv_tc_kernel(const ConvParams p, const int passes) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_acc, 2 * BN);
   }
+}
+
+// =====================================================================================================
+// Persistent variant: grid = #SMs, every CTA loops over output tiles.  The smem ring and the A/weight
+// producers run continuously across tile boundaries, the accumulator is double-buffered in TMEM and a
+// dedicated epilogue warpgroup drains tile i while the tensor core already works on tile i+1.
+//   warp 0      weight producer (TMA bulk copies)          warp 1      TMEM alloc + MMA issuer
+//   warps 2..5  epilogue (one TMEM lane quarter each)      warps 6..13 A producers
+// TMEM columns: buffer b in {0,1} at b*2*BN: [main | correction].
+constexpr int P_NUM_THREADS = 32 * (2 + 4 + NUM_PRODUCER_WARPS);
+
+template <int BN>
+__global__ void __launch_bounds__(P_NUM_THREADS, 1)
+conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  using S = Smem<BN>;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  auto full_a = [&](int s) { return bar_base + 8 * s; };
+  auto full_b = [&](int s) { return bar_base + 8 * (NUM_STAGES + s); };
+  auto empty = [&](int s) { return bar_base + 8 * (2 * NUM_STAGES + s); };
+  auto tmem_full = [&](int b) { return bar_base + 8 * (3 * NUM_STAGES + b); };
+  auto tmem_empty = [&](int b) { return bar_base + 8 * (3 * NUM_STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8 * (3 * NUM_STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFFSET + 8 * (3 * NUM_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int M = p.B * p.Ho * p.Wo;
+  const int nchunks = p.K / BLOCK_K;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(full_a(s), NUM_PRODUCER_WARPS);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      const uint32_t nbytes = (passes == 3 ? 2u : 1u) * S::B_TILE_BYTES;
+      uint32_t g = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % num_n_tiles;
+        const float* src = p.w_packed + (size_t)n_tile * nchunks * 2 * (BN * BLOCK_K);
+        for (int j = 0; j < nchunks; ++j, ++g) {
+          const int s = g % NUM_STAGES;
+          const uint32_t ph = (g / NUM_STAGES) & 1;
+          mbar_wait(empty(s), ph ^ 1);
+          const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
+          mbar_arrive_expect_tx(full_b(s), nbytes);
+          bulk_g2s(dst, src + (size_t)j * 2 * (BN * BLOCK_K), nbytes, full_b(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN);
+    uint32_t g = 0, i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const uint32_t b = i & 1;
+      mbar_wait(tmem_empty(b), ((i >> 1) & 1) ^ 1);        // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t acc = tmem_base + b * 2 * BN;
+      for (int j = 0; j < nchunks; ++j, ++g) {
+        const int s = g % NUM_STAGES;
+        const uint32_t ph = (g / NUM_STAGES) & 1;
+        mbar_wait(full_a(s), ph);
+        mbar_wait(full_b(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_base + s * S::STAGE_BYTES;
+          const uint32_t a_lo = a_hi + A_TILE_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES;
+          const uint32_t b_lo = b_hi + S::B_TILE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
+            const uint64_t dah = make_sw128_desc(a_hi + kk * 32), dbh = make_sw128_desc(b_hi + kk * 32);
+            umma_tf32(acc, dah, dbh, idesc, (j | kk) != 0);
+            if (passes == 3) {
+              const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
+              umma_tf32(acc + BN, dal, dbh, idesc, (j | kk) != 0);
+              umma_tf32(acc + BN, dah, dbl, idesc, 1u);
+            }
+          }
+          umma_commit(empty(s));
+          if (j == nchunks - 1) umma_commit(tmem_full(b));
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue warpgroup =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int HW = p.Ho * p.Wo;
+    uint32_t i = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+      const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
+      const uint32_t b = i & 1;
+      mbar_wait(tmem_full(b), (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
+      const int m = m_tile * BLOCK_M + q * 32 + lane;
+#pragma unroll 1
+      for (int col = 0; col < BN; col += 32) {
+        uint32_t r[32];
+        tmem_ld32(acc + (uint32_t)col, r);
+        tmem_ld_wait();
+        if (passes == 3) {
+          uint32_t rc[32];
+          tmem_ld32(acc + (uint32_t)(BN + col), rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(rc[c]));
+        }
+        if (col + 32 >= BN) {                      // last TMEM read of this tile: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(b));
+        }
+        const int n_base = n_tile * BN + col;
+        if (m < M) {
+          if (!p.out_nchw) {
+            float* __restrict__ orow = p.out + (size_t)m * p.out_c + n_base;
+            const float* __restrict__ rrow = p.residual ? p.residual + (size_t)m * p.out_c + n_base : nullptr;
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              if (n_base + c < p.Cout) {
+                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c));
+                float4 o;
+                o.x = __uint_as_float(r[c]) + bq.x; o.y = __uint_as_float(r[c + 1]) + bq.y;
+                o.z = __uint_as_float(r[c + 2]) + bq.z; o.w = __uint_as_float(r[c + 3]) + bq.w;
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (rrow) {
+                  const float4 rq = *reinterpret_cast<const float4*>(rrow + c);
+                  o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
+                }
+                *reinterpret_cast<float4*>(orow + c) = o;
+              }
+            }
+          } else {
+            const int bb = m / HW, rem = m - bb * HW;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int n = n_base + c;
+              if (n < p.Cout) {
+                float o = __uint_as_float(r[c]) + __ldg(p.bias + n);
+                if (p.relu) o = fmaxf(o, 0.f);
+                p.out[((size_t)bb * p.Cout + n) * HW + rem] = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== A producers =====================
+    const int pt = threadIdx.x - 192;           // 0..255
+    const int g8 = pt & 7;                      // float4 group inside the 128-byte row
+    const int r0 = pt >> 3;                     // rows r0 + 32*i
+    // two cursors over the flat (tile, chunk) sequence of this CTA: L issues global loads PREFETCH chunks
+    // ahead of S, which converts and stores to shared memory
+    struct Cursor { int t, j; PixelCoord pc[4]; bool rok[4]; };
+    auto set_tile = [&](Cursor& c) {
+      const int m_tile = c.t / num_n_tiles;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m_tile * BLOCK_M + r0 + 32 * i;
+        c.rok[i] = (c.t < num_tiles) && (m < M);
+        c.pc[i] = decode_pixel(c.rok[i] ? m : 0, p.Ho, p.Wo);
+      }
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.j == nchunks) { c.j = 0; c.t += gridDim.x; set_tile(c); }
+    };
+    Cursor L, Sx;
+    L.t = blockIdx.x; L.j = 0; set_tile(L);
+    Sx.t = blockIdx.x; Sx.j = 0; set_tile(Sx);
+    float4 v[PREFETCH][4];
+    auto load_chunk = [&](const Cursor& c, float4 (&dst)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t vm;
+        const float* ptr = chunk_ptr(p, c.pc[i], c.j, vm);
+        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c.rok[i] && ((vm >> g8) & 1u)) dst[i] = __ldg(reinterpret_cast<const float4*>(ptr + 4 * g8));
+      }
+    };
+#pragma unroll
+    for (int qq = 0; qq < PREFETCH; ++qq) {
+      if (L.t < num_tiles) { load_chunk(L, v[qq]); advance(L); }
+    }
+    uint32_t g = 0;
+    auto produce = [&](float4 (&buf)[4]) {
+      const int s = g % NUM_STAGES;
+      const uint32_t ph = (g / NUM_STAGES) & 1;
+      float4 cur[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cur[i] = buf[i];
+      if (p.pre_scale) {
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * Sx.j + 4 * g8));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * Sx.j + 4 * g8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (Sx.rok[i]) {
+            cur[i].x = fmaxf(fmaf(cur[i].x, sc.x, sh.x), 0.f); cur[i].y = fmaxf(fmaf(cur[i].y, sc.y, sh.y), 0.f);
+            cur[i].z = fmaxf(fmaf(cur[i].z, sc.z, sh.z), 0.f); cur[i].w = fmaxf(fmaf(cur[i].w, sc.w, sh.w), 0.f);
+          }
+        }
+      }
+      if (L.t < num_tiles) { load_chunk(L, buf); advance(L); }
+      mbar_wait(empty(s), ph ^ 1);
+      uint8_t* a_hi = smem_gen + s * S::STAGE_BYTES;
+      uint8_t* a_lo = a_hi + A_TILE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = r0 + 32 * i;
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) << 4);
+        float4 hi;
+        hi.x = tf32_rna(cur[i].x); hi.y = tf32_rna(cur[i].y); hi.z = tf32_rna(cur[i].z); hi.w = tf32_rna(cur[i].w);
+        *reinterpret_cast<float4*>(a_hi + off) = hi;
+        if (passes == 3) {
+          float4 lo;
+          lo.x = tf32_rna(cur[i].x - hi.x); lo.y = tf32_rna(cur[i].y - hi.y);
+          lo.z = tf32_rna(cur[i].z - hi.z); lo.w = tf32_rna(cur[i].w - hi.w);
+          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_a(s));
+      ++g;
+      advance(Sx);
+    };
+    static_assert(PREFETCH == 2, "producer loop is unrolled for two register buffers");
+    while (Sx.t < num_tiles) {
+      produce(v[0]);
+      if (Sx.t < num_tiles) produce(v[1]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 4 * BN);
+  }
+}
+
+template <int BN>
+int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+  static bool configured = false;
+  static int num_sms = 148;
+  if (!configured) {
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    int dev = 0;
+    SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
+    SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  const int M = p.B * p.Ho * p.Wo;
+  const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
+  const int grid = std::min(mt * nt, num_sms);
+  conv_tc_persistent_kernel<BN><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
 }
 
 template <int BN>
@@ -397,6 +685,10 @@ int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStrea
     return SUO_E_INVALID;
   }
   const int passes = tf32_passes == 1 ? 1 : 3;
+  if (ctx->opt_persistent) {
+    if (conv_tc_block_n(p.Cout_pad) == 128) return launch_persistent<128>(ctx, p, passes, s);
+    return launch_persistent<64>(ctx, p, passes, s);
+  }
   if (conv_tc_block_n(p.Cout_pad) == 128) return launch_bn<128>(ctx, p, passes, s);
   return launch_bn<64>(ctx, p, passes, s);
 }
