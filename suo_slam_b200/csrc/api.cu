@@ -7,6 +7,7 @@
 // packs the weights for the tensor-core kernel once, and replays the op list — as a CUDA
 // graph per (crop count, variant) — on the caller's stream.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -173,6 +174,9 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   suo_ctx* c = new suo_ctx();
   c->device = device; c->max_crops = max_crops; c->crop_res = crop_res; c->num_kp = num_kp;
   c->net = new CtxExtra();
+  // developer overrides (tests run both conv kernel variants through the same ABI)
+  if (const char* e = getenv("SUO_CONV_PERSISTENT")) c->opt_persistent = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_USE_GRAPH")) c->opt_graph = atoi(e) ? 1 : 0;
   *out = c;
   return SUO_OK;
 }
