@@ -781,11 +781,22 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       SUO_CUDA_TRY(ctx, cudaEventRecord(ev[q + 1], s));
     }
     SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    FILE* dump = nullptr;
+    if (it == iters - 1) { if (const char* path = getenv("SUO_PROFILE_DUMP")) dump = fopen(path, "w"); }
+    if (dump) fprintf(dump, "op,type,mode,side_out,Cin,Cout,K,relu,res,pre,ms,gflop\n");
     for (size_t q = 0; q < idx.size(); ++q) {
       float ms = 0;
       SUO_CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev[q], ev[q + 1]));
-      (N.ops[idx[q]].type == OP_CONV ? conv : other) += ms;
+      const OpDesc& o = N.ops[idx[q]];
+      (o.type == OP_CONV ? conv : other) += ms;
+      if (dump) {
+        const int side = R / N.bufs[o.out].div;
+        const double gf = o.type == OP_CONV ? 2.0 * L * side * side * (double)o.Cout_pad * o.K * 1e-9 : 0.0;
+        fprintf(dump, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", idx[q], o.type, o.mode, side, o.Cin, o.Cout, o.K, o.relu,
+                o.res >= 0, o.pre_off >= 0, ms, gf);
+      }
     }
+    if (dump) fclose(dump);
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (conv_ms) *conv_ms = (float)(conv / iters);

@@ -88,6 +88,31 @@ def test_forward_256_vs_oracle(sd):
     assert np.array_equal(out["argmax"].cpu().numpy()[decisive], ref_idx[decisive])
 
 
+def test_forward_tless_shape_with_priors(sd):
+    """BASELINE config 5 shape: 512x512 crops -> 128x128 heat-maps, mixed objects with / without prior
+    planes (symmetric objects get a rendered prior, lib/object_slam.py:486-514)."""
+    rng = np.random.default_rng(5)
+    img = torch.from_numpy(rng.random((1, 3, 480, 640), dtype=np.float32))
+    boxes = torch.tensor([[40.0, 30.0, 420.0, 400.0], [300.0, 100.0, 630.0, 470.0]])
+    prior = torch.zeros(2, 41, 512, 512)
+    yy, xx = torch.meshgrid(torch.arange(512.0), torch.arange(512.0), indexing="ij")
+    for k in range(0, 41, 3):                       # object 1 "symmetric": Gaussian blobs on a third of the planes
+        cy, cx = rng.uniform(60, 450, 2)
+        prior[1, k] = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 14.0 ** 2))
+    m = _model(sd, 1, 3, res=512, max_crops=2)
+    out = m(img.cuda(), [boxes.cuda()], [prior.cuda()])
+    torch.cuda.synchronize()
+    ref = net_oracle.pkpnet_forward(sd, img, [boxes], [prior], (512, 512))
+    assert out["prob_logits"].shape == (2, 41, 128, 128)
+    lr = ref["prob_logits"].numpy()
+    err = np.abs(out["prob_logits"].cpu().numpy() - lr).max()
+    assert err < 5e-4 * max(1.0, np.abs(lr).max() / 10), err
+    np.testing.assert_allclose(out["uv"].cpu().numpy(), ref["uv"].numpy(), atol=5e-5)
+    np.testing.assert_allclose(out["cov"].cpu().numpy(), ref["cov"].numpy(), atol=5e-5)
+    decisive, ref_idx = _margin_ok(lr, None, err)
+    assert np.array_equal(out["argmax"].cpu().numpy()[decisive], ref_idx[decisive])
+
+
 def test_forward_errors(sd):
     m = PkpNet(input_res=(64, 64), max_crops=2)
     with pytest.raises(_lib.SuoError):
