@@ -405,8 +405,34 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   p.in = d_in; p.w = d_w; p.w_packed = d_wp; p.bias = d_b; p.pre_scale = d_ps; p.pre_shift = d_pt; p.residual = d_res;
   p.out = d_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cout_pad = Cout_pad;
   p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
+  long long* d_dbg = nullptr;
+  const char* dbg_path = getenv("SUO_CONV_TIMELINE");
+  if (dbg_path && backend == 1) {
+    SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 5 * 512 * sizeof(long long)));
+    SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 5 * 512 * sizeof(long long), s));
+    p.dbg = d_dbg;
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
   rc = backend == 1 ? launch_conv_tc(ctx, p, tf32_passes, s) : launch_conv_simt(ctx, p, s);
+  cudaEventRecord(e1, s);
   if (rc) return rc;
+  if (d_dbg) {
+    std::vector<long long> h(5 * 512);
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    if (FILE* f = fopen(dbg_path, "a")) {
+      fprintf(f, "# B=%d H=%d W=%d Cin=%d Cout=%d k=%d passes=%d kernel_ms=%.4f\n", B, H, W, Cin, Cout, ksize, tf32_passes, ms);
+      fprintf(f, "g,prod_slot_free,prod_arrived,mma_full_a,mma_full_b,w_slot_free\n");
+      for (int g = 0; g < 512 && h[g]; ++g)
+        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld\n", g, h[g] - h[0], h[512 + g] - h[0], h[1024 + g] - h[0], h[1536 + g] - h[0], h[2048 + g] - h[0]);
+      fclose(f);
+    }
+    cudaFree(d_dbg);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return SUO_OK;

@@ -55,6 +55,7 @@ struct ConvParams {
   int chunks_per_row;     // CONV_STEM7: 32-float chunks per kernel row (ceil(7*Cin/32))
   int relu;               // ReLU after bias
   int out_nchw;           // store NCHW planes instead of NHWC
+  long long* dbg;         // optional [5][512] clock64 timeline of CTA 0 (tools only), else nullptr
 };
 
 struct suo_ctx;

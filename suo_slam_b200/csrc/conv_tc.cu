@@ -62,6 +62,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
 }
+// long waits (epilogue waiting for a whole main loop): back off so the spin does not steal issue slots
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -126,7 +140,9 @@ struct Smem {
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int BAR_OFFSET = NUM_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 128 + 1024;   // + barriers + alignment slack
+  static constexpr int STAGING_OFFSET = BAR_OFFSET + 128;           // epilogue transpose buffers: 4 warps x 32 x 36 floats
+  static constexpr int STAGING_BYTES = 4 * 32 * 36 * 4;
+  static constexpr int TOTAL = STAGING_OFFSET + STAGING_BYTES + 1024;   // + alignment slack
 };
 
 template <int BN>
@@ -407,6 +423,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
           const int s = g % NUM_STAGES;
           const uint32_t ph = (g / NUM_STAGES) & 1;
           mbar_wait(empty(s), ph ^ 1);
+          if (p.dbg && blockIdx.x == 0 && g < 512) p.dbg[4 * 512 + g] = clock64();
           const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
           mbar_arrive_expect_tx(full_b(s), nbytes);
           bulk_g2s(dst, src + (size_t)j * 2 * (BN * BLOCK_K), nbytes, full_b(s));
@@ -426,7 +443,9 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         const int s = g % NUM_STAGES;
         const uint32_t ph = (g / NUM_STAGES) & 1;
         mbar_wait(full_a(s), ph);
+        if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[2 * 512 + g] = clock64();
         mbar_wait(full_b(s), ph);
+        if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[3 * 512 + g] = clock64();
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = smem_base + s * S::STAGE_BYTES;
@@ -457,7 +476,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
       const uint32_t b = i & 1;
-      mbar_wait(tmem_full(b), (i >> 1) & 1);
+      mbar_wait_backoff(tmem_full(b), (i >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
       const int m = m_tile * BLOCK_M + q * 32 + lane;
@@ -479,35 +498,49 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
           if (lane == 0) mbar_arrive(tmem_empty(b));
         }
         const int n_base = n_tile * BN + col;
-        if (m < M) {
-          if (!p.out_nchw) {
-            float* __restrict__ orow = p.out + (size_t)m * p.out_c + n_base;
-            const float* __restrict__ rrow = p.residual ? p.residual + (size_t)m * p.out_c + n_base : nullptr;
+        if (!p.out_nchw) {
+          // Transpose the 32x32 block through shared memory so that global traffic is coalesced: in TMEM
+          // layout a lane owns a whole row (32 lanes -> 32 different 128-byte lines per store instruction);
+          // after the transpose 8 lanes cover one row's 128 contiguous bytes (4 full lines per instruction).
+          float* stg = reinterpret_cast<float*>(smem_gen + S::STAGING_OFFSET) + (warp - 2) * (32 * 36);
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              if (n_base + c < p.Cout) {
-                const float4 bq = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + c));
-                float4 o;
-                o.x = __uint_as_float(r[c]) + bq.x; o.y = __uint_as_float(r[c + 1]) + bq.y;
-                o.z = __uint_as_float(r[c + 2]) + bq.z; o.w = __uint_as_float(r[c + 3]) + bq.w;
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                if (rrow) {
-                  const float4 rq = *reinterpret_cast<const float4*>(rrow + c);
-                  o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w;
-                }
-                *reinterpret_cast<float4*>(orow + c) = o;
-              }
+          for (int c = 0; c < 32; c += 4)
+            *reinterpret_cast<float4*>(stg + lane * 36 + c) =
+                make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+          __syncwarp();
+          const int cg = lane & 7, rsub = lane >> 3;
+          const int n0 = n_base + 4 * cg;
+          const bool ncol_ok = n0 < p.Cout;
+          const float4 bq = ncol_ok ? __ldg(reinterpret_cast<const float4*>(p.bias + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int mrow0 = m_tile * BLOCK_M + q * 32 + rsub;
+          float4 rq[8];
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int mm = mrow0 + 4 * i;
+              rq[i] = (ncol_ok && mm < M) ? *reinterpret_cast<const float4*>(p.residual + (size_t)mm * p.out_c + n0)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          } else {
-            const int bb = m / HW, rem = m - bb * HW;
+          }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int n = n_base + c;
-              if (n < p.Cout) {
-                float o = __uint_as_float(r[c]) + __ldg(p.bias + n);
-                if (p.relu) o = fmaxf(o, 0.f);
-                p.out[((size_t)bb * p.Cout + n) * HW + rem] = o;
-              }
+          for (int i = 0; i < 8; ++i) {
+            const int mm = mrow0 + 4 * i;
+            float4 o = *reinterpret_cast<const float4*>(stg + (rsub + 4 * i) * 36 + 4 * cg);
+            o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
+            if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (p.residual) { o.x += rq[i].x; o.y += rq[i].y; o.z += rq[i].z; o.w += rq[i].w; }
+            if (ncol_ok && mm < M) *reinterpret_cast<float4*>(p.out + (size_t)mm * p.out_c + n0) = o;
+          }
+          __syncwarp();      // staging is rewritten by the next column group
+        } else if (m < M) {
+          const int bb = m / HW, rem = m - bb * HW;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int n = n_base + c;
+            if (n < p.Cout) {
+              float o = __uint_as_float(r[c]) + __ldg(p.bias + n);
+              if (p.relu) o = fmaxf(o, 0.f);
+              p.out[((size_t)bb * p.Cout + n) * HW + rem] = o;   // lanes = consecutive pixels of plane n: coalesced
             }
           }
         }
@@ -515,87 +548,139 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     }
   } else {
     // ===================== A producers =====================
+    // Addressing is hoisted out of the chunk loop: per tile each thread decodes its 4 rows once into a base
+    // pointer + validity bit-mask; per chunk only a shared running offset changes (no divisions per chunk).
     const int pt = threadIdx.x - 192;           // 0..255
     const int g8 = pt & 7;                      // float4 group inside the 128-byte row
     const int r0 = pt >> 3;                     // rows r0 + 32*i
-    // two cursors over the flat (tile, chunk) sequence of this CTA: L issues global loads PREFETCH chunks
-    // ahead of S, which converts and stores to shared memory
-    struct Cursor { int t, j; PixelCoord pc[4]; bool rok[4]; };
-    auto set_tile = [&](Cursor& c) {
+    struct LoadCursor {
+      int t, j, tap, cc;                        // tile, chunk, 3x3 tap / stem kernel row, 32-float sub-chunk
+      ptrdiff_t off;                            // running float offset of this chunk from the row base
+      const float* base[4];
+      uint32_t mask[4];                         // 1x1: bit0 = row valid; 3x3: bit t = tap t in bounds; stem: bits0-6 ky ok, bits8-14 pixel ok
+    };
+    const int cpc = p.Cin >> 5, cpr = p.chunks_per_row;
+    auto set_tile = [&](LoadCursor& c) {
       const int m_tile = c.t / num_n_tiles;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = m_tile * BLOCK_M + r0 + 32 * i;
-        c.rok[i] = (c.t < num_tiles) && (m < M);
-        c.pc[i] = decode_pixel(c.rok[i] ? m : 0, p.Ho, p.Wo);
+        const bool ok = (c.t < num_tiles) && (m < M);
+        const PixelCoord pc = decode_pixel(ok ? m : 0, p.Ho, p.Wo);
+        uint32_t msk = 0;
+        if (p.mode == CONV_1x1) {
+          c.base[i] = p.in + (size_t)(ok ? m : 0) * p.Cin;
+          msk = ok ? 1u : 0u;
+        } else if (p.mode == CONV_3x3) {
+          c.base[i] = p.in + ((size_t)(pc.b * p.H + pc.oy) * p.W + pc.ox) * p.Cin;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int iy = pc.oy + t / 3 - 1, ix = pc.ox + t % 3 - 1;
+            if (ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) msk |= 1u << t;
+          }
+        } else {
+          const int iy0 = 2 * pc.oy - 3, ix0 = 2 * pc.ox - 3;
+          c.base[i] = p.in + ((ptrdiff_t)(pc.b * p.H + iy0) * p.W + ix0) * p.Cin;
+#pragma unroll
+          for (int t = 0; t < 7; ++t) {
+            if (ok && iy0 + t >= 0 && iy0 + t < p.H) msk |= 1u << t;
+            if (ok && ix0 + t >= 0 && ix0 + t < p.W) msk |= 1u << (8 + t);
+          }
+        }
+        c.mask[i] = msk;
+      }
+      c.j = 0; c.tap = 0; c.cc = 0;
+      c.off = (p.mode == CONV_3x3) ? -(ptrdiff_t)(p.W + 1) * p.Cin : 0;
+    };
+    auto advance = [&](LoadCursor& c) {
+      if (++c.j == nchunks) { c.t += gridDim.x; set_tile(c); return; }
+      if (p.mode == CONV_1x1) { c.off += 32; }
+      else if (p.mode == CONV_3x3) {
+        if (++c.cc == cpc) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)((c.tap / 3 - 1) * p.W + (c.tap % 3 - 1)) * p.Cin; }
+        else c.off += 32;
+      } else {
+        if (++c.cc == cpr) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)c.tap * p.W * p.Cin; }
+        else c.off += 32;
       }
     };
-    auto advance = [&](Cursor& c) {
-      if (++c.j == nchunks) { c.j = 0; c.t += gridDim.x; set_tile(c); }
-    };
-    Cursor L, Sx;
-    L.t = blockIdx.x; L.j = 0; set_tile(L);
-    Sx.t = blockIdx.x; Sx.j = 0; set_tile(Sx);
+    LoadCursor L;
+    L.t = blockIdx.x; set_tile(L);
+    int st = blockIdx.x, sj = 0;               // store cursor: tile / chunk
     float4 v[PREFETCH][4];
-    auto load_chunk = [&](const Cursor& c, float4 (&dst)[4]) {
+    uint32_t vbits[PREFETCH];
+    auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4], uint32_t& bits) {
+      uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row this float4 group belongs to
+      if (p.mode == CONV_STEM7) {
+        const int x = 32 * c.cc + 4 * g8;
+        const int pix = (p.Cin == 4) ? (x >> 2) : ((x * 1366) >> 16);   // x / Cin for Cin in {4, 48}
+        pixbit = pix < 7 ? (1u << (8 + pix)) : 0u;
+      }
+      bits = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        uint32_t vm;
-        const float* ptr = chunk_ptr(p, c.pc[i], c.j, vm);
+        bool ok;
+        if (p.mode == CONV_1x1) ok = c.mask[i] & 1u;
+        else if (p.mode == CONV_3x3) ok = (c.mask[i] >> c.tap) & 1u;
+        else ok = ((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pixbit);
         dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c.rok[i] && ((vm >> g8) & 1u)) dst[i] = __ldg(reinterpret_cast<const float4*>(ptr + 4 * g8));
+        if (ok) { dst[i] = __ldg(reinterpret_cast<const float4*>(c.base[i] + c.off + 4 * g8)); bits |= 1u << i; }
       }
     };
 #pragma unroll
     for (int qq = 0; qq < PREFETCH; ++qq) {
-      if (L.t < num_tiles) { load_chunk(L, v[qq]); advance(L); }
+      vbits[qq] = 0;
+      if (L.t < num_tiles) { load_chunk(L, v[qq], vbits[qq]); advance(L); }
     }
     uint32_t g = 0;
-    auto produce = [&](float4 (&buf)[4]) {
+    auto produce = [&](float4 (&buf)[4], uint32_t& bits) {
       const int s = g % NUM_STAGES;
       const uint32_t ph = (g / NUM_STAGES) & 1;
       float4 cur[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) cur[i] = buf[i];
       if (p.pre_scale) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * Sx.j + 4 * g8));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * Sx.j + 4 * g8));
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * sj + 4 * g8));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * sj + 4 * g8));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (Sx.rok[i]) {
+          if ((bits >> i) & 1u) {
             cur[i].x = fmaxf(fmaf(cur[i].x, sc.x, sh.x), 0.f); cur[i].y = fmaxf(fmaf(cur[i].y, sc.y, sh.y), 0.f);
             cur[i].z = fmaxf(fmaf(cur[i].z, sc.z, sh.z), 0.f); cur[i].w = fmaxf(fmaf(cur[i].w, sc.w, sh.w), 0.f);
           }
         }
       }
-      if (L.t < num_tiles) { load_chunk(L, buf); advance(L); }
+      if (L.t < num_tiles) { load_chunk(L, buf, bits); advance(L); }
       mbar_wait(empty(s), ph ^ 1);
+      if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[0 * 512 + g] = clock64();
       uint8_t* a_hi = smem_gen + s * S::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
         const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) << 4);
+        // TF32 split without conversion instructions: the tensor core reads only the top 19 bits of an FP32
+        // word, so hi = x with the low 13 mantissa bits cleared and lo = x - hi (exact) are both full-rate ALU ops.
         float4 hi;
-        hi.x = tf32_rna(cur[i].x); hi.y = tf32_rna(cur[i].y); hi.z = tf32_rna(cur[i].z); hi.w = tf32_rna(cur[i].w);
+        hi.x = __uint_as_float(__float_as_uint(cur[i].x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(cur[i].y) & 0xFFFFE000u);
+        hi.z = __uint_as_float(__float_as_uint(cur[i].z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(cur[i].w) & 0xFFFFE000u);
         *reinterpret_cast<float4*>(a_hi + off) = hi;
         if (passes == 3) {
           float4 lo;
-          lo.x = tf32_rna(cur[i].x - hi.x); lo.y = tf32_rna(cur[i].y - hi.y);
-          lo.z = tf32_rna(cur[i].z - hi.z); lo.w = tf32_rna(cur[i].w - hi.w);
+          lo.x = cur[i].x - hi.x; lo.y = cur[i].y - hi.y; lo.z = cur[i].z - hi.z; lo.w = cur[i].w - hi.w;
           *reinterpret_cast<float4*>(a_lo + off) = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_a(s));
+      if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[1 * 512 + g] = clock64();
       ++g;
-      advance(Sx);
+      if (++sj == nchunks) { sj = 0; st += gridDim.x; }
     };
     static_assert(PREFETCH == 2, "producer loop is unrolled for two register buffers");
-    while (Sx.t < num_tiles) {
-      produce(v[0]);
-      if (Sx.t < num_tiles) produce(v[1]);
+    while (st < num_tiles) {
+      produce(v[0], vbits[0]);
+      if (st < num_tiles) produce(v[1], vbits[1]);
     }
   }
   tc_fence_before();

