@@ -374,6 +374,7 @@ conv_tc_kernel(const ConvParams p, const int passes) {
 //   warps 2..5  epilogue (one TMEM lane quarter each)      warps 6..13 A producers
 // TMEM columns: buffer b in {0,1} at b*2*BN: [main | correction].
 constexpr int P_NUM_THREADS = 32 * (2 + 4 + NUM_PRODUCER_WARPS);
+constexpr int P_PREFETCH = 4;         // chunks of A kept in flight in registers (load latency ~2-3k cycles under load)
 
 template <int BN>
 __global__ void __launch_bounds__(P_NUM_THREADS, 1)
@@ -606,8 +607,8 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     LoadCursor L;
     L.t = blockIdx.x; set_tile(L);
     int st = blockIdx.x, sj = 0;               // store cursor: tile / chunk
-    float4 v[PREFETCH][4];
-    uint32_t vbits[PREFETCH];
+    float4 v[P_PREFETCH][4];
+    uint32_t vbits[P_PREFETCH];
     auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4], uint32_t& bits) {
       uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row this float4 group belongs to
       if (p.mode == CONV_STEM7) {
@@ -627,7 +628,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       }
     };
 #pragma unroll
-    for (int qq = 0; qq < PREFETCH; ++qq) {
+    for (int qq = 0; qq < P_PREFETCH; ++qq) {
       vbits[qq] = 0;
       if (L.t < num_tiles) { load_chunk(L, v[qq], vbits[qq]); advance(L); }
     }
@@ -677,10 +678,12 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       ++g;
       if (++sj == nchunks) { sj = 0; st += gridDim.x; }
     };
-    static_assert(PREFETCH == 2, "producer loop is unrolled for two register buffers");
+    static_assert(P_PREFETCH == 4, "producer loop is unrolled for four register buffers");
     while (st < num_tiles) {
       produce(v[0], vbits[0]);
       if (st < num_tiles) produce(v[1], vbits[1]);
+      if (st < num_tiles) produce(v[2], vbits[2]);
+      if (st < num_tiles) produce(v[3], vbits[3]);
     }
   }
   tc_fence_before();
