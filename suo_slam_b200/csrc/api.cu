@@ -40,9 +40,13 @@ struct NetState {
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
+  // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
+  cudaStream_t side[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> op_done;
 };
 
 struct DevScratch {   // growable device + pinned staging for host-pointer calls
@@ -78,11 +82,33 @@ struct Bump {
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int R = ctx->crop_res;
+  const bool multi = ctx->opt_multistream != 0;
+  auto level_of = [&](const OpDesc& o) { const int d = N.bufs[o.out].div; return !multi ? 0 : (d <= 4 ? 0 : (d == 8 ? 1 : 2)); };
+  cudaStream_t streams[3] = {s, s, s};
+  if (multi) {
+    for (int k = 0; k < 2; ++k)
+      if (!N.side[k]) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&N.side[k], cudaStreamNonBlocking));
+    streams[1] = N.side[0]; streams[2] = N.side[1];
+    if (N.op_done.size() != N.ops.size()) {
+      N.op_done.resize(N.ops.size());
+      for (auto& e : N.op_done) SUO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+  }
+  std::vector<int> writer(N.bufs.size(), -1);
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.variant != 2 && o.variant != variant) continue;
     const BufDesc& bi = N.bufs[o.in];
     const BufDesc& bo = N.bufs[o.out];
+    const int lvl = level_of(o);
+    cudaStream_t st = streams[lvl];
+    if (multi) {
+      const int deps[2] = {o.in, o.res};
+      for (int b : deps) {
+        if (b < 0 || writer[b] < 0) continue;
+        if (level_of(N.ops[writer[b]]) != lvl) SUO_CUDA_TRY(ctx, cudaStreamWaitEvent(st, N.op_done[writer[b]], 0));
+      }
+    }
     int rc = SUO_OK;
     if (o.type == OP_CONV) {
       ConvParams p{};
@@ -98,16 +124,28 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
       p.Ho = R / bo.div; p.Wo = R / bo.div;
       p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
       p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
-      rc = backend == 1 ? launch_conv_tc(ctx, p, passes, s) : launch_conv_simt(ctx, p, s);
+      rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
     } else if (o.type == OP_MAXPOOL) {
-      rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);
+      rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], st);
     } else if (o.type == OP_UPADD) {
-      rc = launch_upsample_add(ctx, N.act[o.in], N.act[o.res], L, R / bo.div, R / bo.div, bo.C, N.act[o.out], s);
+      rc = launch_upsample_add(ctx, N.act[o.in], N.act[o.res], L, R / bo.div, R / bo.div, bo.C, N.act[o.out], st);
     } else {
       ctx->set_error("unknown op type in program", __FILE__, __LINE__);
       return SUO_E_INVALID;
     }
     if (rc != SUO_OK) return rc;
+    writer[o.out] = (int)i;
+    if (multi) {
+      // record completion if a later op on another level stream consumes this output
+      bool cross = false;
+      for (size_t k = i + 1; k < N.ops.size() && !cross; ++k) {
+        const OpDesc& c = N.ops[k];
+        if (c.variant != 2 && c.variant != variant) continue;
+        if ((c.in == o.out || c.res == o.out) && level_of(c) != lvl) cross = true;
+        if (c.out == o.out) break;
+      }
+      if (cross) SUO_CUDA_TRY(ctx, cudaEventRecord(N.op_done[i], st));
+    }
   }
   return SUO_OK;
 }
@@ -116,7 +154,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -177,6 +215,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   // developer overrides (tests run both conv kernel variants through the same ABI)
   if (const char* e = getenv("SUO_CONV_PERSISTENT")) c->opt_persistent = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_USE_GRAPH")) c->opt_graph = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
   *out = c;
   return SUO_OK;
 }
@@ -188,6 +227,8 @@ void suo_destroy(suo_ctx* ctx) {
   if (x) {
     NetState& N = x->net;
     for (auto& kv : N.graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& e : N.op_done) cudaEventDestroy(e);
+    for (auto& st : N.side) if (st) cudaStreamDestroy(st);
     for (float* p : N.packed) if (p) cudaFree(p);
     for (float* p : N.act) if (p) cudaFree(p);
     if (N.pool) cudaFree(N.pool);
@@ -211,6 +252,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_TF32_PASSES: if (value != 1 && value != 3) return SUO_E_INVALID; ctx->opt_passes = value; return SUO_OK;
     case SUO_OPT_USE_GRAPH: ctx->opt_graph = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }

@@ -376,7 +376,51 @@ conv_tc_kernel(const ConvParams p, const int passes) {
 constexpr int P_NUM_THREADS = 32 * (2 + 4 + NUM_PRODUCER_WARPS);
 constexpr int P_PREFETCH = 4;         // chunks of A kept in flight in registers (load latency ~2-3k cycles under load)
 
-template <int BN>
+// ---- A-producer addressing (persistent kernel) -------------------------------------------------------
+// Per tile each producer thread decodes its 4 rows once (out of line: it runs once per ~10-40 chunks and
+// would otherwise be inlined into every unrolled copy of the chunk loop); per chunk only `off`/`tap` move.
+struct LoadCursor {
+  int t, j, tap, cc;                        // tile, chunk, 3x3 tap / stem kernel row, 32-float sub-chunk
+  ptrdiff_t off;                            // running float offset of this chunk from the row base
+  const float* base[4];
+  uint32_t mask[4];                         // 1x1: bit0 = row valid; 3x3: bit t = tap t in bounds; stem: bits0-6 ky ok, bits8-14 pixel ok
+};
+
+template <int MODE>
+__device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p, int M, int num_tiles, int num_n_tiles, int r0) {
+  const int m_tile = c.t / num_n_tiles;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m_tile * BLOCK_M + r0 + 32 * i;
+    const bool ok = (c.t < num_tiles) && (m < M);
+    const PixelCoord pc = decode_pixel(ok ? m : 0, p.Ho, p.Wo);
+    uint32_t msk = 0;
+    if (MODE == CONV_1x1) {
+      c.base[i] = p.in + (size_t)(ok ? m : 0) * p.Cin;
+      msk = ok ? 1u : 0u;
+    } else if (MODE == CONV_3x3) {
+      c.base[i] = p.in + ((size_t)(pc.b * p.H + pc.oy) * p.W + pc.ox) * p.Cin;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int iy = pc.oy + t / 3 - 1, ix = pc.ox + t % 3 - 1;
+        if (ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) msk |= 1u << t;
+      }
+    } else {
+      const int iy0 = 2 * pc.oy - 3, ix0 = 2 * pc.ox - 3;
+      c.base[i] = p.in + ((ptrdiff_t)(pc.b * p.H + iy0) * p.W + ix0) * p.Cin;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        if (ok && iy0 + t >= 0 && iy0 + t < p.H) msk |= 1u << t;
+        if (ok && ix0 + t >= 0 && ix0 + t < p.W) msk |= 1u << (8 + t);
+      }
+    }
+    c.mask[i] = msk;
+  }
+  c.j = 0; c.tap = 0; c.cc = 0;
+  c.off = (MODE == CONV_3x3) ? -(ptrdiff_t)(p.W + 1) * p.Cin : 0;
+}
+
+template <int BN, int MODE, bool PRE>
 __global__ void __launch_bounds__(P_NUM_THREADS, 1)
 conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -549,54 +593,20 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     }
   } else {
     // ===================== A producers =====================
-    // Addressing is hoisted out of the chunk loop: per tile each thread decodes its 4 rows once into a base
-    // pointer + validity bit-mask; per chunk only a shared running offset changes (no divisions per chunk).
     const int pt = threadIdx.x - 192;           // 0..255
     const int g8 = pt & 7;                      // float4 group inside the 128-byte row
     const int r0 = pt >> 3;                     // rows r0 + 32*i
-    struct LoadCursor {
-      int t, j, tap, cc;                        // tile, chunk, 3x3 tap / stem kernel row, 32-float sub-chunk
-      ptrdiff_t off;                            // running float offset of this chunk from the row base
-      const float* base[4];
-      uint32_t mask[4];                         // 1x1: bit0 = row valid; 3x3: bit t = tap t in bounds; stem: bits0-6 ky ok, bits8-14 pixel ok
-    };
     const int cpc = p.Cin >> 5, cpr = p.chunks_per_row;
-    auto set_tile = [&](LoadCursor& c) {
-      const int m_tile = c.t / num_n_tiles;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int m = m_tile * BLOCK_M + r0 + 32 * i;
-        const bool ok = (c.t < num_tiles) && (m < M);
-        const PixelCoord pc = decode_pixel(ok ? m : 0, p.Ho, p.Wo);
-        uint32_t msk = 0;
-        if (p.mode == CONV_1x1) {
-          c.base[i] = p.in + (size_t)(ok ? m : 0) * p.Cin;
-          msk = ok ? 1u : 0u;
-        } else if (p.mode == CONV_3x3) {
-          c.base[i] = p.in + ((size_t)(pc.b * p.H + pc.oy) * p.W + pc.ox) * p.Cin;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int iy = pc.oy + t / 3 - 1, ix = pc.ox + t % 3 - 1;
-            if (ok && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) msk |= 1u << t;
-          }
-        } else {
-          const int iy0 = 2 * pc.oy - 3, ix0 = 2 * pc.ox - 3;
-          c.base[i] = p.in + ((ptrdiff_t)(pc.b * p.H + iy0) * p.W + ix0) * p.Cin;
-#pragma unroll
-          for (int t = 0; t < 7; ++t) {
-            if (ok && iy0 + t >= 0 && iy0 + t < p.H) msk |= 1u << t;
-            if (ok && ix0 + t >= 0 && ix0 + t < p.W) msk |= 1u << (8 + t);
-          }
-        }
-        c.mask[i] = msk;
-      }
-      c.j = 0; c.tap = 0; c.cc = 0;
-      c.off = (p.mode == CONV_3x3) ? -(ptrdiff_t)(p.W + 1) * p.Cin : 0;
-    };
     auto advance = [&](LoadCursor& c) {
-      if (++c.j == nchunks) { c.t += gridDim.x; set_tile(c); return; }
-      if (p.mode == CONV_1x1) { c.off += 32; }
-      else if (p.mode == CONV_3x3) {
+      if (++c.j == nchunks) {      // next tile: decode out of line into a scratch copy so that `c` itself stays in registers
+        LoadCursor tmp;
+        tmp.t = c.t + gridDim.x;
+        cursor_set_tile<MODE>(tmp, p, M, num_tiles, num_n_tiles, r0);
+        c = tmp;
+        return;
+      }
+      if (MODE == CONV_1x1) { c.off += 32; }
+      else if (MODE == CONV_3x3) {
         if (++c.cc == cpc) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)((c.tap / 3 - 1) * p.W + (c.tap % 3 - 1)) * p.Cin; }
         else c.off += 32;
       } else {
@@ -605,26 +615,33 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       }
     };
     LoadCursor L;
-    L.t = blockIdx.x; set_tile(L);
+    {
+      LoadCursor tmp;
+      tmp.t = blockIdx.x;
+      cursor_set_tile<MODE>(tmp, p, M, num_tiles, num_n_tiles, r0);
+      L = tmp;
+    }
     int st = blockIdx.x, sj = 0;               // store cursor: tile / chunk
     float4 v[P_PREFETCH][4];
     uint32_t vbits[P_PREFETCH];
     auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4], uint32_t& bits) {
       uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row this float4 group belongs to
-      if (p.mode == CONV_STEM7) {
+      if (MODE == CONV_STEM7) {
         const int x = 32 * c.cc + 4 * g8;
         const int pix = (p.Cin == 4) ? (x >> 2) : ((x * 1366) >> 16);   // x / Cin for Cin in {4, 48}
         pixbit = pix < 7 ? (1u << (8 + pix)) : 0u;
       }
       bits = 0;
+      const float* __restrict__ q = nullptr;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         bool ok;
-        if (p.mode == CONV_1x1) ok = c.mask[i] & 1u;
-        else if (p.mode == CONV_3x3) ok = (c.mask[i] >> c.tap) & 1u;
+        if (MODE == CONV_1x1) ok = c.mask[i] & 1u;
+        else if (MODE == CONV_3x3) ok = (c.mask[i] >> c.tap) & 1u;
         else ok = ((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pixbit);
         dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) { dst[i] = __ldg(reinterpret_cast<const float4*>(c.base[i] + c.off + 4 * g8)); bits |= 1u << i; }
+        q = c.base[i] + c.off + 4 * g8;
+        if (ok) { dst[i] = __ldg(reinterpret_cast<const float4*>(q)); bits |= 1u << i; }
       }
     };
 #pragma unroll
@@ -633,13 +650,13 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       if (L.t < num_tiles) { load_chunk(L, v[qq], vbits[qq]); advance(L); }
     }
     uint32_t g = 0;
+    int stage = 0;
+    uint32_t phase = 0;
     auto produce = [&](float4 (&buf)[4], uint32_t& bits) {
-      const int s = g % NUM_STAGES;
-      const uint32_t ph = (g / NUM_STAGES) & 1;
       float4 cur[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) cur[i] = buf[i];
-      if (p.pre_scale) {
+      if (PRE) {
         const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * sj + 4 * g8));
         const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * sj + 4 * g8));
 #pragma unroll
@@ -651,9 +668,9 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         }
       }
       if (L.t < num_tiles) { load_chunk(L, buf, bits); advance(L); }
-      mbar_wait(empty(s), ph ^ 1);
+      mbar_wait(empty(stage), phase ^ 1);
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[0 * 512 + g] = clock64();
-      uint8_t* a_hi = smem_gen + s * S::STAGE_BYTES;
+      uint8_t* a_hi = smem_gen + stage * S::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_TILE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -673,9 +690,10 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_a(s));
+      if (lane == 0) mbar_arrive(full_a(stage));
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[1 * 512 + g] = clock64();
       ++g;
+      if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       if (++sj == nchunks) { sj = 0; st += gridDim.x; }
     };
     static_assert(P_PREFETCH == 4, "producer loop is unrolled for four register buffers");
@@ -694,12 +712,12 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
   }
 }
 
-template <int BN>
-int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+template <int BN, int MODE, bool PRE>
+int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
     int dev = 0;
     SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
     SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -708,10 +726,18 @@ int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, num_sms);
-  conv_tc_persistent_kernel<BN><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
+  conv_tc_persistent_kernel<BN, MODE, PRE><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
+}
+
+template <int BN>
+int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false>(ctx, p, passes, s);
+  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false>(ctx, p, passes, s);
+  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true>(ctx, p, passes, s);
+  return launch_persistent_inst<BN, CONV_1x1, false>(ctx, p, passes, s);
 }
 
 template <int BN>
