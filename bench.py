@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--input-sets", type=int, default=3, help="distinct input batches rotated between steps")
     ap.add_argument("--tf32-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--conv-math", default="fp16x3", choices=["fp16x3", "tf32"])
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -196,6 +197,7 @@ def run_native(args):
     model.cuda(local)
     ctx = model.context()
     ctx.set_option(_lib.SUO_OPT_TF32_PASSES, args.tf32_passes)
+    ctx.set_option(_lib.SUO_OPT_CONV_MATH, 1 if args.conv_math == "fp16x3" else 0)
     lib, hdl = _lib.lib(), ctx.handle
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -277,16 +279,23 @@ def run_native(args):
         achieved = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
         h2d = sum(v.numel() * v.element_size() for v in sets_pin[0].values())
         d2h = sum(v.numel() * v.element_size() for v in outs_host.values())
+        if args.conv_math == "fp16x3":
+            dtype_name = "fp16x3 (each FP32 operand split into two FP16 numbers, 22-bit mantissa, FP32 accumulate: fp32-equivalent) convs + f32 reductions + f64 solvers"
+        elif args.tf32_passes == 3:
+            dtype_name = "tf32x3 (3xTF32 split, fp32-equivalent) convs + f32 reductions + f64 solvers"
+        else:
+            dtype_name = "tf32 convs + f32 reductions + f64 solvers"
+        ctx.check(lib.suo_check_range(hdl))       # fp16x3: no activation left the FP16 range during the run
         out = {
             "metric": "frames/sec (8 obj-crops/frame, 640x480)", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32x3 (3xTF32 split, fp32-equivalent) convs + f32 reductions + f64 solvers" if args.tf32_passes == 3 else "tf32 convs + f32 reductions + f64 solvers",
+            "dtype": dtype_name,
             "data": "synthetic (seeded random-init weights, uniform-noise frames)",
             "config": {"workload": "configs[1]: 640x480 frame, 8 crops, 256x256 -> 41x64x64, net+reduce+gating+PnP+single-view BA",
                        "frames_per_step_per_gpu": F, "crops_per_step_per_gpu": L, "parallelism": f"frames sharded over {world} GPU(s), 1 all-gather of pose records/step",
                        "l2": f"{args.input_sets} input sets rotated; per-step activation working set ({L} crops) >> 126 MB L2",
-                       "conv_backend": "tcgen05", "tf32_passes": args.tf32_passes},
+                       "conv_backend": "tcgen05", "conv_math": args.conv_math, "tf32_passes": args.tf32_passes},
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -295,7 +304,7 @@ def run_native(args):
                          "traffic": None, "kernel": "conv_tc_kernel (all conv layers of one forward)",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                          "note": "algorithmic 31.495 GFLOP/crop x crops / summed conv-kernel time (CUDA events per launch, eager pass after the timed region); "
-                                 "3xTF32 issues 3 tf32 MMAs per product, so the hardware ceiling for this kernel is peak/6",
+                                 "each product costs 3 MMAs (fp16x3: 3 f16-kind MMAs -> ceiling peak/3; tf32x3: 3 tf32-kind MMAs -> ceiling peak/6)",
                          "conv_ms_per_step": conv_ms.value, "other_net_ms_per_step": other_ms.value},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -30,7 +30,8 @@ enum {
   SUO_E_INVALID = -1,   /* bad argument / shape */
   SUO_E_CUDA = -2,      /* CUDA runtime error (text in suo_last_error) */
   SUO_E_STATE = -3,     /* e.g. forward before load_weights */
-  SUO_E_NOMEM = -4
+  SUO_E_NOMEM = -4,
+  SUO_E_RANGE = -5      /* fp16x3 conv math saw an activation outside the FP16 range; switch to tf32x3 */
 };
 
 /* Options for suo_set_option */
@@ -39,7 +40,8 @@ enum {
   SUO_OPT_TF32_PASSES = 2,  /* 3 = 3xTF32 split (FP32-equivalent, default), 1 = single-pass TF32 */
   SUO_OPT_USE_GRAPH = 3,    /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
   SUO_OPT_CONV_PERSISTENT = 4, /* 1 = persistent tcgen05 conv kernel with overlapped epilogue (default), 0 = one tile per CTA */
-  SUO_OPT_MULTISTREAM = 5      /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
+  SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
+  SUO_OPT_CONV_MATH = 6        /* 0 = TF32 split (SUO_OPT_TF32_PASSES), 1 = FP16x3 split: x = hi + 2^-11 lo in two FP16 numbers */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */
@@ -61,6 +63,10 @@ long long suo_kernel_launches(const suo_ctx* ctx);
  * `blob` is the packed, BN-folded image produced by suo_slam_b200.weights.pack_state_dict
  * (host pointer, copied). */
 int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes);
+
+/* Synchronises and reports (then clears) the FP16-range flag of the fp16x3 conv math mode: SUO_OK or
+ * SUO_E_RANGE.  Host-pointer calls check it themselves; device-pointer (asynchronous) callers poll it. */
+int suo_check_range(suo_ctx* ctx);
 
 /* ---- network forward ----------------------------------------------------------- */
 /* Replaces PkpNet.forward(images, boxes, prior_kp) (lib/models/pkpnet.py:80-119):
@@ -101,7 +107,7 @@ int suo_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W,
  *   residual [B,Ho,Wo,Cout] or NULL; relu: apply ReLU after bias (before residual is
  *   never needed by the network; residual layers have relu == 0)
  *   ksize in {1,3,7}; stride 1 (ksize 1,3; pad (ksize-1)/2) or 2 (ksize 7, pad 3)
- *   backend: 0 SIMT FP32, 1 tcgen05; tf32_passes as SUO_OPT_TF32_PASSES. */
+ *   backend: 0 SIMT FP32, 1 tcgen05 TF32 (tf32_passes as SUO_OPT_TF32_PASSES), 2 tcgen05 FP16x3. */
 int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin,
                const float* w, const float* bias, int Cout, int ksize, int stride,
                const float* pre_scale, const float* pre_shift, const float* residual, int relu,

@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsuo_b200.so")
 
-SUO_OPT_CONV_BACKEND, SUO_OPT_TF32_PASSES, SUO_OPT_USE_GRAPH, SUO_OPT_CONV_PERSISTENT, SUO_OPT_MULTISTREAM = 1, 2, 3, 4, 5
+SUO_OPT_CONV_BACKEND, SUO_OPT_TF32_PASSES, SUO_OPT_USE_GRAPH, SUO_OPT_CONV_PERSISTENT, SUO_OPT_MULTISTREAM, SUO_OPT_CONV_MATH = 1, 2, 3, 4, 5, 6
 
 _lib = None
 vp = C.c_void_p
@@ -24,7 +24,7 @@ def exported_symbols():
     """Every entry point include/suo_b200.h declares (tests check the .so exports them all)."""
     return ["suo_create", "suo_destroy", "suo_last_error", "suo_set_option", "suo_kernel_launches",
             "suo_load_weights", "suo_forward", "suo_heatmap_reduce", "suo_crop_concat", "suo_conv2d",
-            "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network"]
+            "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range"]
 
 
 def lib():
@@ -55,6 +55,7 @@ def lib():
                                           C.c_uint64, C.c_int, vp, vp, vp, vp, C.c_int, vp]
         L.suo_frames.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_double,
                                  C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [C.c_int, vp]
+        L.suo_check_range.argtypes = [vp]
         L.suo_profile_network.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
         _lib = L
     return _lib

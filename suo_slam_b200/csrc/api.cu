@@ -35,13 +35,15 @@ struct NetState {
   std::vector<BufDesc> bufs;
   std::vector<OpDesc> ops;
   float* pool = nullptr;                     // device float pool (canonical weights, biases, prologues)
-  std::vector<float*> packed;                // per op: tcgen05 weight images (device) or nullptr
+  std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
+  std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
+  int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -124,6 +126,7 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
       p.Ho = R / bo.div; p.Wo = R / bo.div;
       p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
       p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
+      p.math = ctx->opt_math; p.w_packed16 = N.packed16[i]; p.range_flag = N.range_flag;
       rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
     } else if (o.type == OP_MAXPOOL) {
       rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], st);
@@ -154,7 +157,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -216,6 +219,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_CONV_PERSISTENT")) c->opt_persistent = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_USE_GRAPH")) c->opt_graph = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   *out = c;
   return SUO_OK;
 }
@@ -230,6 +234,8 @@ void suo_destroy(suo_ctx* ctx) {
     for (auto& e : N.op_done) cudaEventDestroy(e);
     for (auto& st : N.side) if (st) cudaStreamDestroy(st);
     for (float* p : N.packed) if (p) cudaFree(p);
+    for (uint16_t* p : N.packed16) if (p) cudaFree(p);
+    if (N.range_flag) cudaFree(N.range_flag);
     for (float* p : N.act) if (p) cudaFree(p);
     if (N.pool) cudaFree(N.pool);
     if (N.pooled) cudaFree(N.pooled);
@@ -253,6 +259,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_USE_GRAPH: ctx->opt_graph = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -282,7 +289,9 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   SUO_CUDA_TRY(ctx, cudaMemcpy(N.pool, pool_h, sizeof(float) * (size_t)N.h.n_floats, cudaMemcpyHostToDevice));
   // tensor-core weight images
   N.packed.assign(N.ops.size(), nullptr);
+  N.packed16.assign(N.ops.size(), nullptr);
   std::vector<float> tmp;
+  std::vector<uint16_t> tmp16;
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.type != OP_CONV) continue;
@@ -291,7 +300,16 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
     conv_tc_pack_weights(pool_h + o.w_off, o.Cout_pad, o.K, tmp.data());
     SUO_CUDA_TRY(ctx, cudaMalloc(&N.packed[i], nf * sizeof(float)));
     SUO_CUDA_TRY(ctx, cudaMemcpy(N.packed[i], tmp.data(), nf * sizeof(float), cudaMemcpyHostToDevice));
+    if (o.K % 64 == 0) {
+      const size_t nh = conv_tc_packed16_halfs(o.Cout_pad, o.K);
+      tmp16.resize(nh);
+      conv_tc_pack_weights_f16(pool_h + o.w_off, o.Cout_pad, o.K, tmp16.data());
+      SUO_CUDA_TRY(ctx, cudaMalloc(&N.packed16[i], nh * sizeof(uint16_t)));
+      SUO_CUDA_TRY(ctx, cudaMemcpy(N.packed16[i], tmp16.data(), nh * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
   }
+  SUO_CUDA_TRY(ctx, cudaMalloc(&N.range_flag, sizeof(int)));
+  SUO_CUDA_TRY(ctx, cudaMemset(N.range_flag, 0, sizeof(int)));
   // activation buffers
   N.act.assign(N.bufs.size(), nullptr);
   const int R = ctx->crop_res;
@@ -404,7 +422,7 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   int K, cpr = 0;
   if (p.mode == CONV_1x1) K = Cin;
   else if (p.mode == CONV_3x3) K = 9 * Cin;
-  else { cpr = (7 * Cin + 31) / 32; K = 7 * cpr * 32; }
+  else { cpr = 2 * ((7 * Cin + 63) / 64); K = 7 * cpr * 32; }   // kernel-row stride: multiple of 64 floats (both chunk widths)
   // canonical weights [Cout_pad][K] in gather order from [Cout][kh][kw][Cin]
   std::vector<float> wc((size_t)Cout_pad * K, 0.f), bc(Cout_pad, 0.f);
   for (int co = 0; co < Cout; ++co) {
@@ -421,9 +439,11 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   }
   std::vector<float> wp(conv_tc_packed_floats(Cout_pad, K));
   conv_tc_pack_weights(wc.data(), Cout_pad, K, wp.data());
+  std::vector<uint16_t> wp16;
+  if (K % 64 == 0) { wp16.resize(conv_tc_packed16_halfs(Cout_pad, K)); conv_tc_pack_weights_f16(wc.data(), Cout_pad, K, wp16.data()); }
   const size_t n_in = (size_t)B * H * W * Cin, n_out = (size_t)B * Ho * Wo * Cout;
   CtxExtra* x = X(ctx);
-  rc = x->io.grow(ctx, (n_in + 2 * n_out + wc.size() + wp.size() + bc.size() + 2 * (size_t)Cin) * sizeof(float) + 8192);
+  rc = x->io.grow(ctx, (n_in + 2 * n_out + wc.size() + wp.size() + wp16.size() / 2 + bc.size() + 2 * (size_t)Cin) * sizeof(float) + 16384);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->io.d)};
   float* d_in = bp.take<float>(n_in);
@@ -431,6 +451,8 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   float* d_res = residual ? bp.take<float>(n_out) : nullptr;
   float* d_w = bp.take<float>(wc.size());
   float* d_wp = bp.take<float>(wp.size());
+  uint16_t* d_wp16 = wp16.empty() ? nullptr : bp.take<uint16_t>(wp16.size());
+  int* d_flag = bp.take<int>(1);
   float* d_b = bp.take<float>(bc.size());
   float* d_ps = pre_scale ? bp.take<float>(Cin) : nullptr;
   float* d_pt = pre_scale ? bp.take<float>(Cin) : nullptr;
@@ -438,6 +460,8 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   if (d_res) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_res, residual, n_out * sizeof(float), cudaMemcpyHostToDevice, s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_w, wc.data(), wc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_wp, wp.data(), wp.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (d_wp16) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_wp16, wp16.data(), wp16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_b, bc.data(), bc.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   if (d_ps) {
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_ps, pre_scale, Cin * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -447,9 +471,11 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   p.in = d_in; p.w = d_w; p.w_packed = d_wp; p.bias = d_b; p.pre_scale = d_ps; p.pre_shift = d_pt; p.residual = d_res;
   p.out = d_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cout_pad = Cout_pad;
   p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
+  p.math = backend == 2 ? 1 : 0; p.w_packed16 = d_wp16; p.range_flag = d_flag;
+  if (backend == 2) backend = 1;
   long long* d_dbg = nullptr;
   const char* dbg_path = getenv("SUO_CONV_TIMELINE");
-  if (dbg_path && backend == 1) {
+  if (dbg_path && backend >= 1) {
     SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 5 * 512 * sizeof(long long)));
     SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 5 * 512 * sizeof(long long), s));
     p.dbg = d_dbg;
@@ -477,6 +503,21 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_check_range(suo_ctx* ctx) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!x->loaded || !x->net.range_flag) return SUO_OK;
+  int flag = 0;
+  SUO_CUDA_TRY(ctx, cudaMemcpy(&flag, x->net.range_flag, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    SUO_CUDA_TRY(ctx, cudaMemset(x->net.range_flag, 0, sizeof(int)));
+    ctx->set_error("fp16x3 conv math: an activation exceeded the FP16 range (|x| > 6e4); results are invalid, use SUO_OPT_CONV_MATH = 0 (tf32x3)", __FILE__, __LINE__);
+    return SUO_E_RANGE;
+  }
   return SUO_OK;
 }
 
@@ -539,7 +580,7 @@ int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, cons
   if (logits) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(logits, d_logits, n_hm * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (prob) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(prob, d_prob, n_hm * sizeof(float), cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  return SUO_OK;
+  return suo_check_range(ctx);
 }
 
 int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj, double threshold,
@@ -839,6 +880,7 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
         p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin; p.Ho = R / bo.div; p.Wo = R / bo.div;
         p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode; p.chunks_per_row = o.cpr;
         p.relu = o.relu; p.out_nchw = o.out_nchw;
+        p.math = ctx->opt_math; p.w_packed16 = N.packed16[idx[q]]; p.range_flag = N.range_flag;
         rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
       } else if (o.type == OP_MAXPOOL) {
         rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);

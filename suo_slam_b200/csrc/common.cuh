@@ -56,6 +56,9 @@ struct ConvParams {
   int relu;               // ReLU after bias
   int out_nchw;           // store NCHW planes instead of NHWC
   long long* dbg;         // optional [5][512] clock64 timeline of CTA 0 (tools only), else nullptr
+  const uint16_t* w_packed16;  // tcgen05 fp16x3: per (n_tile, 64-chunk) hi / lo' FP16 images
+  int math;               // 0 = TF32 (1 or 3 passes), 1 = FP16x3 split
+  int* range_flag;        // fp16x3: set to 1 when an operand exceeds the FP16 range
 };
 
 struct suo_ctx;
@@ -65,6 +68,8 @@ int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStrea
 size_t conv_tc_packed_floats(int Cout_pad, int K);
 void conv_tc_pack_weights(const float* w, int Cout_pad, int K, float* dst);
 int conv_tc_block_n(int Cout_pad);
+size_t conv_tc_packed16_halfs(int Cout_pad, int K);
+void conv_tc_pack_weights_f16(const float* w, int Cout_pad, int K, uint16_t* dst);
 
 int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
                           const float* cls_b, float* pooled_scratch, float* uv, float* cov, float* prob,
@@ -107,7 +112,7 @@ struct suo_ctx {
   int max_crops = 0, crop_res = 0, num_kp = 0;
   std::string err;
   long long launches = 0;
-  int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0;
+  int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 0;
   void* net = nullptr;  // NetState (net_exec.cu)
   void* scratch = nullptr; size_t scratch_bytes = 0;        // device scratch for host-pointer calls
   void* pinned = nullptr; size_t pinned_bytes = 0;          // pinned staging

@@ -25,6 +25,7 @@
 //                 operand tiles, fence.proxy.async + mbarrier arrive;
 //                 afterwards the same warps run the epilogue: tcgen05.ld TMEM -> registers,
 //                 + bias, ReLU, + residual, 128-bit stores (NHWC) or coalesced plane stores (NCHW).
+#include <cuda_fp16.h>
 #include <algorithm>
 #include <cstring>
 #include "conv_gather.cuh"
@@ -133,6 +134,25 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 // Instruction descriptor: D = F32, A = B = TF32, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+enum : int { MATH_TF32 = 0, MATH_F16 = 1 };
+// Instruction descriptor: D = F32, A = B = F16, both K-major (kind::f16, K = 16 per instruction).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int MATH>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MATH == MATH_F16) umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 
 template <int BN>
@@ -420,9 +440,15 @@ __device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p,
   c.off = (MODE == CONV_3x3) ? -(ptrdiff_t)(p.W + 1) * p.Cin : 0;
 }
 
-template <int BN, int MODE, bool PRE>
-__global__ void __launch_bounds__(P_NUM_THREADS, 1)
+template <int BN, int MODE, bool PRE, int MATH>
+__global__ void __maxnreg__(144)
 conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
+  // MATH_TF32: chunk = 32 floats, operands FP32 words read as TF32 (hi = top 19 bits, lo = x - hi).
+  // MATH_F16 : chunk = 64 floats, operands FP16: x = hi + 2^-11 lo' with hi = fp16(x with 13 low mantissa bits
+  //            cleared) and lo' = fp16((x - hi) * 2^11): 22 mantissa bits in two FP16 numbers; the correction
+  //            accumulator is scaled by 2^-11 in the epilogue.  Same 128-byte swizzled rows, twice the K per byte.
+  constexpr int KC = (MATH == MATH_F16) ? 64 : 32;       // K elements per chunk
+  constexpr int NV = KC / 32;                            // float4 loads per row per thread per chunk
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -438,7 +464,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B * p.Ho * p.Wo;
-  const int nchunks = p.K / BLOCK_K;
+  const int nchunks = p.K / KC;
   const int num_tiles = num_m_tiles * num_n_tiles;
 
   if (threadIdx.x == 0) {
@@ -477,7 +503,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN);
+    constexpr uint32_t idesc = (MATH == MATH_F16) ? make_idesc_f16(BLOCK_M, BN) : make_idesc_tf32(BLOCK_M, BN);
     uint32_t g = 0, i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const uint32_t b = i & 1;
@@ -500,11 +526,11 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
             const uint64_t dah = make_sw128_desc(a_hi + kk * 32), dbh = make_sw128_desc(b_hi + kk * 32);
-            umma_tf32(acc, dah, dbh, idesc, (j | kk) != 0);
+            umma<MATH>(acc, dah, dbh, idesc, (j | kk) != 0);
             if (passes == 3) {
               const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
-              umma_tf32(acc + BN, dal, dbh, idesc, (j | kk) != 0);
-              umma_tf32(acc + BN, dah, dbl, idesc, 1u);
+              umma<MATH>(acc + BN, dal, dbh, idesc, (j | kk) != 0);
+              umma<MATH>(acc + BN, dah, dbl, idesc, 1u);
             }
           }
           umma_commit(empty(s));
@@ -534,8 +560,9 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
           uint32_t rc[32];
           tmem_ld32(acc + (uint32_t)(BN + col), rc);
           tmem_ld_wait();
+          constexpr float kCorrScale = (MATH == MATH_F16) ? (1.0f / 2048.0f) : 1.0f;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(rc[c]));
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaf(__uint_as_float(rc[c]), kCorrScale, __uint_as_float(r[c])));
         }
         if (col + 32 >= BN) {                      // last TMEM read of this tile: hand the buffer back to the MMA warp
           tc_fence_before();
@@ -596,7 +623,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     const int pt = threadIdx.x - 192;           // 0..255
     const int g8 = pt & 7;                      // float4 group inside the 128-byte row
     const int r0 = pt >> 3;                     // rows r0 + 32*i
-    const int cpc = p.Cin >> 5, cpr = p.chunks_per_row;
+    const int cpc = p.Cin / KC, cpr = p.chunks_per_row * 32 / KC;     // sub-chunks per tap / per stem kernel row
     auto advance = [&](LoadCursor& c) {
       if (++c.j == nchunks) {      // next tile: decode out of line into a scratch copy so that `c` itself stays in registers
         LoadCursor tmp;
@@ -605,13 +632,13 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         c = tmp;
         return;
       }
-      if (MODE == CONV_1x1) { c.off += 32; }
+      if (MODE == CONV_1x1) { c.off += KC; }
       else if (MODE == CONV_3x3) {
         if (++c.cc == cpc) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)((c.tap / 3 - 1) * p.W + (c.tap % 3 - 1)) * p.Cin; }
-        else c.off += 32;
+        else c.off += KC;
       } else {
         if (++c.cc == cpr) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)c.tap * p.W * p.Cin; }
-        else c.off += 32;
+        else c.off += KC;
       }
     };
     LoadCursor L;
@@ -622,48 +649,63 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       L = tmp;
     }
     int st = blockIdx.x, sj = 0;               // store cursor: tile / chunk
-    float4 v[P_PREFETCH][4];
-    uint32_t vbits[P_PREFETCH];
-    auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4], uint32_t& bits) {
-      uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row this float4 group belongs to
+    constexpr int PF = (MATH == MATH_F16) ? 2 : P_PREFETCH;       // register prefetch depth (same bytes in flight)
+    float4 v[PF][4 * NV];
+    uint32_t vbits[PF];
+    auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4 * NV], uint32_t& bits) {
+      // this thread's K elements of the chunk: [ (KC/8) * g8, +KC/8 ) -> one 16-byte slot of the 128-byte operand row
+      uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row these elements belong to
       if (MODE == CONV_STEM7) {
-        const int x = 32 * c.cc + 4 * g8;
+        const int x = KC * c.cc + (KC / 8) * g8;
         const int pix = (p.Cin == 4) ? (x >> 2) : ((x * 1366) >> 16);   // x / Cin for Cin in {4, 48}
         pixbit = pix < 7 ? (1u << (8 + pix)) : 0u;
       }
       bits = 0;
-      const float* __restrict__ q = nullptr;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         bool ok;
         if (MODE == CONV_1x1) ok = c.mask[i] & 1u;
         else if (MODE == CONV_3x3) ok = (c.mask[i] >> c.tap) & 1u;
         else ok = ((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pixbit);
-        dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        q = c.base[i] + c.off + 4 * g8;
-        if (ok) { dst[i] = __ldg(reinterpret_cast<const float4*>(q)); bits |= 1u << i; }
+        const float* __restrict__ q = c.base[i] + c.off + (KC / 8) * g8;
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+          dst[i * NV + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (MODE == CONV_STEM7 && NV == 2 && u == 1 && p.Cin == 4) {
+            // 4-float pixels: the second float4 is the NEXT pixel of the kernel row
+            const uint32_t pb2 = (pixbit << 1) & 0x7F00u;
+            if (((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pb2)) dst[i * NV + u] = __ldg(reinterpret_cast<const float4*>(q) + u);
+          } else if (ok) {
+            dst[i * NV + u] = __ldg(reinterpret_cast<const float4*>(q) + u);
+          }
+        }
+        if (ok) bits |= 1u << i;
       }
     };
 #pragma unroll
-    for (int qq = 0; qq < P_PREFETCH; ++qq) {
+    for (int qq = 0; qq < PF; ++qq) {
       vbits[qq] = 0;
       if (L.t < num_tiles) { load_chunk(L, v[qq], vbits[qq]); advance(L); }
     }
     uint32_t g = 0;
     int stage = 0;
     uint32_t phase = 0;
-    auto produce = [&](float4 (&buf)[4], uint32_t& bits) {
-      float4 cur[4];
+    auto produce = [&](float4 (&buf)[4 * NV], uint32_t& bits) {
+      float4 cur[4 * NV];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) cur[i] = buf[i];
+      for (int i = 0; i < 4 * NV; ++i) cur[i] = buf[i];
       if (PRE) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + 32 * sj + 4 * g8));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + 32 * sj + 4 * g8));
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if ((bits >> i) & 1u) {
-            cur[i].x = fmaxf(fmaf(cur[i].x, sc.x, sh.x), 0.f); cur[i].y = fmaxf(fmaf(cur[i].y, sc.y, sh.y), 0.f);
-            cur[i].z = fmaxf(fmaf(cur[i].z, sc.z, sh.z), 0.f); cur[i].w = fmaxf(fmaf(cur[i].w, sc.w, sh.w), 0.f);
+        for (int u = 0; u < NV; ++u) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + KC * sj + (KC / 8) * g8) + u);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + KC * sj + (KC / 8) * g8) + u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if ((bits >> i) & 1u) {
+              float4& x = cur[i * NV + u];
+              x.x = fmaxf(fmaf(x.x, sc.x, sh.x), 0.f); x.y = fmaxf(fmaf(x.y, sc.y, sh.y), 0.f);
+              x.z = fmaxf(fmaf(x.z, sc.z, sh.z), 0.f); x.w = fmaxf(fmaf(x.w, sc.w, sh.w), 0.f);
+            }
           }
         }
       }
@@ -672,22 +714,44 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[0 * 512 + g] = clock64();
       uint8_t* a_hi = smem_gen + stage * S::STAGE_BYTES;
       uint8_t* a_lo = a_hi + A_TILE_BYTES;
+      float amax = 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = r0 + 32 * i;
         const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) << 4);
-        // TF32 split without conversion instructions: the tensor core reads only the top 19 bits of an FP32
-        // word, so hi = x with the low 13 mantissa bits cleared and lo = x - hi (exact) are both full-rate ALU ops.
-        float4 hi;
-        hi.x = __uint_as_float(__float_as_uint(cur[i].x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(cur[i].y) & 0xFFFFE000u);
-        hi.z = __uint_as_float(__float_as_uint(cur[i].z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(cur[i].w) & 0xFFFFE000u);
-        *reinterpret_cast<float4*>(a_hi + off) = hi;
-        if (passes == 3) {
-          float4 lo;
-          lo.x = cur[i].x - hi.x; lo.y = cur[i].y - hi.y; lo.z = cur[i].z - hi.z; lo.w = cur[i].w - hi.w;
-          *reinterpret_cast<float4*>(a_lo + off) = lo;
+        if (MATH == MATH_F16) {
+          // hi = x with the 13 low mantissa bits cleared (exactly an FP16 number inside FP16's normal range),
+          // lo' = (x - hi) * 2^11 (exact in FP32, rounded once to FP16): x = hi + 2^-11 lo' to ~22 bits.
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 x = cur[i * NV + (NV == 2 ? u : 0)];
+            const float h0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            const float h2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+            __half2 a = __floats2half2_rn(h0, h1), b = __floats2half2_rn(h2, h3);
+            __half2 c = __floats2half2_rn((x.x - h0) * 2048.f, (x.y - h1) * 2048.f), d = __floats2half2_rn((x.z - h2) * 2048.f, (x.w - h3) * 2048.f);
+            hw[2 * u] = *reinterpret_cast<uint32_t*>(&a); hw[2 * u + 1] = *reinterpret_cast<uint32_t*>(&b);
+            lw[2 * u] = *reinterpret_cast<uint32_t*>(&c); lw[2 * u + 1] = *reinterpret_cast<uint32_t*>(&d);
+          }
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (passes == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        } else {
+          // TF32 split without conversion instructions: the tensor core reads only the top 19 bits of an FP32
+          // word, so hi = x with the low 13 mantissa bits cleared and lo = x - hi (exact) are full-rate ALU ops.
+          const float4 x = cur[i * NV];
+          float4 hi;
+          hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          *reinterpret_cast<float4*>(a_hi + off) = hi;
+          if (passes == 3) {
+            float4 lo;
+            lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+            *reinterpret_cast<float4*>(a_lo + off) = lo;
+          }
         }
       }
+      if (MATH == MATH_F16 && amax > 60000.f && p.range_flag) *p.range_flag = 1;   // FP16 operand range exceeded: caller must use tf32x3
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_a(stage));
@@ -696,12 +760,14 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       if (++sj == nchunks) { sj = 0; st += gridDim.x; }
     };
-    static_assert(P_PREFETCH == 4, "producer loop is unrolled for four register buffers");
+    static_assert(P_PREFETCH == 4, "producer loop is unrolled for four (TF32) / two (FP16) register buffers");
     while (st < num_tiles) {
       produce(v[0], vbits[0]);
       if (st < num_tiles) produce(v[1], vbits[1]);
-      if (st < num_tiles) produce(v[2], vbits[2]);
-      if (st < num_tiles) produce(v[3], vbits[3]);
+      if (PF == 4) {
+        if (st < num_tiles) produce(v[PF - 2], vbits[PF - 2]);
+        if (st < num_tiles) produce(v[PF - 1], vbits[PF - 1]);
+      }
     }
   }
   tc_fence_before();
@@ -712,12 +778,12 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
   }
 }
 
-template <int BN, int MODE, bool PRE>
+template <int BN, int MODE, bool PRE, int MATH>
 int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
     int dev = 0;
     SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
     SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -726,18 +792,18 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, num_sms);
-  conv_tc_persistent_kernel<BN, MODE, PRE><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
+  conv_tc_persistent_kernel<BN, MODE, PRE, MATH><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
 }
 
-template <int BN>
+template <int BN, int MATH>
 int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
-  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false>(ctx, p, passes, s);
-  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false>(ctx, p, passes, s);
-  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true>(ctx, p, passes, s);
-  return launch_persistent_inst<BN, CONV_1x1, false>(ctx, p, passes, s);
+  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH>(ctx, p, passes, s);
+  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH>(ctx, p, passes, s);
+  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH>(ctx, p, passes, s);
+  return launch_persistent_inst<BN, CONV_1x1, false, MATH>(ctx, p, passes, s);
 }
 
 template <int BN>
@@ -792,6 +858,71 @@ void conv_tc_pack_weights(const float* w, int Cout_pad, int K, float* dst) {
     }
 }
 
+namespace {
+inline uint16_t host_f32_to_f16_rn(float f) {       // IEEE round-to-nearest-even, handles subnormals; no NaN inputs expected
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((x >> 23) & 0xFF) - 127 + 15;
+  uint32_t m = x & 0x7FFFFFu;
+  if (e >= 31) return (uint16_t)(sign | 0x7C00u);                    // overflow -> inf
+  if (e <= 0) {
+    if (e < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const int shift = 14 - e;
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;
+  return (uint16_t)(sign | h);
+}
+inline float host_f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1F, m = h & 0x3FFu, x;
+  if (e == 0) {
+    if (m == 0) x = sign;
+    else { int sh = 0; while (!(m & 0x400u)) { m <<= 1; ++sh; } m &= 0x3FFu; x = sign | ((uint32_t)(127 - 15 - sh + 1) << 23) | (m << 13); }
+  } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
+  else x = sign | ((e - 15 + 127) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+}  // namespace
+
+size_t conv_tc_packed16_halfs(int Cout_pad, int K) { return (size_t)Cout_pad * K * 2; }
+
+// FP16x3 weight images: per (n_tile, 64-element chunk): hi image then lo' image, BN rows x 128 B, 128B swizzle.
+// w = hi + 2^-11 lo'  with hi = fp16(w with the 13 low mantissa bits cleared), lo' = fp16((w - hi) * 2^11).
+void conv_tc_pack_weights_f16(const float* w, int Cout_pad, int K, uint16_t* dst) {
+  const int BN = conv_tc_block_n(Cout_pad);
+  const int nchunks = K / 64;
+  for (int nt = 0; nt < Cout_pad / BN; ++nt)
+    for (int j = 0; j < nchunks; ++j) {
+      uint16_t* img = dst + ((size_t)nt * nchunks + j) * 2 * (BN * 64);
+      for (int r = 0; r < BN; ++r)
+        for (int g = 0; g < 8; ++g)
+          for (int e = 0; e < 8; ++e) {
+            const float x = w[(size_t)(nt * BN + r) * K + 64 * j + 8 * g + e];
+            uint32_t u;
+            memcpy(&u, &x, 4);
+            u &= 0xFFFFE000u;
+            float ht;
+            memcpy(&ht, &u, 4);
+            const uint16_t hi = host_f32_to_f16_rn(ht);
+            const float hif = host_f16_to_f32(hi);
+            const uint16_t lo = host_f32_to_f16_rn((x - hif) * 2048.0f);
+            const int off = (r >> 3) * 512 + (r & 7) * 64 + ((g ^ (r & 7)) << 3) + e;     // in halfs
+            img[off] = hi;
+            img[BN * 64 + off] = lo;
+          }
+    }
+}
+
 int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s) {
   if (p.K % BLOCK_K || p.Cin % 4 || p.Cout_pad % 64 || (!p.out_nchw && (p.Cout % 4 || p.out_c % 4)) ||
       (p.mode != CONV_STEM7 && p.Cin % 32)) {
@@ -800,8 +931,15 @@ int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStrea
   }
   const int passes = tf32_passes == 1 ? 1 : 3;
   if (ctx->opt_persistent) {
-    if (conv_tc_block_n(p.Cout_pad) == 128) return launch_persistent<128>(ctx, p, passes, s);
-    return launch_persistent<64>(ctx, p, passes, s);
+    if (p.math == MATH_F16) {
+      if (p.K % 64 || !p.w_packed16) { ctx->set_error("conv_tc fp16x3: K % 64 != 0 or weights not packed", __FILE__, __LINE__); return SUO_E_INVALID; }
+      ConvParams q = p;
+      q.w_packed = reinterpret_cast<const float*>(p.w_packed16);
+      if (conv_tc_block_n(p.Cout_pad) == 128) return launch_persistent<128, MATH_F16>(ctx, q, passes, s);
+      return launch_persistent<64, MATH_F16>(ctx, q, passes, s);
+    }
+    if (conv_tc_block_n(p.Cout_pad) == 128) return launch_persistent<128, MATH_TF32>(ctx, p, passes, s);
+    return launch_persistent<64, MATH_TF32>(ctx, p, passes, s);
   }
   if (conv_tc_block_n(p.Cout_pad) == 128) return launch_bn<128>(ctx, p, passes, s);
   return launch_bn<64>(ctx, p, passes, s);

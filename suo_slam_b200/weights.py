@@ -85,14 +85,14 @@ class _Builder:
             wk[:Cout, :, :Cin] = w.transpose(0, 2, 3, 1).reshape(Cout, 9, Cin)
             wk = wk.reshape(Cout_pad, K)
         else:
-            cpr = -(-7 * cin_store // 32)
+            cpr = 2 * -(-7 * cin_store // 64)      # kernel-row stride: a multiple of 64 floats (TF32 and FP16 chunk widths)
             K = 7 * cpr * 32
             wk = np.zeros((Cout_pad, 7, cpr * 32))
             row = np.zeros((Cout, 7, 7, cin_store))
             row[:, :, :, :Cin] = w.transpose(0, 2, 3, 1)
             wk[:Cout, :, :7 * cin_store] = row.reshape(Cout, 7, 7 * cin_store)
             wk = wk.reshape(Cout_pad, K)
-        assert K % 32 == 0, (K, mode)
+        assert K % 64 == 0, (K, mode)
         bk = np.zeros(Cout_pad)
         bk[:Cout] = b
         w_off, b_off = self.put(wk), self.put(bk)

@@ -17,9 +17,12 @@ def sd():
 
 
 def _model(sd, backend, passes, res=64, max_crops=8):
+    """backend 0 = SIMT FP32, 1 = tcgen05 TF32 (passes 1|3), 2 = tcgen05 FP16x3"""
     m = PkpNet(input_res=(res, res), max_crops=max_crops)
     m.load_state_dict(sd)
     m.cuda().eval()
+    m.context().set_option(_lib.SUO_OPT_CONV_MATH, 1 if backend == 2 else 0)
+    backend = min(backend, 1)
     m.context().set_option(_lib.SUO_OPT_CONV_BACKEND, backend)
     m.context().set_option(_lib.SUO_OPT_TF32_PASSES, passes)
     return m
@@ -34,7 +37,7 @@ def _margin_ok(logits, argmax, err):
     return decisive, ref_idx
 
 
-@pytest.mark.parametrize("backend,passes,tol_logit,tol_uv", [(0, 3, 2e-4, 2e-5), (1, 3, 3e-4, 5e-5), (1, 1, 0.3, 2e-2)])
+@pytest.mark.parametrize("backend,passes,tol_logit,tol_uv", [(0, 3, 2e-4, 2e-5), (1, 3, 3e-4, 5e-5), (1, 1, 0.3, 2e-2), (2, 3, 3e-4, 5e-5)])
 @pytest.mark.parametrize("name", ["net_small", "net_prior"])
 def test_forward_vs_reference_golden(golden_dir, sd, name, backend, passes, tol_logit, tol_uv):
     g = np.load(f"{golden_dir}/{name}.npz")
@@ -71,17 +74,19 @@ def test_forward_host_tensors_and_graph_replay(sd, golden_dir):
     assert m.context().kernel_launches() > 400
 
 
-def test_forward_256_vs_oracle(sd):
+@pytest.mark.parametrize("backend", [1, 2])
+def test_forward_256_vs_oracle(sd, backend):
     """BASELINE config-2 shape: 8 crops of a 640x480 frame at 256x256 -> 64x64 heat-maps."""
     fr = synth.make_frame(1)
     img = torch.from_numpy(fr["img"].transpose(2, 0, 1).astype(np.float32) / 255)[None]
     boxes = torch.from_numpy(np.stack([o["bbox"] for o in fr["objs"]]))
-    m = _model(sd, 1, 3, res=256, max_crops=8)
+    m = _model(sd, backend, 3, res=256, max_crops=8)
     out = m(img.cuda(), [boxes.cuda()], None)
     torch.cuda.synchronize()
     ref = net_oracle.pkpnet_forward(sd, img, [boxes], None, (256, 256))
     lg, lr = out["prob_logits"].cpu().numpy(), ref["prob_logits"].numpy()
     err = np.abs(lg - lr).max()
+    print(f"[256 backend={backend}] max|dlogit|={err:.3e} max|duv|={np.abs(out['uv'].cpu().numpy() - ref['uv'].numpy()).max():.3e}")
     assert err < 5e-4 * max(1.0, np.abs(lr).max() / 10), err
     np.testing.assert_allclose(out["uv"].cpu().numpy(), ref["uv"].numpy(), atol=5e-5)
     np.testing.assert_allclose(out["cov"].cpu().numpy(), ref["cov"].numpy(), atol=5e-5)
@@ -100,7 +105,7 @@ def test_forward_tless_shape_with_priors(sd):
     for k in range(0, 41, 3):                       # object 1 "symmetric": Gaussian blobs on a third of the planes
         cy, cx = rng.uniform(60, 450, 2)
         prior[1, k] = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * 14.0 ** 2))
-    m = _model(sd, 1, 3, res=512, max_crops=2)
+    m = _model(sd, 2, 3, res=512, max_crops=2)
     out = m(img.cuda(), [boxes.cuda()], [prior.cuda()])
     torch.cuda.synchronize()
     ref = net_oracle.pkpnet_forward(sd, img, [boxes], [prior], (512, 512))

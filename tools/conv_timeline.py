@@ -14,7 +14,7 @@ rng = np.random.default_rng(0)
 for (B, H, W, Cin, Cout, ks) in [(64, 4, 4, 128, 128, 3), (64, 64, 64, 128, 128, 3), (64, 64, 64, 256, 128, 1), (64, 64, 64, 128, 256, 1)]:
     x = rng.normal(size=(B, H, W, Cin)).astype(np.float32)
     w = (rng.normal(size=(Cout, ks, ks, Cin)) / np.sqrt(ks * ks * Cin)).astype(np.float32)
-    for passes in (3, 1):
-        pkpnet.conv2d(ctx, x, w, None, ks, 1, None, None, False, backend=1, tf32_passes=passes)
-        pkpnet.conv2d(ctx, x, w, None, ks, 1, None, None, False, backend=1, tf32_passes=passes)
+    for backend, passes in ((2, 3), (1, 3)):
+        pkpnet.conv2d(ctx, x, w, None, ks, 1, None, None, False, backend=backend, tf32_passes=passes)
+        pkpnet.conv2d(ctx, x, w, None, ks, 1, None, None, False, backend=backend, tf32_passes=passes)
 print("wrote", out)

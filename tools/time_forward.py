@@ -17,19 +17,20 @@ def main():
         n_img = L // 8
         imgs = torch.rand(n_img, 3, 480, 640, device="cuda")
         boxes = [torch.tensor([[50.0 + 10 * i, 40.0 + 5 * i, 250.0 + 20 * i, 300.0 + 10 * i] for i in range(8)], device="cuda") for _ in range(n_img)]
-        for backend, passes in ((1, 3), (1, 1), (0, 3)):
+        for backend, passes in ((2, 3), (1, 3), (1, 1)):
             m = PkpNet(max_crops=L)
             m.return_prob = False
             m.load_state_dict(sd)
             m.cuda()
             ctx = m.context()
-            ctx.set_option(_lib.SUO_OPT_CONV_BACKEND, backend)
+            ctx.set_option(_lib.SUO_OPT_CONV_MATH, 1 if backend == 2 else 0)
+            ctx.set_option(_lib.SUO_OPT_CONV_BACKEND, min(backend, 1))
             ctx.set_option(_lib.SUO_OPT_TF32_PASSES, passes)
             for _ in range(3):
                 m(imgs, boxes)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 5 if backend == 1 else 2
+            n = 5 if backend >= 1 else 2
             e0.record()
             for _ in range(n):
                 m(imgs, boxes)
