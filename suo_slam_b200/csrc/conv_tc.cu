@@ -441,7 +441,8 @@ __device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p,
 }
 
 template <int BN, int MODE, bool PRE, int MATH>
-__global__ void __maxnreg__(144)
+// 14 warps -> one SMSP hosts 4 of them -> the 16K-register SMSP file caps every thread at 128 registers
+__global__ void __launch_bounds__(P_NUM_THREADS, 1)
 conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
   // MATH_TF32: chunk = 32 floats, operands FP32 words read as TF32 (hi = top 19 bits, lo = x - hi).
   // MATH_F16 : chunk = 64 floats, operands FP16: x = hi + 2^-11 lo' with hi = fp16(x with 13 low mantissa bits
