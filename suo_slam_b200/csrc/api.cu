@@ -476,8 +476,8 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   long long* d_dbg = nullptr;
   const char* dbg_path = getenv("SUO_CONV_TIMELINE");
   if (dbg_path && backend >= 1) {
-    SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 5 * 512 * sizeof(long long)));
-    SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 5 * 512 * sizeof(long long), s));
+    SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 13 * 512 * sizeof(long long)));
+    SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 13 * 512 * sizeof(long long), s));
     p.dbg = d_dbg;
   }
   cudaEvent_t e0, e1;
@@ -487,15 +487,18 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   cudaEventRecord(e1, s);
   if (rc) return rc;
   if (d_dbg) {
-    std::vector<long long> h(5 * 512);
+    std::vector<long long> h(13 * 512);
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
     SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     if (FILE* f = fopen(dbg_path, "a")) {
       fprintf(f, "# B=%d H=%d W=%d Cin=%d Cout=%d k=%d passes=%d kernel_ms=%.4f\n", B, H, W, Cin, Cout, ksize, tf32_passes, ms);
-      fprintf(f, "g,prod_slot_free,prod_arrived,mma_full_a,mma_full_b,w_slot_free\n");
-      for (int g = 0; g < 512 && h[g]; ++g)
-        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld\n", g, h[g] - h[0], h[512 + g] - h[0], h[1024 + g] - h[0], h[1536 + g] - h[0], h[2048 + g] - h[0]);
+      fprintf(f, "g,prod_slot_free,prod_arrived,mma_full_a,mma_full_b,w_slot_free,pw0,pw1,pw2,pw3,pw4,pw5,pw6,pw7\n");
+      for (int g = 0; g < 512 && h[g]; ++g) {
+        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld", g, h[g] - h[0], h[512 + g] - h[0], h[1024 + g] - h[0], h[1536 + g] - h[0], h[2048 + g] - h[0]);
+        for (int w = 0; w < 8; ++w) fprintf(f, ",%lld", h[(5 + w) * 512 + g] - h[0]);
+        fprintf(f, "\n");
+      }
       fclose(f);
     }
     cudaFree(d_dbg);

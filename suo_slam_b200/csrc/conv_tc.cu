@@ -64,6 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 // long waits (epilogue waiting for a whole main loop): back off so the spin does not steal issue slots
+template <int NS = 64>
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   uint32_t done;
   while (true) {
@@ -74,7 +75,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     if (done) break;
-    __nanosleep(64);
+    __nanosleep(NS);
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -494,7 +495,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         for (int j = 0; j < nchunks; ++j, ++g) {
           const int s = g % NUM_STAGES;
           const uint32_t ph = (g / NUM_STAGES) & 1;
-          mbar_wait(empty(s), ph ^ 1);
+          mbar_wait_backoff<32>(empty(s), ph ^ 1);     // single polling lane, but it shares an SMSP with two A-producer warps
           if (p.dbg && blockIdx.x == 0 && g < 512) p.dbg[4 * 512 + g] = clock64();
           const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
           mbar_arrive_expect_tx(full_b(s), nbytes);
@@ -508,15 +509,15 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     uint32_t g = 0, i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const uint32_t b = i & 1;
-      mbar_wait(tmem_empty(b), ((i >> 1) & 1) ^ 1);        // epilogue has drained this accumulator buffer
+      mbar_wait_backoff<32>(tmem_empty(b), ((i >> 1) & 1) ^ 1);        // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t acc = tmem_base + b * 2 * BN;
       for (int j = 0; j < nchunks; ++j, ++g) {
         const int s = g % NUM_STAGES;
         const uint32_t ph = (g / NUM_STAGES) & 1;
-        mbar_wait(full_a(s), ph);
+        mbar_wait_backoff<20>(full_a(s), ph);          // polite polling: this warp shares its SMSP with two A-producer warps
         if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[2 * 512 + g] = clock64();
-        mbar_wait(full_b(s), ph);
+        mbar_wait_backoff<20>(full_b(s), ph);
         if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[3 * 512 + g] = clock64();
         tc_fence_after();
         if (lane == 0) {
@@ -757,6 +758,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
       __syncwarp();
       if (lane == 0) mbar_arrive(full_a(stage));
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[1 * 512 + g] = clock64();
+      if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[(5 + warp - 6) * 512 + g] = clock64();
       ++g;
       if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
       if (++sj == nchunks) { sj = 0; st += gridDim.x; }

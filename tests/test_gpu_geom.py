@@ -188,3 +188,68 @@ def test_solve_keypoints_vs_oracle():
         Tgt = synth.make_frame(100 + f, n_obj=L_per)["objs"][o]["T_OtoC"]
         terr.append(np.linalg.norm(got["T_ba"][c][:, 3] - Tgt[:3, 3]) / np.linalg.norm(Tgt[:3, 3]))
     assert np.median(terr) < 0.05
+
+
+def test_g2o_shim_runs_the_reference_optimize_flow():
+    """The reference's own optimize() body (lib/object_slam.py:706-896, single-view: objects free, camera
+    fixed) driven through the ``g2o`` drop-in module, against the oracle's restatement of the same flow."""
+    from suo_slam_b200 import g2o
+    n_obj, n_kp = 6, 12
+    pr = synth.make_ba_problem(21, n_obj, n_kp, noise_px=0.7, outlier_frac=0.1)
+    pr["T_init"] = pr["T_gt"].copy()
+    pr["T_init"][:, :, 3] += np.random.default_rng(1).normal(scale=0.5, size=(n_obj, 3))
+    optimizer = g2o.SparseOptimizer()
+    optimizer.set_algorithm(g2o.OptimizationAlgorithmLevenberg(g2o.BlockSolverSE3(g2o.LinearSolverCholmodSE3())))
+    obj_v = []
+    for j in range(n_obj):
+        v = g2o.VertexSE3Expmap()
+        v.set_id(j)
+        v.set_estimate(g2o.SE3Quat(pr["T_init"][j][:, :3], pr["T_init"][j][:, 3]))
+        optimizer.add_vertex(v)
+        obj_v.append(v)
+    cam = g2o.VertexSE3Expmap()
+    cam.set_id(n_obj)
+    cam.set_estimate(g2o.SE3Quat(np.eye(3), np.zeros(3)))
+    cam.set_fixed(True)
+    optimizer.add_vertex(cam)
+    edges, inl = [], np.ones(n_obj * n_kp, bool)
+    for j in range(n_obj):
+        for k in range(n_kp):
+            e = g2o.EdgeSE3ProjectFromObject(pr["cam_k"], pr["p_O"][j, k])
+            e.set_vertex(0, obj_v[j]); e.set_vertex(1, cam)
+            e.set_measurement(pr["uv"][j, k]); e.set_information(pr["info"][j, k])
+            e.set_robust_kernel(g2o.RobustKernelHuber(np.sqrt(5.991)))
+            e.set_level(0)
+            edges.append(e); optimizer.add_edge(e)
+    its = [10] * 4
+    num_good = 0
+    for i, e in enumerate(edges):                       # :856-866
+        e.compute_error()
+        if e.chi2() > 5.991:
+            e.set_level(1); inl[i] = False
+        else:
+            num_good += 1; e.set_level(0); inl[i] = True
+    for it in range(len(its)):                          # :868-896
+        if len(optimizer.edges()) < 4 or num_good < 4:
+            break
+        optimizer.initialize_optimization(0)
+        optimizer.set_verbose(False)
+        optimizer.optimize(its[it])
+        num_good = 0
+        for i, e in enumerate(edges):
+            if not inl[i]:
+                e.compute_error()
+            if e.chi2() > 5.991:
+                e.set_level(1); inl[i] = False
+            else:
+                num_good += 1; e.set_level(0); inl[i] = True
+            if it == max(1, len(its) // 2):
+                e.set_robust_kernel(None)
+    got = np.stack([v.estimate().matrix()[:3] for v in obj_v])
+    poses, fixed, e_obj, e_cam, cam_k, _, _ = _pack(pr, n_obj, n_kp, False)
+    Po, io, _ = geom.ba_optimize(poses, fixed, e_obj, e_cam, cam_k, pr["p_O"], pr["uv"], pr["info"], np.ones(n_obj * n_kp), its)
+    assert np.array_equal(inl, io)
+    np.testing.assert_allclose(got, Po[:n_obj], rtol=1e-6, atol=1e-5)
+    with pytest.raises(NotImplementedError):            # free camera + free objects: row f3
+        cam.set_fixed(False)
+        optimizer.optimize(1)
