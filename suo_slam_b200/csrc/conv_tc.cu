@@ -495,7 +495,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         for (int j = 0; j < nchunks; ++j, ++g) {
           const int s = g % NUM_STAGES;
           const uint32_t ph = (g / NUM_STAGES) & 1;
-          mbar_wait_backoff<32>(empty(s), ph ^ 1);     // single polling lane, but it shares an SMSP with two A-producer warps
+          mbar_wait(empty(s), ph ^ 1);
           if (p.dbg && blockIdx.x == 0 && g < 512) p.dbg[4 * 512 + g] = clock64();
           const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
           mbar_arrive_expect_tx(full_b(s), nbytes);
@@ -509,15 +509,15 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     uint32_t g = 0, i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const uint32_t b = i & 1;
-      mbar_wait_backoff<32>(tmem_empty(b), ((i >> 1) & 1) ^ 1);        // epilogue has drained this accumulator buffer
+      mbar_wait(tmem_empty(b), ((i >> 1) & 1) ^ 1);        // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t acc = tmem_base + b * 2 * BN;
       for (int j = 0; j < nchunks; ++j, ++g) {
         const int s = g % NUM_STAGES;
         const uint32_t ph = (g / NUM_STAGES) & 1;
-        mbar_wait_backoff<20>(full_a(s), ph);          // polite polling: this warp shares its SMSP with two A-producer warps
+        mbar_wait(full_a(s), ph);
         if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[2 * 512 + g] = clock64();
-        mbar_wait_backoff<20>(full_b(s), ph);
+        mbar_wait(full_b(s), ph);
         if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[3 * 512 + g] = clock64();
         tc_fence_after();
         if (lane == 0) {
@@ -703,7 +703,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
           const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + KC * sj + (KC / 8) * g8) + u);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            if ((bits >> i) & 1u) {
+            if ((bits >> i) & 1u) {   // (bits of the chunk being stored)
               float4& x = cur[i * NV + u];
               x.x = fmaxf(fmaf(x.x, sc.x, sh.x), 0.f); x.y = fmaxf(fmaf(x.y, sc.y, sh.y), 0.f);
               x.z = fmaxf(fmaf(x.z, sc.z, sh.z), 0.f); x.w = fmaxf(fmaf(x.w, sc.w, sh.w), 0.f);
@@ -711,7 +711,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
           }
         }
       }
-      if (L.t < num_tiles) { load_chunk(L, buf, bits); advance(L); }
+      const uint32_t bits_now = bits;
       mbar_wait(empty(stage), phase ^ 1);
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[0 * 512 + g] = clock64();
       uint8_t* a_hi = smem_gen + stage * S::STAGE_BYTES;
@@ -754,6 +754,10 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         }
       }
       if (MATH == MATH_F16 && amax > 60000.f && p.range_flag) *p.range_flag = 1;   // FP16 operand range exceeded: caller must use tf32x3
+      // issue the global loads of a later chunk while this chunk's shared-memory stores drain: the proxy fence
+      // below waits for them, and its cost grows with the number of stores still in flight
+      (void)bits_now;
+      if (L.t < num_tiles) { load_chunk(L, buf, bits); advance(L); }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_a(stage));
