@@ -36,12 +36,13 @@ enum {
 
 /* Options for suo_set_option */
 enum {
-  SUO_OPT_CONV_BACKEND = 1, /* 0 = FP32 SIMT implicit GEMM, 1 = tcgen05 TF32 tensor cores (default) */
+  SUO_OPT_CONV_BACKEND = 1, /* 0 = FP32 SIMT implicit GEMM, 1 = tcgen05 tensor cores (default; math per SUO_OPT_CONV_MATH) */
   SUO_OPT_TF32_PASSES = 2,  /* 3 = 3xTF32 split (FP32-equivalent, default), 1 = single-pass TF32 */
   SUO_OPT_USE_GRAPH = 3,    /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
   SUO_OPT_CONV_PERSISTENT = 4, /* 1 = persistent tcgen05 conv kernel with overlapped epilogue (default), 0 = one tile per CTA */
   SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
-  SUO_OPT_CONV_MATH = 6        /* 0 = TF32 split (SUO_OPT_TF32_PASSES), 1 = FP16x3 split: x = hi + 2^-11 lo in two FP16 numbers */
+  SUO_OPT_CONV_MATH = 6        /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
+                                  0 = TF32 split (SUO_OPT_TF32_PASSES) */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

@@ -112,7 +112,7 @@ struct suo_ctx {
   int max_crops = 0, crop_res = 0, num_kp = 0;
   std::string err;
   long long launches = 0;
-  int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 0;
+  int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
   void* net = nullptr;  // NetState (net_exec.cu)
   void* scratch = nullptr; size_t scratch_bytes = 0;        // device scratch for host-pointer calls
   void* pinned = nullptr; size_t pinned_bytes = 0;          // pinned staging

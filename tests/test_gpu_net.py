@@ -65,7 +65,7 @@ def test_forward_vs_reference_golden(golden_dir, sd, name, backend, passes, tol_
 def test_forward_host_tensors_and_graph_replay(sd, golden_dir):
     """CPU tensors in -> CPU tensors out (host-pointer ABI path); second call replays the CUDA graph."""
     g = np.load(f"{golden_dir}/net_small.npz")
-    m = _model(sd, 1, 3)
+    m = _model(sd, 2, 3)
     a = m(torch.from_numpy(g["img"]), [torch.from_numpy(g["boxes"])], None)
     b = m(torch.from_numpy(g["img"]), [torch.from_numpy(g["boxes"])], None)
     assert a["uv"].device.type == "cpu"
