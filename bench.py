@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-per-step", type=int, default=32, help="independent frames per GPU per step (stream batching)")
     ap.add_argument("--input-sets", type=int, default=3, help="distinct input batches rotated between steps")
     ap.add_argument("--tf32-passes", type=int, default=3, choices=[1, 3])
     ap.add_argument("--conv-math", default="fp16x3", choices=["fp16x3", "tf32"])
