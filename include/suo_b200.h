@@ -108,7 +108,9 @@ int suo_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W,
  *   residual [B,Ho,Wo,Cout] or NULL; relu: apply ReLU after bias (before residual is
  *   never needed by the network; residual layers have relu == 0)
  *   ksize in {1,3,7}; stride 1 (ksize 1,3; pad (ksize-1)/2) or 2 (ksize 7, pad 3)
- *   backend: 0 SIMT FP32, 1 tcgen05 TF32 (tf32_passes as SUO_OPT_TF32_PASSES), 2 tcgen05 FP16x3. */
+ *   backend: 0 SIMT FP32, 1 tcgen05 TF32 (tf32_passes as SUO_OPT_TF32_PASSES), 2 tcgen05 FP16x3;
+ *            3 = FP16x3 with the A operand fed by TMA from pre-split FP16 planes (the call splits `in` on the host),
+ *            4 = FP16x3 writing the output as FP16 planes (re-joined on the host), 5 = both. */
 int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin,
                const float* w, const float* bias, int Cout, int ksize, int stride,
                const float* pre_scale, const float* pre_shift, const float* residual, int relu,

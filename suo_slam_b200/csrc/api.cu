@@ -9,15 +9,51 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <memory>
 #include <tuple>
+
+#include <cuda.h>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int32_t kMagic = 0x574F5553;  // 'SUOW'
+
+// CUtensorMap of one FP16 plane [B,H,W,C] (NHWC) whose box is one 128-pixel output tile x 64 channels (128 B,
+// SWIZZLE_128B, zero fill outside the tensor = the 3x3 conv's padding).  Driver entry point fetched at run time so the
+// library does not link libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, int H, int B) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult qres;
+    void* f = nullptr;
+    SUO_CUDA_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres));
+    if (!f || qres != cudaDriverEntryPointSuccess) { ctx->set_error("cuTensorMapEncodeTiled not available", __FILE__, __LINE__); return SUO_E_CUDA; }
+    fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  int bw, bh, bb;
+  if (W >= 128) { bw = 128; bh = 1; bb = 1; }
+  else { bw = W; bh = std::min(H, 128 / W); bb = 128 / (W * bh); }
+  if (bw * bh * bb != 128 || C % 64) { ctx->set_error("make_plane_tmap: tile does not cover whole rows", __FILE__, __LINE__); return SUO_E_INVALID; }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r), __FILE__, __LINE__); return SUO_E_CUDA; }
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(out128, &m, 128);
+  return SUO_OK;
+}
 enum OpType : int32_t { OP_CONV = 0, OP_MAXPOOL = 1, OP_UPADD = 2 };
 
 struct BlobHeader {
@@ -25,7 +61,7 @@ struct BlobHeader {
   int32_t in_buf_noprior, in_buf_prior, logits_buf, cls_w_off, cls_b_off, heat_div;
   int32_t reserved[4];
 };
-struct BufDesc { int32_t div, C; };
+struct BufDesc { int32_t div, C, kind; };   // kind 1: may be stored as two FP16 planes when the fp16x3 tensor-core path runs
 struct OpDesc {
   int32_t type, variant, in, out, res, mode, Cin, Cout, Cout_pad, K, cpr, relu, out_nchw, w_off, b_off, pre_off;
 };
@@ -38,6 +74,7 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
+  std::vector<std::array<unsigned char, 256>> tmaps;   // per op: hi / lo CUtensorMap of its split-FP16 input (if any)
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
@@ -127,6 +164,11 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
       p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
       p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
       p.math = ctx->opt_math; p.w_packed16 = N.packed16[i]; p.range_flag = N.range_flag;
+      const bool split_mode = backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && passes == 3;
+      p.in_split = split_mode && bi.kind == 1;
+      p.out_split = split_mode && bo.kind == 1;
+      p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
+      if (p.in_split) { memcpy(p.tmap_hi, N.tmaps[i].data(), 128); memcpy(p.tmap_lo, N.tmaps[i].data() + 128, 128); }
       rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
     } else if (o.type == OP_MAXPOOL) {
       rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], st);
@@ -273,7 +315,7 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   if (nbytes < sizeof(BlobHeader)) return SUO_E_INVALID;
   NetState& N = x->net;
   memcpy(&N.h, b, sizeof(BlobHeader));
-  if (N.h.magic != kMagic || N.h.version != 1 || N.h.num_kp != ctx->num_kp) {
+  if (N.h.magic != kMagic || N.h.version != 2 || N.h.num_kp != ctx->num_kp) {
     ctx->set_error("bad weight blob header", __FILE__, __LINE__);
     return SUO_E_INVALID;
   }
@@ -318,6 +360,18 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
     const size_t n = (size_t)ctx->max_crops * side * side * N.bufs[i].C;
     SUO_CUDA_TRY(ctx, cudaMalloc(&N.act[i], n * sizeof(float)));
     SUO_CUDA_TRY(ctx, cudaMemset(N.act[i], 0, n * sizeof(float)));
+  }
+  N.tmaps.resize(N.ops.size());
+  for (size_t i = 0; i < N.ops.size(); ++i) {
+    const OpDesc& o = N.ops[i];
+    if (o.type != OP_CONV || N.bufs[o.in].kind != 1) continue;
+    const int side = R / N.bufs[o.in].div, C = N.bufs[o.in].C;
+    const uint16_t* base = reinterpret_cast<const uint16_t*>(N.act[o.in]);
+    const size_t plane = (size_t)ctx->max_crops * side * side * C;
+    int rc2 = make_plane_tmap(ctx, N.tmaps[i].data(), base, C, side, side, ctx->max_crops);
+    if (rc2) return rc2;
+    rc2 = make_plane_tmap(ctx, N.tmaps[i].data() + 128, base + plane, C, side, side, ctx->max_crops);
+    if (rc2) return rc2;
   }
   const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
@@ -471,8 +525,23 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   p.in = d_in; p.w = d_w; p.w_packed = d_wp; p.bias = d_b; p.pre_scale = d_ps; p.pre_shift = d_pt; p.residual = d_res;
   p.out = d_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cout_pad = Cout_pad;
   p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
-  p.math = backend == 2 ? 1 : 0; p.w_packed16 = d_wp16; p.range_flag = d_flag;
-  if (backend == 2) backend = 1;
+  // backend 2..5: tcgen05 FP16x3; 3/5 feed A by TMA from pre-split FP16 planes, 4/5 write the output as FP16 planes
+  const bool tma_in = backend == 3 || backend == 5, split_out = backend == 4 || backend == 5;
+  p.math = backend >= 2 ? 1 : 0; p.w_packed16 = d_wp16; p.range_flag = d_flag;
+  if (backend >= 2) backend = 1;
+  uint16_t* d_in16 = nullptr;
+  std::vector<uint16_t> h_out16;
+  if (tma_in) {
+    std::vector<uint16_t> h16(2 * n_in);
+    conv_tc_host_split_f16(in, n_in, h16.data(), h16.data() + n_in);
+    SUO_CUDA_TRY(ctx, cudaMalloc(&d_in16, 2 * n_in * sizeof(uint16_t)));
+    SUO_CUDA_TRY(ctx, cudaMemcpy(d_in16, h16.data(), 2 * n_in * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    rc = make_plane_tmap(ctx, p.tmap_hi, d_in16, Cin, W, H, B);
+    if (!rc) rc = make_plane_tmap(ctx, p.tmap_lo, d_in16 + n_in, Cin, W, H, B);
+    if (rc) { cudaFree(d_in16); return rc; }
+    p.in_split = 1;
+  }
+  if (split_out) { p.out_split = 1; p.out_plane = n_out; }   // d_out holds 2 * n_out halfs = n_out floats of storage
   long long* d_dbg = nullptr;
   const char* dbg_path = getenv("SUO_CONV_TIMELINE");
   if (dbg_path && backend >= 1) {
@@ -506,6 +575,12 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  if (split_out) {
+    h_out16.resize(2 * n_out);
+    memcpy(h_out16.data(), out, n_out * sizeof(float));
+    conv_tc_host_join_f16(h_out16.data(), h_out16.data() + n_out, n_out, out);
+  }
+  if (d_in16) cudaFree(d_in16);
   return SUO_OK;
 }
 
@@ -884,6 +959,11 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
         p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode; p.chunks_per_row = o.cpr;
         p.relu = o.relu; p.out_nchw = o.out_nchw;
         p.math = ctx->opt_math; p.w_packed16 = N.packed16[idx[q]]; p.range_flag = N.range_flag;
+        const bool split_mode = ctx->opt_backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && ctx->opt_passes == 3;
+        p.in_split = split_mode && bi.kind == 1;
+        p.out_split = split_mode && bo.kind == 1;
+        p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
+        if (p.in_split) { memcpy(p.tmap_hi, N.tmaps[idx[q]].data(), 128); memcpy(p.tmap_lo, N.tmaps[idx[q]].data() + 128, 128); }
         rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
       } else if (o.type == OP_MAXPOOL) {
         rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);

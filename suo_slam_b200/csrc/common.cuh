@@ -59,6 +59,11 @@ struct ConvParams {
   const uint16_t* w_packed16;  // tcgen05 fp16x3: per (n_tile, 64-chunk) hi / lo' FP16 images
   int math;               // 0 = TF32 (1 or 3 passes), 1 = FP16x3 split
   int* range_flag;        // fp16x3: set to 1 when an operand exceeds the FP16 range
+  int in_split;           // input is two FP16 planes (hi, lo') -> A operand by TMA (tmap_hi / tmap_lo)
+  int out_split;          // write the output as two FP16 planes (out_plane = halfs between them)
+  size_t out_plane;
+  alignas(64) unsigned char tmap_hi[128];   // CUtensorMap of the hi plane [B,H,W,C] fp16, box = one 128-pixel tile x 64 ch
+  alignas(64) unsigned char tmap_lo[128];
 };
 
 struct suo_ctx;
@@ -70,6 +75,8 @@ void conv_tc_pack_weights(const float* w, int Cout_pad, int K, float* dst);
 int conv_tc_block_n(int Cout_pad);
 size_t conv_tc_packed16_halfs(int Cout_pad, int K);
 void conv_tc_pack_weights_f16(const float* w, int Cout_pad, int K, uint16_t* dst);
+void conv_tc_host_split_f16(const float* x, size_t n, uint16_t* hi, uint16_t* lo);
+void conv_tc_host_join_f16(const uint16_t* hi, const uint16_t* lo, size_t n, float* x);
 
 int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
                           const float* cls_b, float* pooled_scratch, float* uv, float* cov, float* prob,

@@ -82,6 +82,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// 4-D tiled TMA load (UTMALDG): box of the tensor map at (c0,c1,c2,c3) -> swizzled shared memory, completes on mbar
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -441,10 +446,14 @@ __device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p,
   c.off = (MODE == CONV_3x3) ? -(ptrdiff_t)(p.W + 1) * p.Cin : 0;
 }
 
-template <int BN, int MODE, bool PRE, int MATH>
+// A_TMA: the A operand comes straight from HBM by TMA (cp.async.bulk.tensor, 128B swizzle, hardware zero fill
+// for the 3x3 padding) out of a tensor whose producer layer already wrote it as two FP16 planes (hi, lo'):
+// no A-producer warps, no register staging, no proxy fences — the CTA is 6 warps.
+template <int BN, int MODE, bool PRE, int MATH, bool A_TMA>
 // 14 warps -> one SMSP hosts 4 of them -> the 16K-register SMSP file caps every thread at 128 registers
-__global__ void __launch_bounds__(P_NUM_THREADS, 1)
-conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
+__global__ void __launch_bounds__(A_TMA ? 192 : P_NUM_THREADS, 1)
+conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
+  static_assert(!A_TMA || (MATH == MATH_F16 && !PRE && MODE != CONV_STEM7), "TMA-fed A needs pre-split FP16 activations");
   // MATH_TF32: chunk = 32 floats, operands FP32 words read as TF32 (hi = top 19 bits, lo = x - hi).
   // MATH_F16 : chunk = 64 floats, operands FP16: x = hi + 2^-11 lo' with hi = fp16(x with 13 low mantissa bits
   //            cleared) and lo' = fp16((x - hi) * 2^11): 22 mantissa bits in two FP16 numbers; the correction
@@ -471,7 +480,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NUM_STAGES; ++s) {
-      mbar_init(full_a(s), NUM_PRODUCER_WARPS);
+      mbar_init(full_a(s), A_TMA ? 1 : NUM_PRODUCER_WARPS);
       mbar_init(full_b(s), 1);
       mbar_init(empty(s), 1);
     }
@@ -489,16 +498,31 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
     if (lane == 0) {
       const uint32_t nbytes = (passes == 3 ? 2u : 1u) * S::B_TILE_BYTES;
       uint32_t g = 0;
+      const int HWi = p.H * p.W, cpc64 = p.Cin / 64;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_tile = t % num_n_tiles;
+        const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
         const float* src = p.w_packed + (size_t)n_tile * nchunks * 2 * (BN * BLOCK_K);
+        // tile origin in (b, y) — tiles cover whole image rows (128 % W == 0 or W % 128 == 0)
+        const int m0 = m_tile * BLOCK_M;
+        const int b0 = m0 / HWi, rem = m0 - b0 * HWi;
+        const int y0 = rem / p.W, x0 = rem - y0 * p.W;
         for (int j = 0; j < nchunks; ++j, ++g) {
           const int s = g % NUM_STAGES;
           const uint32_t ph = (g / NUM_STAGES) & 1;
           mbar_wait(empty(s), ph ^ 1);
           if (p.dbg && blockIdx.x == 0 && g < 512) p.dbg[4 * 512 + g] = clock64();
-          const uint32_t dst = smem_base + s * S::STAGE_BYTES + 2 * A_TILE_BYTES;
-          mbar_arrive_expect_tx(full_b(s), nbytes);
+          const uint32_t a_dst = smem_base + s * S::STAGE_BYTES;
+          const uint32_t dst = a_dst + 2 * A_TILE_BYTES;
+          if (A_TMA) {
+            const int tap = (MODE == CONV_3x3) ? j / cpc64 : 0, cc = (MODE == CONV_3x3) ? j - tap * cpc64 : j;
+            const int dy = (MODE == CONV_3x3) ? tap / 3 - 1 : 0, dx = (MODE == CONV_3x3) ? tap % 3 - 1 : 0;
+            mbar_arrive_expect_tx(full_b(s), nbytes + (passes == 3 ? 2u : 1u) * A_TILE_BYTES);
+            tma_load_4d(a_dst, p.tmap_hi, 64 * cc, x0 + dx, y0 + dy, b0, full_b(s));
+            if (passes == 3) tma_load_4d(a_dst + A_TILE_BYTES, p.tmap_lo, 64 * cc, x0 + dx, y0 + dy, b0, full_b(s));
+            mbar_arrive(full_a(s));
+          } else {
+            mbar_arrive_expect_tx(full_b(s), nbytes);
+          }
           bulk_g2s(dst, src + (size_t)j * 2 * (BN * BLOCK_K), nbytes, full_b(s));
         }
       }
@@ -603,7 +627,21 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
             o.x += bq.x; o.y += bq.y; o.z += bq.z; o.w += bq.w;
             if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             if (p.residual) { o.x += rq[i].x; o.y += rq[i].y; o.z += rq[i].z; o.w += rq[i].w; }
-            if (ncol_ok && mm < M) *reinterpret_cast<float4*>(p.out + (size_t)mm * p.out_c + n0) = o;
+            if (ncol_ok && mm < M) {
+              if (p.out_split) {
+                // consumer is a TMA-fed conv: write the two FP16 planes it will load (same split as the A producers)
+                const float h0 = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                const float h2 = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                __half2 a = __floats2half2_rn(h0, h1), b2 = __floats2half2_rn(h2, h3);
+                __half2 c2 = __floats2half2_rn((o.x - h0) * 2048.f, (o.y - h1) * 2048.f), d2 = __floats2half2_rn((o.z - h2) * 2048.f, (o.w - h3) * 2048.f);
+                uint16_t* oh = reinterpret_cast<uint16_t*>(p.out) + (size_t)mm * p.out_c + n0;
+                *reinterpret_cast<uint2*>(oh) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b2));
+                *reinterpret_cast<uint2*>(oh + p.out_plane) = make_uint2(*reinterpret_cast<uint32_t*>(&c2), *reinterpret_cast<uint32_t*>(&d2));
+                if (fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))) > 60000.f && p.range_flag) *p.range_flag = 1;
+              } else {
+                *reinterpret_cast<float4*>(p.out + (size_t)mm * p.out_c + n0) = o;
+              }
+            }
           }
           __syncwarp();      // staging is rewritten by the next column group
         } else if (m < M) {
@@ -620,7 +658,7 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
         }
       }
     }
-  } else {
+  } else if (!A_TMA) {
     // ===================== A producers =====================
     const int pt = threadIdx.x - 192;           // 0..255
     const int g8 = pt & 7;                      // float4 group inside the 128-byte row
@@ -785,12 +823,12 @@ conv_tc_persistent_kernel(const ConvParams p, const int passes, const int num_m_
   }
 }
 
-template <int BN, int MODE, bool PRE, int MATH>
+template <int BN, int MODE, bool PRE, int MATH, bool A_TMA>
 int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
     int dev = 0;
     SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
     SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -799,7 +837,7 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, num_sms);
-  conv_tc_persistent_kernel<BN, MODE, PRE, MATH><<<grid, P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
+  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA><<<grid, A_TMA ? 192 : P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
@@ -807,10 +845,15 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
 
 template <int BN, int MATH>
 int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
-  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH>(ctx, p, passes, s);
-  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH>(ctx, p, passes, s);
-  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH>(ctx, p, passes, s);
-  return launch_persistent_inst<BN, CONV_1x1, false, MATH>(ctx, p, passes, s);
+  if (MATH == MATH_F16 && p.in_split) {
+    if (p.pre_scale || p.mode == CONV_STEM7 || p.Cin % 64) { ctx->set_error("conv_tc: TMA-fed A needs a plain 1x1/3x3 conv with Cin % 64 == 0", __FILE__, __LINE__); return SUO_E_INVALID; }
+    if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true>(ctx, p, passes, s);
+    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, true>(ctx, p, passes, s);
+  }
+  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH, false>(ctx, p, passes, s);
+  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH, false>(ctx, p, passes, s);
+  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH, false>(ctx, p, passes, s);
+  return launch_persistent_inst<BN, CONV_1x1, false, MATH, false>(ctx, p, passes, s);
 }
 
 template <int BN>
@@ -902,6 +945,22 @@ inline float host_f16_to_f32(uint16_t h) {
 }  // namespace
 
 size_t conv_tc_packed16_halfs(int Cout_pad, int K) { return (size_t)Cout_pad * K * 2; }
+
+// host mirror of the device split: x -> (hi, lo') with x ~= hi + 2^-11 lo'
+void conv_tc_host_split_f16(const float* x, size_t n, uint16_t* hi, uint16_t* lo) {
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u;
+    memcpy(&u, &x[i], 4);
+    u &= 0xFFFFE000u;
+    float ht;
+    memcpy(&ht, &u, 4);
+    hi[i] = host_f32_to_f16_rn(ht);
+    lo[i] = host_f32_to_f16_rn((x[i] - host_f16_to_f32(hi[i])) * 2048.0f);
+  }
+}
+void conv_tc_host_join_f16(const uint16_t* hi, const uint16_t* lo, size_t n, float* x) {
+  for (size_t i = 0; i < n; ++i) x[i] = host_f16_to_f32(hi[i]) + host_f16_to_f32(lo[i]) * (1.0f / 2048.0f);
+}
 
 // FP16x3 weight images: per (n_tile, 64-element chunk): hi image then lo' image, BN rows x 128 B, 128B swizzle.
 // w = hi + 2^-11 lo'  with hi = fp16(w with the 13 low mantissa bits cleared), lo' = fp16((w - hi) * 2^11).

@@ -9,7 +9,7 @@ bottleneck becomes a per-input-channel affine prologue of its first 1x1 conv.
 
 The blob also carries the *program*: a buffer table and an op list that the C++
 executor (csrc/api.cu) replays; the network topology therefore lives only here.
-Blob layout (little endian): BlobHeader (16 x i32) | n_bufs x {div, C} |
+Blob layout (little endian): BlobHeader (16 x i32) | n_bufs x {div, C, kind} |
 n_ops x OpDesc (16 x i32) | float pool.
 """
 from __future__ import annotations
@@ -49,8 +49,10 @@ class _Builder:
         self.pool_len += a.size
         return off
 
-    def buf(self, div, C):
-        self.bufs.append((div, C))
+    def buf(self, div, C, kind=0):
+        """kind 1: consumed only by plain (no prologue) 1x1/3x3 convs -> the executor may keep it as two FP16 planes
+        (hi, lo') that the consumer loads by TMA (fp16x3 tensor-core path)."""
+        self.bufs.append((div, C, kind))
         return len(self.bufs) - 1
 
     # ---- folding ------------------------------------------------------------------
@@ -110,9 +112,9 @@ class _Builder:
         """layers/Residual.py:20-35 as 3 (or 4) fused conv ops."""
         mid = cout // 2
         w1, b1 = self.conv_wb(p + ".conv1", p + ".bn1")
-        t1 = self.conv(x, self.buf(div, mid), w1, b1, CONV_1x1, pre=self.bn_affine(p + ".bn"), relu=1)
+        t1 = self.conv(x, self.buf(div, mid, 1), w1, b1, CONV_1x1, pre=self.bn_affine(p + ".bn"), relu=1)
         w2, b2 = self.conv_wb(p + ".conv2", p + ".bn2")
-        t2 = self.conv(t1, self.buf(div, mid), w2, b2, CONV_3x3, relu=1)
+        t2 = self.conv(t1, self.buf(div, mid, 1), w2, b2, CONV_3x3, relu=1)
         skip = x
         if cin != cout:
             w4, b4 = self.conv_wb(p + ".conv4")
@@ -175,10 +177,10 @@ def pack_state_dict(sd, num_kp: int = arch.NUM_KP) -> bytes:
         for j in range(arch.N_MODULES):
             ll = B.residual(f"{p}.Residual.{i * arch.N_MODULES + j}", ll, F, F, 4)
         wl, bl = B.conv_wb(f"{p}.lin_.{i}.0", f"{p}.lin_.{i}.1")
-        ll = B.conv(ll, B.buf(4, F), wl, bl, CONV_1x1, relu=1)
+        ll = B.conv(ll, B.buf(4, F, 1), wl, bl, CONV_1x1, relu=1)
         wt, bt = B.conv_wb(f"{p}.tmpOut.{i}")
         if i < arch.N_STACK - 1:
-            tmp = B.conv(ll, B.buf(4, 64), wt, bt, CONV_1x1, cout_store=64)       # NHWC, 41 real + 23 zero channels
+            tmp = B.conv(ll, B.buf(4, 64, 1), wt, bt, CONV_1x1, cout_store=64)    # NHWC, 41 real + 23 zero channels
             wll, bll = B.conv_wb(f"{p}.ll_.{i}")
             t = B.conv(ll, B.buf(4, F), wll, bll, CONV_1x1, res=x)                 # x + ll_
             wto, bto = B.conv_wb(f"{p}.tmpOut_.{i}")
@@ -189,7 +191,7 @@ def pack_state_dict(sd, num_kp: int = arch.NUM_KP) -> bytes:
     cls_b = B.put(_np(sd["classifier.2.bias"]))
     pool = np.concatenate(B.pool).astype(np.float32)
     header = np.zeros(16, np.int32)
-    header[:12] = [MAGIC, 1, num_kp, len(B.bufs), len(B.ops), pool.size, in4, in48, logits, cls_w, cls_b, 4]
+    header[:12] = [MAGIC, 2, num_kp, len(B.bufs), len(B.ops), pool.size, in4, in48, logits, cls_w, cls_b, 4]
     return b"".join([header.tobytes(), np.asarray(B.bufs, np.int32).tobytes(),
                      np.asarray(B.ops, np.int32).tobytes(), pool.tobytes()])
 
@@ -197,5 +199,5 @@ def pack_state_dict(sd, num_kp: int = arch.NUM_KP) -> bytes:
 def program_summary(blob: bytes):
     """(n_bufs, n_ops, n_convs, pool floats) of a packed blob — for tests / docs."""
     h = np.frombuffer(blob[:64], np.int32)
-    ops = np.frombuffer(blob[64 + 8 * h[3]: 64 + 8 * h[3] + 64 * h[4]], np.int32).reshape(-1, 16)
+    ops = np.frombuffer(blob[64 + 12 * h[3]: 64 + 12 * h[3] + 64 * h[4]], np.int32).reshape(-1, 16)
     return dict(n_bufs=int(h[3]), n_ops=int(h[4]), n_convs=int((ops[:, 0] == OP_CONV).sum()), n_floats=int(h[5]))
