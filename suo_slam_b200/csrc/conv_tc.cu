@@ -573,11 +573,29 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
       const uint32_t b = i & 1;
+      // TMA-fed kernels have 6 warps -> up to 255 registers per thread: fetch the residual of the WHOLE tile (BN/32
+      // column groups x 8 rows per lane) before waiting for the accumulator, so its HBM latency hides behind the main loop
+      constexpr int NG = A_TMA ? BN / 32 : 1;
+      float4 rqa[NG][8];
+      if (A_TMA && p.residual && !p.out_nchw) {
+        const int cg = lane & 7, rsub = lane >> 3;
+        const int mrow0 = m_tile * BLOCK_M + q * 32 + rsub;
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) {
+          const int n0 = n_tile * BN + 32 * gi + 4 * cg;
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const int mm = mrow0 + 4 * ii;
+            rqa[gi][ii] = (n0 < p.Cout && mm < M) ? *reinterpret_cast<const float4*>(p.residual + (size_t)mm * p.out_c + n0)
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
       mbar_wait_backoff(tmem_full(b), (i >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
       const int m = m_tile * BLOCK_M + q * 32 + lane;
-#pragma unroll 1
+#pragma unroll
       for (int col = 0; col < BN; col += 32) {
         uint32_t r[32];
         tmem_ld32(acc + (uint32_t)col, r);
@@ -612,7 +630,10 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
           const float4 bq = ncol_ok ? __ldg(reinterpret_cast<const float4*>(p.bias + n0)) : make_float4(0.f, 0.f, 0.f, 0.f);
           const int mrow0 = m_tile * BLOCK_M + q * 32 + rsub;
           float4 rq[8];
-          if (p.residual) {
+          if (A_TMA && p.residual) {
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) rq[ii] = rqa[A_TMA ? col / 32 : 0][ii];
+          } else if (p.residual) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int mm = mrow0 + 4 * i;
