@@ -28,8 +28,9 @@ constexpr int32_t kMagic = 0x574F5553;  // 'SUOW'
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
 int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, int H, int B) {
-  static EncodeTiledFn fn = nullptr;
+  EncodeTiledFn& fn = g_encode_tiled;
   if (!fn) {
     cudaDriverEntryPointQueryResult qres;
     void* f = nullptr;
@@ -37,6 +38,7 @@ int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, 
     if (!f || qres != cudaDriverEntryPointSuccess) { ctx->set_error("cuTensorMapEncodeTiled not available", __FILE__, __LINE__); return SUO_E_CUDA; }
     fn = reinterpret_cast<EncodeTiledFn>(f);
   }
+  if (!out128) return SUO_OK;       // entry-point resolution only
   int bw, bh, bb;
   if (W >= 128) { bw = 128; bh = 1; bb = 1; }
   else { bw = W; bh = std::min(H, 128 / W); bb = 128 / (W * bh); }
@@ -51,6 +53,25 @@ int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r), __FILE__, __LINE__); return SUO_E_CUDA; }
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+  memcpy(out128, &m, 128);
+  return SUO_OK;
+}
+// CUtensorMap of a row-major 2-D view [rows, cols] (the NHWC tensor with pixels flattened) whose box is 32 rows x 128 bytes
+// (32 floats or 64 halfs), SWIZZLE_128B: what one epilogue warp stores (or fetches, for the skip tensor) per TMA operation.
+int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size_t rows, int cols) {
+  CUtensorMap m;
+  const int es = fp16 ? 2 : 4;
+  if (((size_t)cols * es) % 16 || (reinterpret_cast<uintptr_t>(base) & 15)) { ctx->set_error("make_rows_tmap: row pitch / base not 16-byte aligned", __FILE__, __LINE__); return SUO_E_INVALID; }
+  int rc = make_plane_tmap(ctx, nullptr, nullptr, 0, 0, 0, 0);   // resolves the driver entry point
+  (void)rc;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * es};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled (rows) failed: " + std::to_string((int)r), __FILE__, __LINE__); return SUO_E_CUDA; }
   memcpy(out128, &m, 128);
   return SUO_OK;
 }
@@ -74,7 +95,8 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
-  std::vector<std::array<unsigned char, 256>> tmaps;   // per op: hi / lo CUtensorMap of its split-FP16 input (if any)
+  std::vector<std::array<unsigned char, 640>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip CUtensorMaps (split mode)
+  std::vector<int> epi_ok;                              // per op: the output / skip maps are valid
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
@@ -118,6 +140,36 @@ struct Bump {
   template <typename T> T* take(size_t n) { off = align_up(off, 256); T* p = reinterpret_cast<T*>(base + off); off += n * sizeof(T); return p; }
 };
 
+// One conv op of the program as the engine sees it, for L crops.
+void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, int passes, ConvParams& p) {
+  const OpDesc& o = N.ops[i];
+  const BufDesc& bi = N.bufs[o.in];
+  const BufDesc& bo = N.bufs[o.out];
+  const int R = ctx->crop_res;
+  p.in = N.act[o.in];
+  p.w = N.pool + o.w_off;
+  p.w_packed = N.packed[i];
+  p.bias = N.pool + o.b_off;
+  p.pre_scale = o.pre_off >= 0 ? N.pool + o.pre_off : nullptr;
+  p.pre_shift = o.pre_off >= 0 ? N.pool + o.pre_off + o.Cin : nullptr;
+  p.residual = o.res >= 0 ? N.act[o.res] : nullptr;
+  p.out = N.act[o.out];
+  p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin;
+  p.Ho = R / bo.div; p.Wo = R / bo.div;
+  p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
+  p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
+  p.math = ctx->opt_math; p.w_packed16 = N.packed16[i]; p.range_flag = N.range_flag;
+  const bool split_mode = backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && passes == 3;
+  p.in_split = split_mode && bi.kind == 1;
+  p.out_split = split_mode && bo.kind == 1;
+  p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
+  p.mma_merge = ctx->opt_mma_merge;
+  const unsigned char* tm = N.tmaps[i].data();
+  if (p.in_split) { memcpy(p.tmap_hi, tm, 128); memcpy(p.tmap_lo, tm + 128, 128); }
+  p.epi_tma = split_mode && ctx->opt_epi_tma && N.epi_ok[i];
+  if (p.epi_tma) { memcpy(p.tmap_out, tm + 256, 128); memcpy(p.tmap_out_lo, tm + 384, 128); memcpy(p.tmap_res, tm + 512, 128); }
+}
+
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int R = ctx->crop_res;
@@ -151,24 +203,7 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
     int rc = SUO_OK;
     if (o.type == OP_CONV) {
       ConvParams p{};
-      p.in = N.act[o.in];
-      p.w = N.pool + o.w_off;
-      p.w_packed = N.packed[i];
-      p.bias = N.pool + o.b_off;
-      p.pre_scale = o.pre_off >= 0 ? N.pool + o.pre_off : nullptr;
-      p.pre_shift = o.pre_off >= 0 ? N.pool + o.pre_off + o.Cin : nullptr;
-      p.residual = o.res >= 0 ? N.act[o.res] : nullptr;
-      p.out = N.act[o.out];
-      p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin;
-      p.Ho = R / bo.div; p.Wo = R / bo.div;
-      p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode;
-      p.chunks_per_row = o.cpr; p.relu = o.relu; p.out_nchw = o.out_nchw;
-      p.math = ctx->opt_math; p.w_packed16 = N.packed16[i]; p.range_flag = N.range_flag;
-      const bool split_mode = backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && passes == 3;
-      p.in_split = split_mode && bi.kind == 1;
-      p.out_split = split_mode && bo.kind == 1;
-      p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
-      if (p.in_split) { memcpy(p.tmap_hi, N.tmaps[i].data(), 128); memcpy(p.tmap_lo, N.tmaps[i].data() + 128, 128); }
+      fill_conv_params(ctx, N, i, L, backend, passes, p);
       rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
     } else if (o.type == OP_MAXPOOL) {
       rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], st);
@@ -262,6 +297,8 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_USE_GRAPH")) c->opt_graph = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   *out = c;
   return SUO_OK;
 }
@@ -362,16 +399,35 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
     SUO_CUDA_TRY(ctx, cudaMemset(N.act[i], 0, n * sizeof(float)));
   }
   N.tmaps.resize(N.ops.size());
+  N.epi_ok.assign(N.ops.size(), 0);
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
-    if (o.type != OP_CONV || N.bufs[o.in].kind != 1) continue;
-    const int side = R / N.bufs[o.in].div, C = N.bufs[o.in].C;
-    const uint16_t* base = reinterpret_cast<const uint16_t*>(N.act[o.in]);
-    const size_t plane = (size_t)ctx->max_crops * side * side * C;
-    int rc2 = make_plane_tmap(ctx, N.tmaps[i].data(), base, C, side, side, ctx->max_crops);
+    if (o.type != OP_CONV) continue;
+    if (N.bufs[o.in].kind == 1) {
+      const int side = R / N.bufs[o.in].div, C = N.bufs[o.in].C;
+      const uint16_t* base = reinterpret_cast<const uint16_t*>(N.act[o.in]);
+      const size_t plane = (size_t)ctx->max_crops * side * side * C;
+      int rc2 = make_plane_tmap(ctx, N.tmaps[i].data(), base, C, side, side, ctx->max_crops);
+      if (rc2) return rc2;
+      rc2 = make_plane_tmap(ctx, N.tmaps[i].data() + 128, base + plane, C, side, side, ctx->max_crops);
+      if (rc2) return rc2;
+    }
+    // output (and skip) maps of the TMA-store epilogue: rows = every pixel of every crop slot of the buffer
+    const BufDesc& bo = N.bufs[o.out];
+    if (o.out_nchw || bo.C % 8) continue;
+    const int so = R / bo.div;
+    const size_t rows = (size_t)ctx->max_crops * so * so;
+    int rc2;
+    if (bo.kind == 1) {
+      const uint16_t* ob = reinterpret_cast<const uint16_t*>(N.act[o.out]);
+      rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 256, ob, true, rows, bo.C);
+      if (!rc2) rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 384, ob + rows * bo.C, true, rows, bo.C);
+    } else {
+      rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 256, N.act[o.out], false, rows, bo.C);
+    }
+    if (!rc2 && o.res >= 0) rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 512, N.act[o.res], false, rows, bo.C);
     if (rc2) return rc2;
-    rc2 = make_plane_tmap(ctx, N.tmaps[i].data() + 128, base + plane, C, side, side, ctx->max_crops);
-    if (rc2) return rc2;
+    N.epi_ok[i] = 1;
   }
   const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
@@ -542,11 +598,25 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
     p.in_split = 1;
   }
   if (split_out) { p.out_split = 1; p.out_plane = n_out; }   // d_out holds 2 * n_out halfs = n_out floats of storage
+  p.mma_merge = ctx->opt_mma_merge;
+  if (p.math == 1 && ctx->opt_epi_tma && Cout % 8 == 0) {
+    const size_t rows = (size_t)B * Ho * Wo;
+    int r2;
+    if (split_out) {
+      r2 = make_rows_tmap(ctx, p.tmap_out, d_out, true, rows, Cout);
+      if (!r2) r2 = make_rows_tmap(ctx, p.tmap_out_lo, reinterpret_cast<uint16_t*>(d_out) + n_out, true, rows, Cout);
+    } else {
+      r2 = make_rows_tmap(ctx, p.tmap_out, d_out, false, rows, Cout);
+    }
+    if (!r2 && d_res) r2 = make_rows_tmap(ctx, p.tmap_res, d_res, false, rows, Cout);
+    if (r2) { if (d_in16) cudaFree(d_in16); return r2; }
+    p.epi_tma = 1;
+  }
   long long* d_dbg = nullptr;
   const char* dbg_path = getenv("SUO_CONV_TIMELINE");
   if (dbg_path && backend >= 1) {
-    SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 13 * 512 * sizeof(long long)));
-    SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 13 * 512 * sizeof(long long), s));
+    SUO_CUDA_TRY(ctx, cudaMalloc(&d_dbg, 16 * 512 * sizeof(long long)));
+    SUO_CUDA_TRY(ctx, cudaMemsetAsync(d_dbg, 0, 16 * 512 * sizeof(long long), s));
     p.dbg = d_dbg;
   }
   cudaEvent_t e0, e1;
@@ -556,18 +626,24 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   cudaEventRecord(e1, s);
   if (rc) return rc;
   if (d_dbg) {
-    std::vector<long long> h(13 * 512);
+    std::vector<long long> h(16 * 512);
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, s));
     SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     if (FILE* f = fopen(dbg_path, "a")) {
       fprintf(f, "# B=%d H=%d W=%d Cin=%d Cout=%d k=%d passes=%d kernel_ms=%.4f\n", B, H, W, Cin, Cout, ksize, tf32_passes, ms);
       fprintf(f, "g,prod_slot_free,prod_arrived,mma_full_a,mma_full_b,w_slot_free,pw0,pw1,pw2,pw3,pw4,pw5,pw6,pw7\n");
-      for (int g = 0; g < 512 && h[g]; ++g) {
-        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld", g, h[g] - h[0], h[512 + g] - h[0], h[1024 + g] - h[0], h[1536 + g] - h[0], h[2048 + g] - h[0]);
-        for (int w = 0; w < 8; ++w) fprintf(f, ",%lld", h[(5 + w) * 512 + g] - h[0]);
+      long long t0 = 0;
+      for (long long v : h) if (v && (!t0 || v < t0)) t0 = v;
+      auto rel = [&](long long v) { return v ? v - t0 : -1; };
+      for (int g = 0; g < 512 && (h[g] || h[1024 + g]); ++g) {
+        fprintf(f, "%d,%lld,%lld,%lld,%lld,%lld", g, rel(h[g]), rel(h[512 + g]), rel(h[1024 + g]), rel(h[1536 + g]), rel(h[2048 + g]));
+        for (int w = 0; w < 8; ++w) fprintf(f, ",%lld", rel(h[(5 + w) * 512 + g]));
         fprintf(f, "\n");
       }
+      fprintf(f, "tile,epi_wait_start,epi_acc_full,epi_done\n");
+      for (int t = 0; t < 512 && h[13 * 512 + t]; ++t)
+        fprintf(f, "%d,%lld,%lld,%lld\n", t, rel(h[13 * 512 + t]), rel(h[14 * 512 + t]), rel(h[15 * 512 + t]));
       fclose(f);
     }
     cudaFree(d_dbg);
@@ -950,20 +1026,7 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       const BufDesc& bo = N.bufs[o.out];
       if (o.type == OP_CONV) {
         ConvParams p{};
-        p.in = N.act[o.in]; p.w = N.pool + o.w_off; p.w_packed = N.packed[idx[q]]; p.bias = N.pool + o.b_off;
-        p.pre_scale = o.pre_off >= 0 ? N.pool + o.pre_off : nullptr;
-        p.pre_shift = o.pre_off >= 0 ? N.pool + o.pre_off + o.Cin : nullptr;
-        p.residual = o.res >= 0 ? N.act[o.res] : nullptr;
-        p.out = N.act[o.out];
-        p.B = L; p.H = R / bi.div; p.W = R / bi.div; p.Cin = o.Cin; p.Ho = R / bo.div; p.Wo = R / bo.div;
-        p.Cout = o.Cout; p.Cout_pad = o.Cout_pad; p.out_c = bo.C; p.K = o.K; p.mode = o.mode; p.chunks_per_row = o.cpr;
-        p.relu = o.relu; p.out_nchw = o.out_nchw;
-        p.math = ctx->opt_math; p.w_packed16 = N.packed16[idx[q]]; p.range_flag = N.range_flag;
-        const bool split_mode = ctx->opt_backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && ctx->opt_passes == 3;
-        p.in_split = split_mode && bi.kind == 1;
-        p.out_split = split_mode && bo.kind == 1;
-        p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
-        if (p.in_split) { memcpy(p.tmap_hi, N.tmaps[idx[q]].data(), 128); memcpy(p.tmap_lo, N.tmaps[idx[q]].data() + 128, 128); }
+        fill_conv_params(ctx, N, idx[q], L, ctx->opt_backend, ctx->opt_passes, p);
         rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
       } else if (o.type == OP_MAXPOOL) {
         rc = launch_maxpool2(ctx, N.act[o.in], L, R / bi.div, R / bi.div, bi.C, N.act[o.out], s);

@@ -64,6 +64,11 @@ struct ConvParams {
   size_t out_plane;
   alignas(64) unsigned char tmap_hi[128];   // CUtensorMap of the hi plane [B,H,W,C] fp16, box = one 128-pixel tile x 64 ch
   alignas(64) unsigned char tmap_lo[128];
+  int epi_tma;            // tmap_out (/ tmap_out_lo, tmap_res) are valid: the epilogue may store (and fetch the skip tensor) by TMA
+  int mma_merge;          // issue A_hi x [B_hi | B_lo'] as one N = 2*BN MMA (fp16x3 / tf32x3)
+  alignas(64) unsigned char tmap_out[128];     // FP32 output [rows, out_c], box 32 rows x 32 floats — or the hi plane [rows, C] FP16, box 32 x 64
+  alignas(64) unsigned char tmap_out_lo[128];  // lo' plane (out_split)
+  alignas(64) unsigned char tmap_res[128];     // skip tensor, FP32 [rows, out_c], box 32 x 32
 };
 
 struct suo_ctx;
@@ -120,6 +125,7 @@ struct suo_ctx {
   std::string err;
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
+  int opt_epi_tma = 1, opt_mma_merge = 1;   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
   void* net = nullptr;  // NetState (net_exec.cu)
   void* scratch = nullptr; size_t scratch_bytes = 0;        // device scratch for host-pointer calls
   void* pinned = nullptr; size_t pinned_bytes = 0;          // pinned staging

@@ -87,6 +87,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, int 
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
                ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
+// 2-D tiled TMA load / store (UTMALDG / UTMASTG) and the bulk async-group bookkeeping of the issuing thread
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -400,6 +412,26 @@ conv_tc_kernel(const ConvParams p, const int passes) {
 //   warps 2..5  epilogue (one TMEM lane quarter each)      warps 6..13 A producers
 // TMEM columns: buffer b in {0,1} at b*2*BN: [main | correction].
 constexpr int P_NUM_THREADS = 32 * (2 + 4 + NUM_PRODUCER_WARPS);
+
+// Shared-memory plan of the persistent kernel.  EPI selects the epilogue:
+//   0  registers -> padded transpose buffer -> st.global (any layout: NCHW logits, unaligned channel counts, TF32 modes)
+//   1  TMA-store epilogue: each epilogue warp owns NBUF 4 KB boxes (32 rows x 128 B, 128B swizzle) that it fills from TMEM
+//      and hands to cp.async.bulk.tensor stores (and, with a residual, fills first by TMA loads); 3-stage operand ring
+//   2  same, tuned for the HBM-bound 1x1 convs that add a skip tensor (K <= 256: two chunk stages are enough):
+//      2-stage ring and 5 boxes per warp so that the residual of the next ~3 column groups is always in flight
+template <int BN, int EPI>
+struct PSmem {
+  static constexpr int NS = (EPI == 2) ? 2 : 3;
+  static constexpr int NBUF = (EPI == 2) ? 5 : 2;
+  static constexpr int B_TILE_BYTES = BN * BLOCK_K * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGING_OFFSET = NS * STAGE_BYTES;                                  // 1024-byte aligned
+  static constexpr int STAGING_BYTES = (EPI == 0) ? 4 * 32 * 36 * 4 : 4 * NBUF * 4096;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;                       // 512 B of mbarriers
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;                                    // bias of the layer (<= 256 floats)
+  static constexpr int TOTAL = BIAS_OFFSET + 1024 + 1024;                                 // + alignment slack
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB a CTA may use");
+};
 constexpr int P_PREFETCH = 4;         // chunks of A kept in flight in registers (load latency ~2-3k cycles under load)
 
 // ---- A-producer addressing (persistent kernel) -------------------------------------------------------
@@ -449,7 +481,7 @@ __device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p,
 // A_TMA: the A operand comes straight from HBM by TMA (cp.async.bulk.tensor, 128B swizzle, hardware zero fill
 // for the 3x3 padding) out of a tensor whose producer layer already wrote it as two FP16 planes (hi, lo'):
 // no A-producer warps, no register staging, no proxy fences — the CTA is 6 warps.
-template <int BN, int MODE, bool PRE, int MATH, bool A_TMA>
+template <int BN, int MODE, bool PRE, int MATH, bool A_TMA, int EPI>
 // 14 warps -> one SMSP hosts 4 of them -> the 16K-register SMSP file caps every thread at 128 registers
 __global__ void __launch_bounds__(A_TMA ? 192 : P_NUM_THREADS, 1)
 conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
@@ -463,15 +495,17 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  using S = Smem<BN>;
+  using S = PSmem<BN, EPI>;
+  constexpr int NS = S::NS;                      // operand ring depth
+  static_assert(EPI == 0 || MATH == MATH_F16, "the TMA-store epilogue is built for the fp16x3 path");
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
   auto full_a = [&](int s) { return bar_base + 8 * s; };
-  auto full_b = [&](int s) { return bar_base + 8 * (NUM_STAGES + s); };
-  auto empty = [&](int s) { return bar_base + 8 * (2 * NUM_STAGES + s); };
-  auto tmem_full = [&](int b) { return bar_base + 8 * (3 * NUM_STAGES + b); };
-  auto tmem_empty = [&](int b) { return bar_base + 8 * (3 * NUM_STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8 * (3 * NUM_STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFFSET + 8 * (3 * NUM_STAGES + 4));
+  auto full_b = [&](int s) { return bar_base + 8 * (NS + s); };
+  auto empty = [&](int s) { return bar_base + 8 * (2 * NS + s); };
+  auto tmem_full = [&](int b) { return bar_base + 8 * (3 * NS + b); };
+  auto tmem_empty = [&](int b) { return bar_base + 8 * (3 * NS + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8 * (3 * NS + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFFSET + 8 * (3 * NS + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B * p.Ho * p.Wo;
@@ -479,12 +513,14 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   const int num_tiles = num_m_tiles * num_n_tiles;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(full_a(s), A_TMA ? 1 : NUM_PRODUCER_WARPS);
       mbar_init(full_b(s), 1);
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+    if (EPI != 0)
+      for (int b = 0; b < 4 * S::NBUF; ++b) mbar_init(bar_base + 8 * (16 + b), 1);     // residual boxes: [warp][buffer]
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
@@ -507,8 +543,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
         const int b0 = m0 / HWi, rem = m0 - b0 * HWi;
         const int y0 = rem / p.W, x0 = rem - y0 * p.W;
         for (int j = 0; j < nchunks; ++j, ++g) {
-          const int s = g % NUM_STAGES;
-          const uint32_t ph = (g / NUM_STAGES) & 1;
+          const int s = g % NS;
+          const uint32_t ph = (g / NS) & 1;
           mbar_wait(empty(s), ph ^ 1);
           if (p.dbg && blockIdx.x == 0 && g < 512) p.dbg[4 * 512 + g] = clock64();
           const uint32_t a_dst = smem_base + s * S::STAGE_BYTES;
@@ -530,6 +566,11 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = (MATH == MATH_F16) ? make_idesc_f16(BLOCK_M, BN) : make_idesc_tf32(BLOCK_M, BN);
+    // hi and lo' weight images of a chunk are adjacent in shared memory = ONE K-major operand of 2*BN rows: a single
+    // N = 2*BN MMA forms A_hi*B_hi (main accumulator) and A_hi*B_lo' (correction accumulator, the next BN TMEM columns)
+    // and reads A_hi once instead of twice; A_lo'*B_hi then adds into the correction columns.
+    constexpr uint32_t idesc2 = (MATH == MATH_F16) ? make_idesc_f16(BLOCK_M, 2 * BN) : make_idesc_tf32(BLOCK_M, 2 * BN);
+    const bool merge = p.mma_merge && passes == 3;
     uint32_t g = 0, i = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
       const uint32_t b = i & 1;
@@ -537,8 +578,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
       tc_fence_after();
       const uint32_t acc = tmem_base + b * 2 * BN;
       for (int j = 0; j < nchunks; ++j, ++g) {
-        const int s = g % NUM_STAGES;
-        const uint32_t ph = (g / NUM_STAGES) & 1;
+        const int s = g % NS;
+        const uint32_t ph = (g / NS) & 1;
         mbar_wait(full_a(s), ph);
         if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[2 * 512 + g] = clock64();
         mbar_wait(full_b(s), ph);
@@ -552,11 +593,17 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / 8; ++kk) {
             const uint64_t dah = make_sw128_desc(a_hi + kk * 32), dbh = make_sw128_desc(b_hi + kk * 32);
-            umma<MATH>(acc, dah, dbh, idesc, (j | kk) != 0);
-            if (passes == 3) {
-              const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
-              umma<MATH>(acc + BN, dal, dbh, idesc, (j | kk) != 0);
-              umma<MATH>(acc + BN, dah, dbl, idesc, 1u);
+            if (merge) {
+              const uint64_t dal = make_sw128_desc(a_lo + kk * 32);
+              umma<MATH>(acc, dah, dbh, idesc2, (j | kk) != 0);
+              umma<MATH>(acc + BN, dal, dbh, idesc, 1u);
+            } else {
+              umma<MATH>(acc, dah, dbh, idesc, (j | kk) != 0);
+              if (passes == 3) {
+                const uint64_t dal = make_sw128_desc(a_lo + kk * 32), dbl = make_sw128_desc(b_lo + kk * 32);
+                umma<MATH>(acc + BN, dal, dbh, idesc, (j | kk) != 0);
+                umma<MATH>(acc + BN, dah, dbl, idesc, 1u);
+              }
             }
           }
           umma_commit(empty(s));
@@ -567,6 +614,179 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     }
   } else if (warp < 6) {
     // ===================== epilogue warpgroup =====================
+    if constexpr (EPI != 0) {
+      // TMEM -> registers -> (bias, ReLU, + residual) -> the warp's own 32-row x 128-byte staging boxes -> TMA store.
+      // A lane owns one output row (that is how tcgen05.ld hands the accumulator out); the 16-byte chunk c of row r
+      // lives at chunk c ^ (r & 7) — the 128B swizzle of the tensor maps — so the 32 lanes' float4 accesses are
+      // bank-conflict free and the TMA engine does the global coalescing.  No global load/store is issued by these
+      // warps: the skip tensor arrives by TMA into the same boxes (NBUF - 2 column groups ahead), results leave by TMA.
+      constexpr int NBUF = S::NBUF;
+      constexpr int D = NBUF - 2;                       // residual prefetch distance in column groups
+      const int ew = warp - 2, q = warp & 3;            // staging owner index / TMEM lane quarter
+      float* bias_s = reinterpret_cast<float*>(smem_gen + S::BIAS_OFFSET);
+      for (int c = threadIdx.x - 64; c < p.Cout_pad; c += 128) bias_s[c] = __ldg(p.bias + c);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t stg_base = smem_base + S::STAGING_OFFSET + ew * (NBUF * 4096);
+      uint8_t* stg_gen = smem_gen + S::STAGING_OFFSET + ew * (NBUF * 4096);
+      auto res_bar = [&](uint32_t bf) { return bar_base + 8 * (16 + ew * NBUF + bf); };
+      const bool has_res = p.residual != nullptr && !p.out_split;
+      const int swz = lane & 7;
+      uint32_t i = 0;
+      if (!p.out_split) {
+        constexpr int NU = BN / 32;                     // column groups (units) per tile
+        auto issue_res_load = [&](uint32_t v) {         // lane 0: residual box of unit v -> buffer v % NBUF
+          const uint32_t iv = v / NU, gv = v - iv * NU;
+          const long long tv = (long long)blockIdx.x + (long long)iv * gridDim.x;
+          if (tv < num_tiles) {
+            const int mt = (int)tv / num_n_tiles, nt = (int)tv - mt * num_n_tiles;
+            const int n0 = nt * BN + 32 * (int)gv;
+            if (n0 < p.Cout && mt * BLOCK_M + q * 32 < M) {
+              const uint32_t bar = res_bar(v % NBUF);
+              mbar_arrive_expect_tx(bar, 4096);
+              tma_load_2d(stg_base + (v % NBUF) * 4096, p.tmap_res, n0, mt * BLOCK_M + q * 32, bar);
+            }
+          }
+        };
+        if (has_res && lane == 0)
+          for (uint32_t v = 0; v < (uint32_t)D; ++v) issue_res_load(v);
+        uint32_t u = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+          const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
+          const uint32_t b = i & 1;
+          const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+          for (int gi = 0; gi < NU; ++gi, ++u) {
+            const uint32_t buf = u % NBUF;
+            const int n_base = n_tile * BN + 32 * gi;
+            const bool col_ok = n_base < p.Cout && m_tile * BLOCK_M + q * 32 < M;   // box not entirely outside the tensor
+            if (lane == 0) {
+              bulk_wait_read<1>();                      // the store that last used buffer (u - 2) % NBUF has left shared memory
+              if (has_res) issue_res_load(u + D);
+            }
+            if (gi == 0) {
+              if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[13 * 512 + i] = clock64();
+              mbar_wait_backoff<32>(tmem_full(b), (i >> 1) & 1);
+              tc_fence_after();
+              if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[14 * 512 + i] = clock64();
+            }
+            uint32_t r[32];
+            if (col_ok) {
+              tmem_ld32(acc + (uint32_t)(32 * gi), r);
+              tmem_ld_wait();
+              if (passes == 3) {
+                uint32_t rc[32];
+                tmem_ld32(acc + (uint32_t)(BN + 32 * gi), rc);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaf(__uint_as_float(rc[c]), 1.0f / 2048.0f, __uint_as_float(r[c])));
+              }
+            }
+            if (gi == NU - 1) {                         // last TMEM read of this tile: hand the buffer back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tmem_empty(b));
+            }
+            __syncwarp();                               // lane 0 has seen the buffer free
+            if (col_ok) {
+              if (has_res) mbar_wait(res_bar(buf), (u / NBUF) & 1);
+              uint8_t* rowp = stg_gen + buf * 4096 + lane * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float4 bq = *reinterpret_cast<const float4*>(bias_s + n_base + 4 * c);
+                float4 o = make_float4(__uint_as_float(r[4 * c]) + bq.x, __uint_as_float(r[4 * c + 1]) + bq.y,
+                                       __uint_as_float(r[4 * c + 2]) + bq.z, __uint_as_float(r[4 * c + 3]) + bq.w);
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                float4* slot = reinterpret_cast<float4*>(rowp + ((c ^ swz) << 4));
+                if (has_res) { const float4 rq = *slot; o.x += rq.x; o.y += rq.y; o.z += rq.z; o.w += rq.w; }
+                *slot = o;
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(p.tmap_out, stg_base + buf * 4096, n_base, m_tile * BLOCK_M + q * 32);
+                bulk_commit();
+              }
+            }
+          }
+          if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[15 * 512 + i] = clock64();
+        }
+      } else {
+        // output as two FP16 planes (hi, lo') for a TMA-fed consumer: 64 columns per unit = one 128-byte row per plane
+        constexpr int NU = BN / 64;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+          const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
+          const uint32_t b = i & 1;
+          const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
+          const bool row_ok = m_tile * BLOCK_M + q * 32 + lane < M;
+#pragma unroll 1
+          for (int gi = 0; gi < NU; ++gi) {
+            const int n_base = n_tile * BN + 64 * gi;
+            const bool col_ok = n_base < p.Cout && m_tile * BLOCK_M + q * 32 < M;
+            if (gi == 0) {
+              if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[13 * 512 + i] = clock64();
+              mbar_wait_backoff<32>(tmem_full(b), (i >> 1) & 1);
+              tc_fence_after();
+              if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[14 * 512 + i] = clock64();
+            }
+            float amax = 0.f;
+            uint8_t* rowp = stg_gen + lane * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32], rc[32];
+              if (col_ok) {
+                tmem_ld32(acc + (uint32_t)(64 * gi + 32 * h), r);
+                if (passes == 3) tmem_ld32(acc + (uint32_t)(BN + 64 * gi + 32 * h), rc);
+              }
+              if (h == 0) {                             // the TMEM loads above are in flight while lane 0 waits for the
+                if (lane == 0) bulk_wait_read<0>();     // previous unit's two stores to leave the boxes
+                __syncwarp();
+              }
+              if (col_ok) {
+                tmem_ld_wait();
+                if (passes == 3) {
+#pragma unroll
+                  for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(fmaf(__uint_as_float(rc[c]), 1.0f / 2048.0f, __uint_as_float(r[c])));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {           // 8 outputs -> one 16-byte chunk of each plane
+                  uint32_t hp[4], lp[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int c = 8 * k + 2 * e;
+                    float o0 = __uint_as_float(r[c]) + bias_s[n_base + 32 * h + c], o1 = __uint_as_float(r[c + 1]) + bias_s[n_base + 32 * h + c + 1];
+                    if (p.relu) { o0 = fmaxf(o0, 0.f); o1 = fmaxf(o1, 0.f); }
+                    amax = fmaxf(amax, fmaxf(fabsf(o0), fabsf(o1)));
+                    const float h0 = __uint_as_float(__float_as_uint(o0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(o1) & 0xFFFFE000u);
+                    const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn((o0 - h0) * 2048.f, (o1 - h1) * 2048.f);
+                    hp[e] = *reinterpret_cast<const uint32_t*>(&hh); lp[e] = *reinterpret_cast<const uint32_t*>(&ll);
+                  }
+                  const int ch = ((4 * h + k) ^ swz) << 4;
+                  *reinterpret_cast<uint4*>(rowp + ch) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                  *reinterpret_cast<uint4*>(rowp + 4096 + ch) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+                }
+              }
+            }
+            if (gi == NU - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tmem_empty(b));
+            }
+            if (col_ok) {
+              if (row_ok && amax > 60000.f && p.range_flag) *p.range_flag = 1;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_2d(p.tmap_out, stg_base, n_base, m_tile * BLOCK_M + q * 32);
+                tma_store_2d(p.tmap_out_lo, stg_base + 4096, n_base, m_tile * BLOCK_M + q * 32);
+                bulk_commit();
+              }
+            }
+          }
+          if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[15 * 512 + i] = clock64();
+        }
+      }
+      if (lane == 0) bulk_wait_read<0>();               // shared memory must outlive the last stores' reads
+    } else {
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int HW = p.Ho * p.Wo;
     uint32_t i = 0;
@@ -591,8 +811,10 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[13 * 512 + i] = clock64();
       mbar_wait_backoff(tmem_full(b), (i >> 1) & 1);
       tc_fence_after();
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[14 * 512 + i] = clock64();
       const uint32_t acc = tmem_base + b * 2 * BN + ((uint32_t)(q * 32) << 16);
       const int m = m_tile * BLOCK_M + q * 32 + lane;
 #pragma unroll
@@ -678,6 +900,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[15 * 512 + i] = clock64();
+    }
     }
   } else if (!A_TMA) {
     // ===================== A producers =====================
@@ -823,7 +1047,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
       if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[1 * 512 + g] = clock64();
       if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[(5 + warp - 6) * 512 + g] = clock64();
       ++g;
-      if (++stage == NUM_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == NS) { stage = 0; phase ^= 1; }
       if (++sj == nchunks) { sj = 0; st += gridDim.x; }
     };
     static_assert(P_PREFETCH == 4, "producer loop is unrolled for four (TF32) / two (FP16) register buffers");
@@ -844,12 +1068,12 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   }
 }
 
-template <int BN, int MODE, bool PRE, int MATH, bool A_TMA>
+template <int BN, int MODE, bool PRE, int MATH, bool A_TMA, int EPI>
 int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<BN, EPI>::TOTAL));
     int dev = 0;
     SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
     SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -858,23 +1082,37 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, num_sms);
-  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA><<<grid, A_TMA ? 192 : P_NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes, mt, nt);
+  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI><<<grid, A_TMA ? 192 : P_NUM_THREADS, PSmem<BN, EPI>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
 }
 
-template <int BN, int MATH>
-int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+template <int BN, int MATH, int EPI>
+int launch_persistent_epi(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   if (MATH == MATH_F16 && p.in_split) {
     if (p.pre_scale || p.mode == CONV_STEM7 || p.Cin % 64) { ctx->set_error("conv_tc: TMA-fed A needs a plain 1x1/3x3 conv with Cin % 64 == 0", __FILE__, __LINE__); return SUO_E_INVALID; }
-    if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true>(ctx, p, passes, s);
-    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, true>(ctx, p, passes, s);
+    if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true, (EPI == 2 ? 1 : EPI)>(ctx, p, passes, s);
+    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, true, EPI>(ctx, p, passes, s);
   }
-  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH, false>(ctx, p, passes, s);
-  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH, false>(ctx, p, passes, s);
-  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH, false>(ctx, p, passes, s);
-  return launch_persistent_inst<BN, CONV_1x1, false, MATH, false>(ctx, p, passes, s);
+  constexpr int E = EPI == 2 ? 1 : EPI;      // the residual-streaming plan exists for the TMA-fed 1x1 kernel only
+  if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH, false, E>(ctx, p, passes, s);
+  if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH, false, E>(ctx, p, passes, s);
+  if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH, false, E>(ctx, p, passes, s);
+  return launch_persistent_inst<BN, CONV_1x1, false, MATH, false, E>(ctx, p, passes, s);
+}
+
+template <int BN, int MATH>
+int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
+  if (MATH == MATH_F16) {
+    // TMA-store epilogue: needs the output (and skip) tensor maps, NHWC, <= 256 channels of bias in shared memory
+    const bool epi_tma = p.epi_tma && !p.out_nchw && p.Cout_pad <= 256 && !(p.residual && p.out_split);
+    if (epi_tma) {
+      if (p.residual && p.in_split && p.mode == CONV_1x1 && p.K <= 256) return launch_persistent_epi<BN, MATH_F16, 2>(ctx, p, passes, s);
+      return launch_persistent_epi<BN, MATH_F16, 1>(ctx, p, passes, s);
+    }
+  }
+  return launch_persistent_epi<BN, MATH, 0>(ctx, p, passes, s);
 }
 
 template <int BN>
