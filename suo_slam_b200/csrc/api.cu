@@ -58,7 +58,7 @@ int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, 
 }
 // CUtensorMap of a row-major 2-D view [rows, cols] (the NHWC tensor with pixels flattened) whose box is 32 rows x 128 bytes
 // (32 floats or 64 halfs), SWIZZLE_128B: what one epilogue warp stores (or fetches, for the skip tensor) per TMA operation.
-int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size_t rows, int cols) {
+int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size_t rows, int cols, int box_rows = 32) {
   CUtensorMap m;
   const int es = fp16 ? 2 : 4;
   if (((size_t)cols * es) % 16 || (reinterpret_cast<uintptr_t>(base) & 15)) { ctx->set_error("make_rows_tmap: row pitch / base not 16-byte aligned", __FILE__, __LINE__); return SUO_E_INVALID; }
@@ -66,7 +66,7 @@ int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size
   (void)rc;
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)cols * es};
-  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), 32};
+  const cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(&m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -95,8 +95,8 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
-  std::vector<std::array<unsigned char, 640>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip CUtensorMaps (split mode)
-  std::vector<int> epi_ok;                              // per op: the output / skip maps are valid
+  std::vector<std::array<unsigned char, 768>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip CUtensorMaps (split mode)
+  std::vector<int> epi_ok, raw_ok;                      // per op: the output / skip maps, the FP32 input map are valid
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
@@ -168,6 +168,9 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   if (p.in_split) { memcpy(p.tmap_hi, tm, 128); memcpy(p.tmap_lo, tm + 128, 128); }
   p.epi_tma = split_mode && ctx->opt_epi_tma && N.epi_ok[i];
   if (p.epi_tma) { memcpy(p.tmap_out, tm + 256, 128); memcpy(p.tmap_out_lo, tm + 384, 128); memcpy(p.tmap_res, tm + 512, 128); }
+  p.raw_tma = p.epi_tma && ctx->opt_raw_tma && N.raw_ok[i] && !p.in_split;
+  if (const char* e = getenv("SUO_RAW_ONLY_OP")) { if (atoi(e) >= 0 && atoi(e) != (int)i) p.raw_tma = 0; }   // developer bisect switch
+  if (p.raw_tma) memcpy(p.tmap_raw, tm + 640, 128);
 }
 
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
@@ -299,6 +302,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   *out = c;
   return SUO_OK;
 }
@@ -400,6 +404,7 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   }
   N.tmaps.resize(N.ops.size());
   N.epi_ok.assign(N.ops.size(), 0);
+  N.raw_ok.assign(N.ops.size(), 0);
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.type != OP_CONV) continue;
@@ -428,6 +433,12 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
     if (!rc2 && o.res >= 0) rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 512, N.act[o.res], false, rows, bo.C);
     if (rc2) return rc2;
     N.epi_ok[i] = 1;
+    if (o.mode == CONV_1x1 && o.Cin % 64 == 0 && N.bufs[o.in].C == o.Cin) {      // FP32 input [pixels, Cin] fetched by TMA (plan 3)
+      const int si = R / N.bufs[o.in].div;
+      rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 640, N.act[o.in], false, (size_t)ctx->max_crops * si * si, o.Cin, 128);
+      if (rc2) return rc2;
+      N.raw_ok[i] = 1;
+    }
   }
   const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
@@ -609,6 +620,10 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
       r2 = make_rows_tmap(ctx, p.tmap_out, d_out, false, rows, Cout);
     }
     if (!r2 && d_res) r2 = make_rows_tmap(ctx, p.tmap_res, d_res, false, rows, Cout);
+    if (!r2 && ctx->opt_raw_tma && !tma_in && p.mode == CONV_1x1 && Cin % 64 == 0) {
+      r2 = make_rows_tmap(ctx, p.tmap_raw, d_in, false, (size_t)B * H * W, Cin, 128);
+      p.raw_tma = r2 ? 0 : 1;
+    }
     if (r2) { if (d_in16) cudaFree(d_in16); return r2; }
     p.epi_tma = 1;
   }

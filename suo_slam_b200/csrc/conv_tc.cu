@@ -419,13 +419,20 @@ constexpr int P_NUM_THREADS = 32 * (2 + 4 + NUM_PRODUCER_WARPS);
 //      and hands to cp.async.bulk.tensor stores (and, with a residual, fills first by TMA loads); 3-stage operand ring
 //   2  same, tuned for the HBM-bound 1x1 convs that add a skip tensor (K <= 256: two chunk stages are enough):
 //      2-stage ring and 5 boxes per warp so that the residual of the next ~3 column groups is always in flight
+//   3  plan 1's epilogue for the register-fed 1x1 convs (FP32 input, optional BN+ReLU prologue): the FP32 activations
+//      come by TMA into a ring of four 16 KB boxes (128 pixels x 32 floats) and the producer warps only transform
+//      shared -> shared (prologue, FP16 hi/lo' split); 2-stage operand ring
+constexpr int RAW_BOXES = 4;
+constexpr int RAW_BOX_BYTES = BLOCK_M * 32 * 4;
 template <int BN, int EPI>
 struct PSmem {
-  static constexpr int NS = (EPI == 2) ? 2 : 3;
+  static constexpr int NS = (EPI == 2 || EPI == 3) ? 2 : 3;
   static constexpr int NBUF = (EPI == 2) ? 5 : 2;
+  static constexpr int RAW_OFFSET = 2 * (2 * A_TILE_BYTES + 2 * BN * BLOCK_K * 4);      // plan 3: raw ring right behind the 2 operand stages
+  static constexpr int RING_BYTES = (EPI == 3) ? RAW_OFFSET + RAW_BOXES * RAW_BOX_BYTES : NS * (2 * A_TILE_BYTES + 2 * BN * BLOCK_K * 4);
   static constexpr int B_TILE_BYTES = BN * BLOCK_K * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGING_OFFSET = NS * STAGE_BYTES;                                  // 1024-byte aligned
+  static constexpr int STAGING_OFFSET = RING_BYTES;                                        // 1024-byte aligned
   static constexpr int STAGING_BYTES = (EPI == 0) ? 4 * 32 * 36 * 4 : 4 * NBUF * 4096;
   static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;                       // 512 B of mbarriers
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;                                    // bias of the layer (<= 256 floats)
@@ -483,7 +490,7 @@ __device__ __noinline__ void cursor_set_tile(LoadCursor& c, const ConvParams& p,
 // no A-producer warps, no register staging, no proxy fences — the CTA is 6 warps.
 template <int BN, int MODE, bool PRE, int MATH, bool A_TMA, int EPI>
 // 14 warps -> one SMSP hosts 4 of them -> the 16K-register SMSP file caps every thread at 128 registers
-__global__ void __launch_bounds__(A_TMA ? 192 : P_NUM_THREADS, 1)
+__global__ void __launch_bounds__(A_TMA ? 192 : (EPI == 3 ? P_NUM_THREADS + 32 : P_NUM_THREADS), 1)
 conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes, const int num_m_tiles, const int num_n_tiles) {
   static_assert(!A_TMA || (MATH == MATH_F16 && !PRE && MODE != CONV_STEM7), "TMA-fed A needs pre-split FP16 activations");
   // MATH_TF32: chunk = 32 floats, operands FP32 words read as TF32 (hi = top 19 bits, lo = x - hi).
@@ -498,6 +505,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   using S = PSmem<BN, EPI>;
   constexpr int NS = S::NS;                      // operand ring depth
   static_assert(EPI == 0 || MATH == MATH_F16, "the TMA-store epilogue is built for the fp16x3 path");
+  constexpr bool RAW = (EPI == 3);               // A operand: FP32 tensor -> TMA -> raw ring -> producer warps -> operand ring
+  static_assert(!RAW || (MODE == CONV_1x1 && !A_TMA), "raw-TMA A path: register-fed 1x1 convs only");
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
   auto full_a = [&](int s) { return bar_base + 8 * s; };
   auto full_b = [&](int s) { return bar_base + 8 * (NS + s); };
@@ -506,6 +515,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   auto tmem_empty = [&](int b) { return bar_base + 8 * (3 * NS + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8 * (3 * NS + 4);
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + S::BAR_OFFSET + 8 * (3 * NS + 4));
+  auto raw_full = [&](uint32_t b) { return bar_base + 8 * (40 + b); };
+  auto raw_empty = [&](uint32_t b) { return bar_base + 8 * (40 + RAW_BOXES + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.B * p.Ho * p.Wo;
@@ -521,6 +532,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
     if (EPI != 0)
       for (int b = 0; b < 4 * S::NBUF; ++b) mbar_init(bar_base + 8 * (16 + b), 1);     // residual boxes: [warp][buffer]
+    if (RAW)
+      for (int b = 0; b < RAW_BOXES; ++b) { mbar_init(raw_full(b), 1); mbar_init(raw_empty(b), NUM_PRODUCER_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 4 * BN);
@@ -648,7 +661,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
           }
         };
         if (has_res && lane == 0)
-          for (uint32_t v = 0; v < (uint32_t)D; ++v) issue_res_load(v);
+          for (int v = 0; v < D; ++v) issue_res_load((uint32_t)v);
         uint32_t u = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
           const int m_tile = t / num_n_tiles, n_tile = t - m_tile * num_n_tiles;
@@ -903,6 +916,98 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
       if (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && i < 512) p.dbg[15 * 512 + i] = clock64();
     }
     }
+  } else if (RAW && warp == 6 + NUM_PRODUCER_WARPS) {
+    // ===================== raw activation loader (plan 3): FP32 [pixels, Cin] -> 16 KB boxes, runs RAW_BOXES ahead =====================
+    if (lane == 0) {
+      uint32_t x = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_tile = t / num_n_tiles;
+        for (int j = 0; j < nchunks; ++j)
+          for (int h = 0; h < 2; ++h, ++x) {
+            const uint32_t slot = x % RAW_BOXES;
+            mbar_wait(raw_empty(slot), ((x / RAW_BOXES) & 1) ^ 1);
+            mbar_arrive_expect_tx(raw_full(slot), RAW_BOX_BYTES);
+            tma_load_2d(smem_base + S::RAW_OFFSET + slot * RAW_BOX_BYTES, p.tmap_raw, 64 * j + 32 * h, m_tile * BLOCK_M, raw_full(slot));
+          }
+      }
+    }
+  } else if (RAW) {
+    // ===================== A producers (plan 3): shared -> shared transform =====================
+    // Thread (row r, 16-byte operand slot g8) turns K elements [8 g8, 8 g8 + 8) of its four rows — two 16-byte chunks of
+    // raw box g8 / 4 — into one 16-byte chunk of the hi plane and one of the lo' plane.  No global loads, no address
+    // math per tile; the only waits are the two mbarriers (raw box full, operand stage free).
+    const int pt = threadIdx.x - 192;           // 0..255
+    const int g8 = pt & 7, r0 = pt >> 3;
+    const int hb = g8 >> 2, c2 = 2 * (g8 & 3);
+    const uint8_t* raw_gen = smem_gen + S::RAW_OFFSET;
+    uint32_t g = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int j = 0; j < nchunks; ++j, ++g) {
+        const uint32_t x0 = 2 * g, slot0 = x0 % RAW_BOXES;           // RAW_BOXES is even: the pair never wraps
+        mbar_wait(raw_full(slot0), (x0 / RAW_BOXES) & 1);
+        mbar_wait(raw_full(slot0 + 1), (x0 / RAW_BOXES) & 1);
+        float4 cur[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 32 * i;
+          const uint8_t* rowp = raw_gen + (slot0 + hb) * RAW_BOX_BYTES + r * 128;
+          cur[2 * i] = *reinterpret_cast<const float4*>(rowp + ((c2 ^ (r & 7)) << 4));
+          cur[2 * i + 1] = *reinterpret_cast<const float4*>(rowp + (((c2 + 1) ^ (r & 7)) << 4));
+        }
+        if (PRE) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.pre_scale + KC * j + 8 * g8) + u);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.pre_shift + KC * j + 8 * g8) + u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float4& x = cur[2 * i + u];
+              x.x = fmaxf(fmaf(x.x, sc.x, sh.x), 0.f); x.y = fmaxf(fmaf(x.y, sc.y, sh.y), 0.f);
+              x.z = fmaxf(fmaf(x.z, sc.z, sh.z), 0.f); x.w = fmaxf(fmaf(x.w, sc.w, sh.w), 0.f);
+            }
+          }
+        }
+        // the boxes are refilled by the async proxy (TMA): order this thread's generic-proxy reads before that write,
+        // then release (without the fence the ld.shared of a lane may still be in flight when the next box lands)
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(raw_empty(slot0)); mbar_arrive(raw_empty(slot0 + 1)); }
+        mbar_wait(empty(stage), phase ^ 1);
+        if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[0 * 512 + g] = clock64();
+        uint8_t* a_hi = smem_gen + stage * S::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + A_TILE_BYTES;
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 32 * i;
+          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((g8 ^ (r & 7)) << 4);
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 x = cur[2 * i + u];
+            const float h0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            const float h2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+            __half2 a = __floats2half2_rn(h0, h1), b = __floats2half2_rn(h2, h3);
+            __half2 c = __floats2half2_rn((x.x - h0) * 2048.f, (x.y - h1) * 2048.f), d = __floats2half2_rn((x.z - h2) * 2048.f, (x.w - h3) * 2048.f);
+            hw[2 * u] = *reinterpret_cast<uint32_t*>(&a); hw[2 * u + 1] = *reinterpret_cast<uint32_t*>(&b);
+            lw[2 * u] = *reinterpret_cast<uint32_t*>(&c); lw[2 * u + 1] = *reinterpret_cast<uint32_t*>(&d);
+          }
+          *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          if (passes == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        // rows past the end of the tensor are zero-filled by TMA (finite after the prologue): no row mask needed here
+        if (amax > 60000.f && p.range_flag) *p.range_flag = 1;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(stage));
+        if (p.dbg && blockIdx.x == 0 && pt == 0 && g < 512) p.dbg[1 * 512 + g] = clock64();
+        if (p.dbg && blockIdx.x == 0 && lane == 0 && g < 512) p.dbg[(5 + warp - 6) * 512 + g] = clock64();
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (!A_TMA) {
     // ===================== A producers =====================
     const int pt = threadIdx.x - 192;           // 0..255
@@ -1082,7 +1187,7 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, num_sms);
-  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI><<<grid, A_TMA ? 192 : P_NUM_THREADS, PSmem<BN, EPI>::TOTAL, s>>>(p, passes, mt, nt);
+  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI><<<grid, A_TMA ? 192 : (EPI == 3 ? P_NUM_THREADS + 32 : P_NUM_THREADS), PSmem<BN, EPI>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
@@ -1092,10 +1197,14 @@ template <int BN, int MATH, int EPI>
 int launch_persistent_epi(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
   if (MATH == MATH_F16 && p.in_split) {
     if (p.pre_scale || p.mode == CONV_STEM7 || p.Cin % 64) { ctx->set_error("conv_tc: TMA-fed A needs a plain 1x1/3x3 conv with Cin % 64 == 0", __FILE__, __LINE__); return SUO_E_INVALID; }
-    if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true, (EPI == 2 ? 1 : EPI)>(ctx, p, passes, s);
-    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, true, EPI>(ctx, p, passes, s);
+    if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true, (EPI >= 2 ? 1 : EPI)>(ctx, p, passes, s);
+    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, true, (EPI == 3 ? 1 : EPI)>(ctx, p, passes, s);
   }
-  constexpr int E = EPI == 2 ? 1 : EPI;      // the residual-streaming plan exists for the TMA-fed 1x1 kernel only
+  if (MATH == MATH_F16 && EPI == 3) {          // FP32 activations by TMA + shared->shared transform (1x1 only)
+    if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH_F16, false, (EPI == 3 ? 3 : 1)>(ctx, p, passes, s);
+    return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, false, (EPI == 3 ? 3 : 1)>(ctx, p, passes, s);
+  }
+  constexpr int E = (EPI == 2 || EPI == 3) ? 1 : EPI;      // plans 2 and 3 exist for 1x1 kernels only
   if (p.mode == CONV_3x3) return launch_persistent_inst<BN, CONV_3x3, false, MATH, false, E>(ctx, p, passes, s);
   if (p.mode == CONV_STEM7) return launch_persistent_inst<BN, CONV_STEM7, false, MATH, false, E>(ctx, p, passes, s);
   if (p.pre_scale) return launch_persistent_inst<BN, CONV_1x1, true, MATH, false, E>(ctx, p, passes, s);
@@ -1109,6 +1218,7 @@ int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_
     const bool epi_tma = p.epi_tma && !p.out_nchw && p.Cout_pad <= 256 && !(p.residual && p.out_split);
     if (epi_tma) {
       if (p.residual && p.in_split && p.mode == CONV_1x1 && p.K <= 256) return launch_persistent_epi<BN, MATH_F16, 2>(ctx, p, passes, s);
+      if (p.raw_tma && !p.in_split && p.mode == CONV_1x1 && p.Cin % 64 == 0) return launch_persistent_epi<BN, MATH_F16, 3>(ctx, p, passes, s);
       return launch_persistent_epi<BN, MATH_F16, 1>(ctx, p, passes, s);
     }
   }

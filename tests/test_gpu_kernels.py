@@ -35,6 +35,16 @@ CONV_CASES = [
     (1, 32, 32, 48, 64, 7, 2, False, False, True),      # stem, 44+4 channel layout
     (2, 16, 16, 256, 41, 1, 1, False, False, False),    # tmpOut (N = 41 -> padded tile)
     (2, 16, 16, 64, 256, 1, 1, False, True, False),     # tmpOut_ (K = 64)
+    (3, 32, 32, 64, 64, 1, 1, True, False, True),       # r1.conv1: 64-column tiles, K = 64, prologue
+    (3, 16, 16, 128, 64, 1, 1, True, False, True),      # r4.conv1: 64-column tiles, two K chunks
+    (3, 32, 32, 64, 128, 1, 1, False, False, False),    # r1.conv4 (skip projection, FP32 in / FP32 out)
+    (3, 1, 1, 256, 128, 1, 1, True, False, True),       # deepest hourglass level of a 64x64 crop: M = 3
+    (3, 2, 2, 128, 256, 1, 1, False, True, False),      # M = 12
+    (40, 32, 32, 256, 128, 1, 1, True, False, True),    # 320 tiles: several tiles per CTA (persistent loop, ring wrap)
+    (40, 32, 32, 128, 256, 1, 1, False, True, False),   # 640 tiles, skip tensor streamed
+    (24, 32, 32, 128, 128, 3, 1, False, False, True),   # 192 tiles of the 3x3
+    (40, 32, 32, 128, 256, 1, 1, False, False, False),  # two column tiles, several tiles per CTA, no skip
+    (40, 32, 32, 128, 128, 1, 1, False, True, False),   # one column tile, skip tensor
 ]
 
 
