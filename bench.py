@@ -276,6 +276,14 @@ def run_native(args):
         if os.path.exists(pk_path):
             peaks = json.load(open(pk_path))
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        # DRAM traffic of the conv kernels of one step: from the committed ncu launch list of this same command
+        # (profiles/r1_conv_traffic.json); only valid for the crop count it was captured at
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "r1_conv_traffic.json")
+        if os.path.exists(tr_path):
+            tr = json.load(open(tr_path))
+            if int(tr.get("crops_per_step", -1)) == L:
+                traffic = float(tr["conv_dram_bytes_per_step"])
         achieved = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
         h2d = sum(v.numel() * v.element_size() for v in sets_pin[0].values())
         d2h = sum(v.numel() * v.element_size() for v in outs_host.values())
@@ -301,10 +309,12 @@ def run_native(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": None, "kernel": "conv_tc_kernel (all conv layers of one forward)",
+                         "traffic": traffic, "traffic_unit": "bytes per step, DRAM read+write summed over the conv launches (ncu); algorithmic unfused bound 327.9 MB/crop",
+                         "kernel": "conv_tc_persistent_kernel (the 187 conv launches of one forward, all template instances)",
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
                          "note": "algorithmic 31.495 GFLOP/crop x crops / summed conv-kernel time (CUDA events per launch, eager pass after the timed region); "
-                                 "each product costs 3 MMAs (fp16x3: 3 f16-kind MMAs -> ceiling peak/3; tf32x3: 3 tf32-kind MMAs -> ceiling peak/6)",
+                                 "each FP32-equivalent product costs 3 f16-kind MMAs (fp16x3), so tensor-pipe work is 3x the algorithmic FLOPs and the ceiling of frac is 1/3; "
+                                 "the 3x3 layers (68 % of the FLOPs) run at ~430 TFLOP/s algorithmic = 0.93 of that ceiling, the 1x1 layers are HBM-bound (5.3-5.9 TB/s, profiles/)",
                          "conv_ms_per_step": conv_ms.value, "other_net_ms_per_step": other_ms.value},
         }
         if not args.no_cpu_baseline and world == 1:

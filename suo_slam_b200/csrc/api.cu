@@ -127,6 +127,8 @@ struct CtxExtra {
   DevScratch io;        // staged inputs/outputs of host-pointer calls
   DevScratch ba;        // BA err/level/fv scratch
   DevScratch fr;        // suo_frames workspace
+  int32_t* pnp_off = nullptr;   // row offsets c * num_kp of the gated keypoint lists (grown on demand)
+  int pnp_off_n = 0;
   bool loaded = false;
 };
 
@@ -164,6 +166,7 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   p.out_split = split_mode && bo.kind == 1;
   p.out_plane = (size_t)ctx->max_crops * p.Ho * p.Wo * bo.C;
   p.mma_merge = ctx->opt_mma_merge;
+  p.trace = ctx->trace;
   const unsigned char* tm = N.tmaps[i].data();
   if (p.in_split) { memcpy(p.tmap_hi, tm, 128); memcpy(p.tmap_lo, tm + 128, 128); }
   p.epi_tma = split_mode && ctx->opt_epi_tma && N.epi_ok[i];
@@ -303,6 +306,11 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
+  if (getenv("SUO_TRACE")) {
+    if (cudaMalloc(&c->trace, (1 + 4 * 8192) * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(c->trace, 0, (1 + 4 * 8192) * sizeof(unsigned long long));
+    else c->trace = nullptr;
+  }
   *out = c;
   return SUO_OK;
 }
@@ -310,6 +318,20 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
 void suo_destroy(suo_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->trace) {
+    std::vector<unsigned long long> h(1 + 4 * 8192);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h.data(), ctx->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      const std::string path = std::string(getenv("SUO_TRACE") ? getenv("SUO_TRACE") : "trace") + "." + std::to_string((unsigned long long)(uintptr_t)ctx) + ".csv";
+      if (FILE* f = fopen(path.c_str(), "w")) {
+        fprintf(f, "launch,t_start_ns,t_end_ns,grid,smid\n");
+        for (unsigned long long k = 0; k < std::min<unsigned long long>(h[0], 8192); ++k)
+          fprintf(f, "%llu,%llu,%llu,%llu,%llu\n", k, h[1 + 4 * k], h[2 + 4 * k], h[3 + 4 * k], h[4 + 4 * k]);
+        fclose(f);
+      }
+    }
+    cudaFree(ctx->trace);
+  }
   CtxExtra* x = X(ctx);
   if (x) {
     NetState& N = x->net;
@@ -326,6 +348,7 @@ void suo_destroy(suo_ctx* ctx) {
     if (x->io.d) cudaFree(x->io.d);
     if (x->ba.d) cudaFree(x->ba.d);
     if (x->fr.d) cudaFree(x->fr.d);
+    if (x->pnp_off) cudaFree(x->pnp_off);
     delete x;
   }
   delete ctx;
@@ -870,13 +893,20 @@ static int solve_keypoints_device(suo_ctx* ctx, Bump& bp, const float* d_uv, con
                                d_ys, d_cnt, d_kpi, d_used, s);
   if (rc) return rc;
   // PnP: object c owns rows [c*K, c*K + count[c])
-  int32_t* d_off = bp.take<int32_t>(L);
-  {
-    std::vector<int32_t> off(L);
-    for (int c = 0; c < L; ++c) off[c] = c * K;
-    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, off.data(), L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // `off` goes out of scope
+  // (the offsets c*K never change: built once per context, so the device path stays free of host synchronisation)
+  CtxExtra* xo = X(ctx);
+  if (xo->pnp_off_n < L) {
+    const int n = std::max(L, ctx->max_crops);
+    std::vector<int32_t> off(n);
+    for (int c = 0; c < n; ++c) off[c] = c * K;
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));        // (re)allocation only: earlier work may still read the old array
+    if (xo->pnp_off) cudaFree(xo->pnp_off);
+    xo->pnp_off = nullptr; xo->pnp_off_n = 0;
+    SUO_CUDA_TRY(ctx, cudaMalloc(&xo->pnp_off, off.size() * sizeof(int32_t)));
+    SUO_CUDA_TRY(ctx, cudaMemcpy(xo->pnp_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    xo->pnp_off_n = n;
   }
+  const int32_t* d_off = xo->pnp_off;
   rc = launch_pnp_batch_counts(ctx, d_xs, d_ys, d_off, d_cnt, L, 0.001, seed, nullptr, d_Tpnp, d_pst, s);
   if (rc) return rc;
   if (!run_ba) return SUO_OK;

@@ -69,6 +69,7 @@ struct ConvParams {
   alignas(64) unsigned char tmap_out[128];     // FP32 output [rows, out_c], box 32 rows x 32 floats — or the hi plane [rows, C] FP16, box 32 x 64
   alignas(64) unsigned char tmap_out_lo[128];  // lo' plane (out_split)
   alignas(64) unsigned char tmap_res[128];     // skip tensor, FP32 [rows, out_c], box 32 x 32
+  unsigned long long* trace;  // developer tool (SUO_TRACE): [0] = launch counter, then {globaltimer start, end, grid, smid} per persistent conv launch
   int raw_tma;            // tmap_raw is valid: a register-fed 1x1 conv may fetch its FP32 input by TMA (plan 3)
   alignas(64) unsigned char tmap_raw[128];     // FP32 input [rows, Cin], box 128 rows x 32 floats
 };
@@ -127,7 +128,9 @@ struct suo_ctx {
   std::string err;
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
-  int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
+  int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
+  unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
+  int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
   void* net = nullptr;  // NetState (net_exec.cu)
   void* scratch = nullptr; size_t scratch_bytes = 0;        // device scratch for host-pointer calls
   void* pinned = nullptr; size_t pinned_bytes = 0;          // pinned staging

@@ -523,6 +523,16 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   const int nchunks = p.K / KC;
   const int num_tiles = num_m_tiles * num_n_tiles;
 
+  unsigned long long trace_slot = 0;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x == 0) {
+    trace_slot = atomicAdd(p.trace, 1ull);
+    if (trace_slot < 8192) {
+      unsigned long long t; uint32_t smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[1 + 4 * trace_slot] = t; p.trace[1 + 4 * trace_slot + 2] = gridDim.x; p.trace[1 + 4 * trace_slot + 3] = smid;
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(full_a(s), A_TMA ? 1 : NUM_PRODUCER_WARPS);
@@ -1167,6 +1177,11 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_slot < 8192) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[1 + 4 * trace_slot + 1] = t;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 4 * BN);
@@ -1186,7 +1201,7 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   }
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
-  const int grid = std::min(mt * nt, num_sms);
+  const int grid = std::min(mt * nt, ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms);
   conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI><<<grid, A_TMA ? 192 : (EPI == 3 ? P_NUM_THREADS + 32 : P_NUM_THREADS), PSmem<BN, EPI>::TOTAL, s>>>(p, passes, mt, nt);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" | tee -a gpurun_out/summary.txt; timeout -s KILL $1 "${@:2}" > gpurun_out/$name.log 2>&1; echo "rc=$?" | tee -a gpurun_out/summary.txt; tail -n ${TAILN:-3} gpurun_out/$name.log | cut -c1-400 | tee -a gpurun_out/summary.txt; }
+run s1 300 python tools/dual_stream.py 1 32
+SUO_GRID_CAP=74 run s2_74 300 python tools/dual_stream.py 2 32
+SUO_GRID_CAP=148 run s2_148 300 python tools/dual_stream.py 2 32
+SUO_GRID_CAP=100 run s2_100 300 python tools/dual_stream.py 2 32
+SUO_GRID_CAP=50 run s3_50 300 python tools/dual_stream.py 3 30
+SUO_GRID_CAP=74 run s4_74 300 python tools/dual_stream.py 4 32
+SUO_GRID_CAP=37 run s4_37 300 python tools/dual_stream.py 4 32
+run f1 300 python tools/dual_stream.py 1 1
+run f2s2 300 python tools/dual_stream.py 2 2
