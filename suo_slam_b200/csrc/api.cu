@@ -17,6 +17,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "ba_math.cuh"
 
 namespace {
 
@@ -127,6 +128,7 @@ struct CtxExtra {
   DevScratch io;        // staged inputs/outputs of host-pointer calls
   DevScratch ba;        // BA err/level/fv scratch
   DevScratch fr;        // suo_frames workspace
+  DevScratch bg;        // coupled-graph BA structure + workspace (ba_global.cu)
   int32_t* pnp_off = nullptr;   // row offsets c * num_kp of the gated keypoint lists (grown on demand)
   int pnp_off_n = 0;
   bool loaded = false;
@@ -348,6 +350,7 @@ void suo_destroy(suo_ctx* ctx) {
     if (x->io.d) cudaFree(x->io.d);
     if (x->ba.d) cudaFree(x->ba.d);
     if (x->fr.d) cudaFree(x->fr.d);
+    if (x->bg.d) cudaFree(x->bg.d);
     if (x->pnp_off) cudaFree(x->pnp_off);
     delete x;
   }
@@ -810,6 +813,119 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
   return SUO_OK;
 }
 
+// ---- coupled camera+object graphs: host-side grouping of the edges, then ba_global_kernel ----------------------
+// True when some edge has a free camera AND a free object (global BA, lib/object_slam.py:736-778) or a problem has
+// more vertices than the block-diagonal kernel keeps in shared memory.
+static bool ba_needs_global(int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, const uint8_t* fixed,
+                            const int32_t* e_obj, const int32_t* e_cam) {
+  for (int pr = 0; pr < n_prob; ++pr) {
+    if (prob_vert[pr + 1] - prob_vert[pr] > 64) return true;
+    for (int e = prob_edge[pr]; e < prob_edge[pr + 1]; ++e)
+      if (e_obj[e] >= 0 && !fixed[e_obj[e]] && !fixed[e_cam[e]]) return true;
+  }
+  return false;
+}
+
+// Host arrays describe the graph structure (indices only); every d_* pointer is the device copy of the packed graph.
+static int run_ba_global(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, const uint8_t* fixed,
+                         int n_vert, const int32_t* e_obj, const int32_t* e_cam, int n_edges, ba::BaArgs base, cudaStream_t s) {
+  CtxExtra* x = X(ctx);
+  std::vector<int32_t> perm(n_edges), pair_cam, pair_obj, pair_eoff, prob_pair(n_prob + 1, 0), obj_slot(n_vert, -1),
+      slot_vert, prob_slot(n_prob, 0), prob_nobj(n_prob, 0), peer;
+  std::vector<long long> prob_peer(n_prob, 0), prob_S(n_prob, 0);
+  std::vector<uint8_t> is_obj(n_vert, 0), is_cam(n_vert, 0);
+  long long S_total = 0;
+  for (int pr = 0; pr < n_prob; ++pr) {
+    const int v0 = prob_vert[pr], v1 = prob_vert[pr + 1], e0 = prob_edge[pr], e1 = prob_edge[pr + 1];
+    for (int e = e0; e < e1; ++e) {
+      if (e_cam[e] < v0 || e_cam[e] >= v1 || (e_obj[e] >= 0 && (e_obj[e] < v0 || e_obj[e] >= v1))) {
+        ctx->set_error("suo_ba_batch: edge references a vertex outside its problem", __FILE__, __LINE__); return SUO_E_INVALID;
+      }
+      is_cam[e_cam[e]] = 1;
+      if (e_obj[e] >= 0) is_obj[e_obj[e]] = 1;
+      perm[e] = e;
+    }
+    std::stable_sort(perm.begin() + e0, perm.begin() + e1, [&](int32_t a, int32_t b) {
+      return e_cam[a] != e_cam[b] ? e_cam[a] < e_cam[b] : e_obj[a] < e_obj[b];
+    });
+    prob_pair[pr] = (int32_t)pair_cam.size();
+    for (int i = e0; i < e1; ++i) {
+      const int e = perm[i];
+      if (i == e0 || e_cam[e] != pair_cam.back() || e_obj[e] != pair_obj.back()) { pair_cam.push_back(e_cam[e]); pair_obj.push_back(e_obj[e]); pair_eoff.push_back(i); }
+    }
+    prob_slot[pr] = (int32_t)slot_vert.size();
+    int no = 0;
+    for (int v = v0; v < v1; ++v) {
+      if (is_obj[v] && is_cam[v] && !fixed[v]) { ctx->set_error("suo_ba_batch: a free vertex is used both as object and as camera", __FILE__, __LINE__); return SUO_E_INVALID; }
+      if (is_obj[v] && !fixed[v]) { obj_slot[v] = no++; slot_vert.push_back(v); }
+    }
+    prob_nobj[pr] = no;
+    prob_S[pr] = S_total;
+    S_total += (long long)(6 * no) * (6 * no) + 12 * no;
+  }
+  const int n_pairs = (int)pair_cam.size();
+  prob_pair[n_prob] = n_pairs;
+  pair_eoff.push_back(prob_edge[n_prob]);   // prob_edge is one offset array: the problems' edge ranges are contiguous
+  std::vector<int32_t> cam_poff(n_vert + 1, 0), obj_poff(n_vert + 1, 0), obj_plist(n_pairs);
+  for (int gp = 0; gp < n_pairs; ++gp) { cam_poff[pair_cam[gp] + 1]++; if (pair_obj[gp] >= 0) obj_poff[pair_obj[gp] + 1]++; }
+  for (int v = 0; v < n_vert; ++v) { cam_poff[v + 1] += cam_poff[v]; obj_poff[v + 1] += obj_poff[v]; }
+  {
+    std::vector<int32_t> fill(obj_poff.begin(), obj_poff.end() - 1);
+    for (int gp = 0; gp < n_pairs; ++gp) if (pair_obj[gp] >= 0) obj_plist[fill[pair_obj[gp]]++] = gp;
+  }
+  for (int pr = 0; pr < n_prob; ++pr) {
+    const int no = prob_nobj[pr], pp0 = prob_pair[pr], pp1 = prob_pair[pr + 1];
+    prob_peer[pr] = (long long)peer.size();
+    peer.resize(peer.size() + (size_t)(pp1 - pp0) * no, -1);
+    int32_t* P = peer.data() + prob_peer[pr];
+    for (int a0 = pp0; a0 < pp1;) {
+      int a1 = a0;
+      while (a1 < pp1 && pair_cam[a1] == pair_cam[a0]) ++a1;
+      if (!fixed[pair_cam[a0]])
+        for (int q = a0; q < a1; ++q) {
+          const int sq = pair_obj[q] >= 0 ? obj_slot[pair_obj[q]] : -1;
+          if (sq < 0) continue;
+          for (int pp = a0; pp < a1; ++pp) P[(size_t)(pp - pp0) * no + sq] = q;
+        }
+      a0 = a1;
+    }
+  }
+  // one upload of the structure, one workspace
+  struct Seg { const void* src; size_t bytes; size_t off; };
+  std::vector<Seg> segs;
+  size_t off = 0;
+  auto add = [&](const void* src, size_t bytes) { off = align_up(off, 256); segs.push_back({src, bytes, off}); off += bytes; return segs.size() - 1; };
+  const size_t i_perm = add(perm.data(), perm.size() * 4), i_pc = add(pair_cam.data(), pair_cam.size() * 4), i_po = add(pair_obj.data(), pair_obj.size() * 4),
+               i_pe = add(pair_eoff.data(), pair_eoff.size() * 4), i_pp = add(prob_pair.data(), prob_pair.size() * 4), i_cp = add(cam_poff.data(), cam_poff.size() * 4),
+               i_op = add(obj_poff.data(), obj_poff.size() * 4), i_ol = add(obj_plist.data(), obj_plist.size() * 4), i_os = add(obj_slot.data(), obj_slot.size() * 4),
+               i_sv = add(slot_vert.data(), slot_vert.size() * 4), i_ps = add(prob_slot.data(), prob_slot.size() * 4), i_peer = add(peer.data(), peer.size() * 4),
+               i_ppe = add(prob_peer.data(), prob_peer.size() * 8), i_pn = add(prob_nobj.data(), prob_nobj.size() * 4), i_pS = add(prob_S.data(), prob_S.size() * 8);
+  const size_t struct_bytes = align_up(off, 256);
+  const size_t work_bytes = ((size_t)S_total + (size_t)n_pairs * 156 + (size_t)n_vert * (36 + 6 + 6 + 36)) * 8 + 2 * (size_t)n_vert * sizeof(ba::SE3q) + n_vert + 8 * 256;
+  // the previous launch may still be reading the workspace
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  int rc = x->bg.grow(ctx, struct_bytes + work_bytes);
+  if (rc) return rc;
+  uint8_t* d = static_cast<uint8_t*>(x->bg.d);
+  std::vector<uint8_t> stage(struct_bytes, 0);
+  for (const Seg& g : segs) if (g.bytes) memcpy(stage.data() + g.off, g.src, g.bytes);
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d, stage.data(), struct_bytes, cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));   // `stage` goes out of scope
+  ba::BgArgs a;
+  a.g = base;
+  auto I = [&](size_t i) { return reinterpret_cast<const int32_t*>(d + segs[i].off); };
+  a.perm = I(i_perm); a.pair_cam = I(i_pc); a.pair_obj = I(i_po); a.pair_eoff = I(i_pe); a.prob_pair = I(i_pp); a.cam_poff = I(i_cp);
+  a.obj_poff = I(i_op); a.obj_plist = I(i_ol); a.obj_slot = I(i_os); a.slot_vert = I(i_sv); a.prob_slot = I(i_ps); a.peer = I(i_peer);
+  a.prob_peer = reinterpret_cast<const long long*>(d + segs[i_ppe].off); a.prob_nobj = I(i_pn);
+  a.prob_S = reinterpret_cast<const long long*>(d + segs[i_pS].off);
+  Bump wb{d + struct_bytes};
+  a.S = wb.take<double>((size_t)S_total); a.pairw = wb.take<double>((size_t)n_pairs * 156);
+  a.est = wb.take<ba::SE3q>(n_vert); a.bak = wb.take<ba::SE3q>(n_vert);
+  a.Hv = wb.take<double>((size_t)n_vert * 36); a.bv = wb.take<double>((size_t)n_vert * 6); a.xv = wb.take<double>((size_t)n_vert * 6);
+  a.Minv = wb.take<double>((size_t)n_vert * 36); a.vact = wb.take<uint8_t>(n_vert);
+  return launch_ba_global(ctx, n_prob, a, s);
+}
+
 int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, double* poses,
                  const uint8_t* fixed, int n_vert, const int32_t* e_obj, const int32_t* e_cam, const double* cam_k,
                  const double* p, const double* uv, const double* info, uint8_t* inliers, int n_edges,
@@ -827,21 +943,40 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   double* d_err = sb.take<double>(2 * (size_t)n_edges);
   uint8_t* d_level = sb.take<uint8_t>(n_edges);
   int8_t* d_fv = sb.take<int8_t>(n_edges);
+  auto base_args = [&](const int32_t* pv, const int32_t* pe, double* po, const uint8_t* fx, const int32_t* eo, const int32_t* ec,
+                       const double* ck, const double* pp, const double* uu, const double* inf, uint8_t* inl, const int32_t* it, int32_t* st) {
+    ba::BaArgs b;
+    b.prob_vert = pv; b.prob_edge = pe; b.vert_cnt = nullptr; b.edge_cnt = nullptr; b.poses = po; b.fixed = fx; b.e_obj = eo; b.e_cam = ec;
+    b.cam_k = ck; b.p = pp; b.uv = uu; b.info = inf; b.inliers = inl; b.its = it; b.n_rounds = n_rounds; b.huber_delta = huber_delta;
+    b.chi2_gate = chi2_gate; b.init_with_outliers = init_with_outliers; b.stats = st; b.err = d_err; b.level = d_level; b.fv_kind = d_fv;
+    return b;
+  };
   if (on_device) {
+    // The graph structure decides the kernel: bring the index arrays to the host (this synchronises `stream`; the
+    // device-resident frame path, suo_solve_keypoints / suo_frames, does not come through here).
+    std::vector<int32_t> h_pv(n_prob + 1), h_pe(n_prob + 1), h_eo(n_edges), h_ec(n_edges);
+    std::vector<uint8_t> h_fx(n_vert);
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h_pv.data(), prob_vert, (n_prob + 1) * 4, cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h_pe.data(), prob_edge, (n_prob + 1) * 4, cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h_eo.data(), e_obj, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h_ec.data(), e_cam, (size_t)n_edges * 4, cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h_fx.data(), fixed, n_vert, cudaMemcpyDeviceToHost, s));
+    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+    if (h_pv[n_prob] > n_vert || h_pe[n_prob] > n_edges) { ctx->set_error("suo_ba_batch: offsets exceed n_vert / n_edges", __FILE__, __LINE__); return SUO_E_INVALID; }
+    if (ba_needs_global(n_prob, h_pv.data(), h_pe.data(), h_fx.data(), h_eo.data(), h_ec.data()))
+      return run_ba_global(ctx, n_prob, h_pv.data(), h_pe.data(), h_fx.data(), n_vert, h_eo.data(), h_ec.data(), n_edges,
+                           base_args(prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, stats), s);
     return launch_ba_batch_scratch(ctx, n_prob, prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers,
                                    its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s);
   }
-  // host-side validation (the kernel reports the same conditions through stats)
-  for (int pr = 0; pr < n_prob; ++pr) {
-    if (prob_vert[pr + 1] - prob_vert[pr] > 64) { ctx->set_error("suo_ba_batch: > 64 vertices in one problem", __FILE__, __LINE__); return SUO_E_INVALID; }
-    for (int e = prob_edge[pr]; e < prob_edge[pr + 1]; ++e) {
-      const bool fo = e_obj[e] >= 0 && !fixed[e_obj[e]], fc = !fixed[e_cam[e]];
-      if (fo && fc) { ctx->set_error("suo_ba_batch: edge with free camera AND free object (global graph, SURVEY f3) not supported", __FILE__, __LINE__); return SUO_E_INVALID; }
+  // host-side validation (the kernels report the same conditions through stats)
+  if (prob_vert[n_prob] > n_vert || prob_edge[n_prob] > n_edges) { ctx->set_error("suo_ba_batch: offsets exceed n_vert / n_edges", __FILE__, __LINE__); return SUO_E_INVALID; }
+  for (int pr = 0; pr < n_prob; ++pr)
+    for (int e = prob_edge[pr]; e < prob_edge[pr + 1]; ++e)
       if (e_cam[e] < prob_vert[pr] || e_cam[e] >= prob_vert[pr + 1] || (e_obj[e] >= 0 && (e_obj[e] < prob_vert[pr] || e_obj[e] >= prob_vert[pr + 1]))) {
         ctx->set_error("suo_ba_batch: edge references a vertex outside its problem", __FILE__, __LINE__); return SUO_E_INVALID;
       }
-    }
-  }
+  const bool global = ba_needs_global(n_prob, prob_vert, prob_edge, fixed, e_obj, e_cam);
   rc = x->io.grow(ctx, (size_t)n_vert * (12 * 8 + 1) + (size_t)n_edges * (4 + 4 + (4 + 3 + 2 + 4) * 8 + 1) + (size_t)n_prob * (8 + 12) + 16 * 4 + 16384);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->io.d)};
@@ -866,8 +1001,12 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   H2D(d_uv, uv, 2 * (size_t)n_edges * 8); H2D(d_info, info, 4 * (size_t)n_edges * 8);
   H2D(d_inl, inliers, n_edges); H2D(d_its, its, n_rounds * 4);
 #undef H2D
-  rc = launch_ba_batch_scratch(ctx, n_prob, d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its,
-                               n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s);
+  if (global)   // coupled camera+object graph (global BA) or a graph too large for the shared-memory kernel
+    rc = run_ba_global(ctx, n_prob, prob_vert, prob_edge, fixed, n_vert, e_obj, e_cam, n_edges,
+                       base_args(d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its, d_st), s);
+  else
+    rc = launch_ba_batch_scratch(ctx, n_prob, d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its,
+                                 n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s);
   if (rc) return rc;
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(poses, d_poses, 12 * (size_t)n_vert * 8, cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(inliers, d_inl, n_edges, cudaMemcpyDeviceToHost, s));

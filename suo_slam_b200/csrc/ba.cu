@@ -20,6 +20,8 @@
 // + shuffle tree): results are deterministic run to run, as the reference insists on
 // (lib/object_slam.py:440-442).  Latency / FP64-issue bound; no bandwidth claim.
 #include "common.cuh"
+#include "ba_math.cuh"
+using namespace ba;
 
 namespace {
 
@@ -27,116 +29,6 @@ constexpr int BA_THREADS = 128;
 constexpr int BA_WARPS = BA_THREADS / 32;
 constexpr int BA_MAXV = 64;     // vertices per graph held in shared memory
 
-struct SE3q { double qx, qy, qz, qw, t[3]; };
-
-__device__ void se3_from_Rt(const double* R, const double* t, SE3q& o) {   // Eigen::Quaterniond(R) + normalizeRotation (se3quat.h:55-57,277-282)
-  double q[4];
-  const double tr = R[0] + R[4] + R[8];
-  if (tr > 0) {
-    double s = sqrt(tr + 1.0);
-    q[3] = 0.5 * s; s = 0.5 / s;
-    q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
-  } else {
-    int i = 0;
-    if (R[4] > R[0]) i = 1;
-    if (R[8] > R[4 * i]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    double s = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
-    q[i] = 0.5 * s; s = 0.5 / s;
-    q[3] = (R[3 * k + j] - R[3 * j + k]) * s; q[j] = (R[3 * j + i] + R[3 * i + j]) * s; q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
-  }
-  if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  o.qx = q[0] / n; o.qy = q[1] / n; o.qz = q[2] / n; o.qw = q[3] / n;
-  o.t[0] = t[0]; o.t[1] = t[1]; o.t[2] = t[2];
-}
-__device__ __forceinline__ void se3_R(const SE3q& T, double* R) {          // Eigen toRotationMatrix
-  const double tx = 2 * T.qx, ty = 2 * T.qy, tz = 2 * T.qz;
-  const double twx = tx * T.qw, twy = ty * T.qw, twz = tz * T.qw;
-  const double txx = tx * T.qx, txy = ty * T.qx, txz = tz * T.qx, tyy = ty * T.qy, tyz = tz * T.qy, tzz = tz * T.qz;
-  R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
-  R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
-}
-__device__ __forceinline__ void se3_map(const SE3q& T, const double* p, double* o) {
-  double R[9];
-  se3_R(T, R);
-  o[0] = R[0] * p[0] + R[1] * p[1] + R[2] * p[2] + T.t[0];
-  o[1] = R[3] * p[0] + R[4] * p[1] + R[5] * p[2] + T.t[1];
-  o[2] = R[6] * p[0] + R[7] * p[1] + R[8] * p[2] + T.t[2];
-}
-__device__ void se3_oplus(const SE3q& T, const double* u, SE3q& out) {     // exp(u) * T
-  const double theta = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-  const double Om[9] = {0, -u[2], u[1], u[2], 0, -u[0], -u[1], u[0], 0};
-  double Om2[9];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) Om2[3 * i + j] = Om[3 * i] * Om[j] + Om[3 * i + 1] * Om[3 + j] + Om[3 * i + 2] * Om[6 + j];
-  double R[9], V[9];
-  if (theta < 0.00001) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { R[i] = (i % 4 == 0 ? 1.0 : 0.0) + Om[i] + Om2[i]; V[i] = R[i]; }
-  } else {
-    const double a = sin(theta) / theta, b = (1 - cos(theta)) / (theta * theta), c = (theta - sin(theta)) / (theta * theta * theta);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { const double I = (i % 4 == 0 ? 1.0 : 0.0); R[i] = I + a * Om[i] + b * Om2[i]; V[i] = I + b * Om[i] + c * Om2[i]; }
-  }
-  const double td[3] = {V[0] * u[3] + V[1] * u[4] + V[2] * u[5], V[3] * u[3] + V[4] * u[4] + V[5] * u[5], V[6] * u[3] + V[7] * u[4] + V[8] * u[5]};
-  SE3q E;
-  se3_from_Rt(R, td, E);
-  double RE[9];
-  se3_R(E, RE);
-  out.t[0] = E.t[0] + RE[0] * T.t[0] + RE[1] * T.t[1] + RE[2] * T.t[2];
-  out.t[1] = E.t[1] + RE[3] * T.t[0] + RE[4] * T.t[1] + RE[5] * T.t[2];
-  out.t[2] = E.t[2] + RE[6] * T.t[0] + RE[7] * T.t[1] + RE[8] * T.t[2];
-  double w = E.qw * T.qw - E.qx * T.qx - E.qy * T.qy - E.qz * T.qz;
-  double x = E.qw * T.qx + E.qx * T.qw + E.qy * T.qz - E.qz * T.qy;
-  double y = E.qw * T.qy - E.qx * T.qz + E.qy * T.qw + E.qz * T.qx;
-  double z = E.qw * T.qz + E.qx * T.qy - E.qy * T.qx + E.qz * T.qw;
-  if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
-  const double n = sqrt(x * x + y * y + z * z + w * w);
-  out.qx = x / n; out.qy = y / n; out.qz = z / n; out.qw = w / n;
-}
-
-__device__ __forceinline__ void huber(double e, double delta, double& rho0, double& rho1) {
-  const double dsqr = delta * delta;
-  if (e <= dsqr) { rho0 = e; rho1 = 1.0; }
-  else { const double sq = sqrt(e); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
-}
-
-__device__ bool chol6(double* A, double* b) {   // in place, row-major lower
-  for (int j = 0; j < 6; ++j) {
-    double d = A[j * 6 + j];
-    for (int k = 0; k < j; ++k) d -= A[j * 6 + k] * A[j * 6 + k];
-    if (!(d > 0) || !isfinite(d)) return false;
-    d = sqrt(d);
-    A[j * 6 + j] = d;
-    for (int i = j + 1; i < 6; ++i) {
-      double s = A[i * 6 + j];
-      for (int k = 0; k < j; ++k) s -= A[i * 6 + k] * A[j * 6 + k];
-      A[i * 6 + j] = s / d;
-    }
-  }
-  for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= A[i * 6 + k] * b[k]; b[i] = s / A[i * 6 + i]; }
-  for (int i = 5; i >= 0; --i) { double s = b[i]; for (int k = i + 1; k < 6; ++k) s -= A[k * 6 + i] * b[k]; b[i] = s / A[i * 6 + i]; }
-  return true;
-}
-
-struct BaArgs {
-  const int32_t* prob_vert; const int32_t* prob_edge;
-  const int32_t* vert_cnt; const int32_t* edge_cnt;   // optional explicit counts (else next offset - offset)
-  double* poses; const uint8_t* fixed;
-  const int32_t* e_obj; const int32_t* e_cam;
-  const double* cam_k; const double* p; const double* uv; const double* info;
-  uint8_t* inliers;
-  const int32_t* its; int n_rounds;
-  double huber_delta, chi2_gate; int init_with_outliers;
-  int32_t* stats;
-  double* err;        // scratch [n_edges,2]: the edge's _error as last computed (g2o keeps it in the edge)
-  uint8_t* level;     // scratch [n_edges]
-  int8_t* fv_kind;    // scratch [n_edges]: 0 = free vertex is the object, 1 = the camera, -1 = none / invalid
-};
 
 __device__ double block_sum_d(double v, double* sh) {
   v = warp_sum(v);
@@ -207,7 +99,7 @@ ba_kernel(const BaArgs a) {
   int my_good = 0;
   for (int e = tid; e < ne; e += BA_THREADS) {
     const int ge = e0 + e;
-    if (a.init_with_outliers) { a.level[ge] = 0; my_good++; }
+    if (a.init_with_outliers) { a.level[ge] = 0; a.err[2 * ge] = 0.0; a.err[2 * ge + 1] = 0.0; my_good++; }   // an edge that never becomes active keeps a zero error
     else {
       edge_error(ge);
       if (edge_chi2(ge) > a.chi2_gate) { a.level[ge] = 1; a.inliers[ge] = 0; }

@@ -6,9 +6,9 @@ types_object_slam.h:17-52, python/types/slam3d/se3quat.h:18-72, python/core/robu
 The graph is only *recorded* in Python; every ``optimizer.optimize(n)`` packs the level-0 edges
 into arrays and runs ONE ``suo_ba_batch`` launch (the g2o Levenberg loop of
 optimization_algorithm_levenberg.cpp:58-150 on the GPU).  With this module on the path as
-``g2o`` the reference's optimize() body runs unchanged for single-view and curr_only graphs;
-a graph where cameras AND objects are free (global BA, CHOLMOD path) raises
-NotImplementedError.
+``g2o`` the reference's optimize() body runs unchanged for single-view, curr_only AND global graphs
+(cameras and objects free, the CHOLMOD path of lib/object_slam.py:710: the library eliminates the
+cameras by a Schur complement, csrc/ba_global.cu).
 
 One documented difference: g2o leaves the error of the last *rejected* LM trial in the active
 edges (the reference then reads it through ``e.chi2()``); here ``chi2()`` after ``optimize()``
@@ -191,9 +191,6 @@ class SparseOptimizer:
         for e in active:
             if isinstance(e, EdgeSE3ProjectFromObject):
                 o, c = index[id(e._verts[0])], index[id(e._verts[1])]
-                if not fixed[o] and not fixed[c]:
-                    raise NotImplementedError("global BA with free cameras and free objects (SURVEY.md §8 f3) "
-                                              "is not handled by suo_ba_batch yet")
                 e_obj.append(o)
                 e_cam.append(c)
             else:

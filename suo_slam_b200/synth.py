@@ -173,3 +173,60 @@ def make_ba_problem(seed: int, n_obj: int = 512, n_kp: int = 12, noise_px: float
         T_init[o, :, :3] = R @ dR          # perturb in the object frame: T_gt * exp(delta)
         T_init[o, :, 3] = R @ dt + t
     return dict(cam_k=cam_k, p_O=p_O, uv=uv, info=info, T_gt=T_gt, T_init=T_init)
+
+
+def make_global_graph(seed: int, n_views: int = 12, n_obj: int = 6, kp_range=(8, 16), see_prob: float = 0.7,
+                      noise_px: float = 1.0, outlier_frac: float = 0.05, perturb: float = 1.0):
+    """A multi-view object-SLAM graph as ObjectSLAM.optimize(curr_only=False) builds it in SLAM / SfM mode
+    (lib/object_slam.py:736-837): object vertices 0..n_obj-1 (T_wo), then one camera vertex per view (T_cw,
+    the first one fixed, :771), one EdgeSE3ProjectFromObject per detected keypoint, information = inv(cov).
+    Scene modelled on thirdparty/g2opy/python/examples/object_slam_demo.py:54-150 (objects on a table, the
+    camera circling it); pixel-unit intrinsics of YCB-V.  Returns the packed arrays of suo_ba_batch."""
+    rng = np.random.default_rng(seed)
+    cam_k = np.array([1066.778, 1067.487, 312.9869, 241.3109])
+    T_wo = np.zeros((n_obj, 3, 4))
+    kps = []
+    for o in range(n_obj):
+        T_wo[o, :, :3] = random_rotation(rng)
+        T_wo[o, :, 3] = [rng.uniform(-250, 250), rng.uniform(-250, 250), rng.uniform(-40, 40)]
+        kps.append(rng.uniform(-60, 60, size=(int(rng.integers(kp_range[0], kp_range[1] + 1)), 3)))
+    T_cw = np.zeros((n_views, 3, 4))
+    for v in range(n_views):
+        ang = 2 * np.pi * v / n_views + rng.normal(scale=0.05)
+        c = np.array([900 * np.cos(ang), 900 * np.sin(ang), rng.uniform(350, 600)])      # camera centre in the world
+        z = -c / np.linalg.norm(c)                                                        # looks at the origin
+        x = np.cross([0, 0, 1.0], z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        R = np.stack([x, y, z])                                                           # rows = camera axes in the world
+        T_cw[v, :, :3], T_cw[v, :, 3] = R, -R @ c
+    e_obj, e_cam, p, uv, info = [], [], [], [], []
+    for v in range(n_views):
+        seen = [o for o in range(n_obj) if rng.random() < see_prob] or [int(rng.integers(n_obj))]
+        for o in seen:
+            pw = kps[o] @ T_wo[o, :, :3].T + T_wo[o, :, 3]
+            pc = pw @ T_cw[v, :, :3].T + T_cw[v, :, 3]
+            m = np.c_[cam_k[0] * pc[:, 0] / pc[:, 2] + cam_k[2], cam_k[1] * pc[:, 1] / pc[:, 2] + cam_k[3]]
+            m += rng.normal(scale=noise_px, size=m.shape)
+            out = rng.random(len(m)) < outlier_frac
+            m[out] += rng.uniform(-80, 80, size=(int(out.sum()), 2))
+            sig = rng.uniform(0.5, 2.0, size=(len(m), 2)) * noise_px
+            rho = rng.uniform(-0.5, 0.5, size=len(m))
+            for k in range(len(m)):
+                cov = np.array([[sig[k, 0] ** 2, rho[k] * sig[k, 0] * sig[k, 1]], [rho[k] * sig[k, 0] * sig[k, 1], sig[k, 1] ** 2]])
+                e_obj.append(o); e_cam.append(n_obj + v); p.append(kps[o][k]); uv.append(m[k]); info.append(np.linalg.inv(cov).ravel())
+    def jitter(T, first_exact):
+        out = T.copy()
+        for i in range(len(T)):
+            if first_exact and i == 0:
+                continue
+            dR = so3_exp(np.deg2rad(rng.normal(scale=2.0 * perturb, size=3)))
+            out[i, :, :3] = dR @ T[i, :, :3]
+            out[i, :, 3] = dR @ T[i, :, 3] + rng.normal(scale=8.0 * perturb, size=3)
+        return out
+    poses = np.concatenate([jitter(T_wo, False), jitter(T_cw, True)], 0)
+    fixed = np.zeros(n_obj + n_views, np.uint8)
+    fixed[n_obj] = 1
+    n_e = len(e_obj)
+    return dict(poses=poses, poses_gt=np.concatenate([T_wo, T_cw], 0), fixed=fixed, e_obj=np.asarray(e_obj, np.int32),
+                e_cam=np.asarray(e_cam, np.int32), cam_k=np.tile(cam_k, (n_e, 1)), p=np.asarray(p), uv=np.asarray(uv),
+                info=np.asarray(info), n_obj=n_obj, n_views=n_views)

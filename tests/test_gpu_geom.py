@@ -151,11 +151,83 @@ def test_ba_curr_only_vs_oracle():
     np.testing.assert_allclose(P, Po, rtol=TOL, atol=TOL * 1e3)
 
 
-def test_ba_rejects_coupled_graph():
+def _global_args(g):
+    return (g["poses"], g["fixed"], g["e_obj"], g["e_cam"], g["cam_k"], g["p"], g["uv"], g["info"], np.ones(len(g["e_obj"])))
+
+
+@pytest.mark.parametrize("n_views,n_obj,its,iwo", [(12, 6, [10, 10, 40, 40], True), (40, 10, [10, 10, 40, 40], False),
+                                                     (3, 2, [10] * 4, True), (90, 21, [10, 10, 40, 40], True)])
+def test_ba_global_graph_vs_oracle(n_views, n_obj, its, iwo):
+    """Global BA (row a7/a8 global mode, f3): cameras AND objects free, first camera fixed (lib/object_slam.py:736-778).
+    The kernel eliminates the cameras (Schur complement), the oracle solves the full dense system as g2o/CHOLMOD do:
+    same LM step up to rounding."""
+    g = synth.make_global_graph(11 + n_views, n_views, n_obj, perturb=1.0 if iwo else 0.05)
+    ne = len(g["e_obj"])
+    P, inl, st = ba.ba_batch([0, n_obj + n_views], [0, ne], *_global_args(g), its, init_with_outliers=iwo)
+    Po, io, so = geom.ba_optimize(*_global_args(g), its, init_with_outliers=iwo)
+    print(f"[ba global V={n_views} N={n_obj} E={ne}] gpu stats {tuple(st[0])} oracle {(so['rounds'], so['outer'], so['trials'])} "
+          f"inliers equal {np.array_equal(inl, io)} max |dP| {np.abs(P - Po).max():.2e}")
+    assert st[0, 0] == so["rounds"]
+    assert np.array_equal(inl, io)
+    assert np.abs(P[:, :, :3] - Po[:, :, :3]).max() < 1e-7          # rotations
+    assert np.abs(P[:, :, 3] - Po[:, :, 3]).max() < 1e-5            # translations are ~1e3 mm: 1e-8 relative
+    assert np.abs(P[n_obj] - g["poses"][n_obj]).max() < 1e-10       # the fixed camera did not move (R -> q -> R round trip only)
+    # and the solve did its job: closer to the ground truth than the start
+    if iwo:
+        assert np.abs(P - g["poses_gt"])[:, :, 3].max() < np.abs(g["poses"] - g["poses_gt"])[:, :, 3].max()
+
+
+def test_ba_global_batch_of_graphs_and_edge_order():
+    """Two coupled graphs in one launch, edges shuffled (the host groups them by (camera, object) pair) and some
+    EdgeSE3ProjectFromFixedObject-style unary edges mixed in."""
+    rng = np.random.default_rng(0)
+    gs = [synth.make_global_graph(50, 8, 4), synth.make_global_graph(51, 15, 7)]
+    packs, refs = [], []
+    pv, pe, voff, eoff = [0], [0], 0, 0
+    for g in gs:
+        perm = rng.permutation(len(g["e_obj"]))
+        for k in ("e_obj", "e_cam", "cam_k", "p", "uv", "info"):
+            g[k] = g[k][perm]
+        # fold the first object into the points of its edges: unary edges on the cameras
+        un = g["e_obj"] == 0
+        T0 = g["poses"][0]
+        g["p"][un] = g["p"][un] @ T0[:, :3].T + T0[:, 3]
+        g["e_obj"][un] = -1
+        refs.append(geom.ba_optimize(*_global_args(g), [10, 10, 20, 20], init_with_outliers=True))
+        packs.append(g)
+        voff += len(g["poses"]); eoff += len(g["e_obj"])
+        pv.append(voff); pe.append(eoff)
+    cat = lambda k: np.concatenate([g[k] for g in packs])
+    e_obj = np.concatenate([np.where(g["e_obj"] >= 0, g["e_obj"] + o, -1) for g, o in zip(packs, pv)])
+    e_cam = np.concatenate([g["e_cam"] + o for g, o in zip(packs, pv)])
+    P, inl, st = ba.ba_batch(pv, pe, cat("poses"), cat("fixed"), e_obj, e_cam, cat("cam_k"), cat("p"), cat("uv"), cat("info"),
+                             np.ones(pe[-1]), [10, 10, 20, 20], init_with_outliers=True)
+    for i, (Po, io, so) in enumerate(refs):
+        assert st[i, 0] == so["rounds"]
+        assert np.array_equal(inl[pe[i]:pe[i + 1]], io)
+        assert np.abs(P[pv[i]:pv[i + 1]] - Po).max() < 1e-5
+
+
+def test_ba_large_block_diagonal_graph_uses_the_global_kernel():
+    """> 64 vertices in one uncoupled graph (camera fixed): the workspace kernel handles it, same answer as the oracle."""
+    n_obj, n_kp = 100, 10
+    pr = synth.make_ba_problem(21, n_obj, n_kp, noise_px=0.7, outlier_frac=0.1)
+    poses, fixed, e_obj, e_cam, cam_k, pv, pe = _pack(pr, n_obj, n_kp, False)
+    args = (poses, fixed, e_obj, e_cam, cam_k, pr["p_O"], pr["uv"], pr["info"], np.ones(n_obj * n_kp), [10] * 4)
+    P, inl, st = ba.ba_batch(pv, pe, *args, init_with_outliers=True)
+    Po, io, so = geom.ba_optimize(*args, init_with_outliers=True)
+    assert np.array_equal(inl, io)
+    np.testing.assert_allclose(P, Po, rtol=1e-7, atol=1e-5)
+
+
+def test_ba_rejects_malformed_graphs():
     from suo_slam_b200 import _lib
-    with pytest.raises(_lib.SuoError):
-        ba.ba_batch([0, 2], [0, 1], np.tile(np.c_[np.eye(3), [0, 0, 500.0]], (2, 1, 1)), [0, 0], [0], [1],
-                    [[320, 320, 320, 240.0]], [[1.0, 2, 3]], [[300.0, 200]], [[1.0, 0, 0, 1]], [1], [5])
+    T = np.tile(np.c_[np.eye(3), [0, 0, 500.0]], (2, 1, 1))
+    with pytest.raises(_lib.SuoError):      # edge points outside its problem
+        ba.ba_batch([0, 2], [0, 1], T, [0, 0], [0], [5], [[320, 320, 320, 240.0]], [[1.0, 2, 3]], [[300.0, 200]], [[1.0, 0, 0, 1]], [1], [5])
+    with pytest.raises(_lib.SuoError):      # one free vertex used as object and as camera
+        ba.ba_batch([0, 2], [0, 2], T, [0, 0], [0, 1], [1, 0], [[320, 320, 320, 240.0]] * 2, [[1.0, 2, 3]] * 2, [[300.0, 200]] * 2,
+                    [[1.0, 0, 0, 1]] * 2, [1, 1], [5])
 
 
 def test_solve_keypoints_vs_oracle():
@@ -190,38 +262,9 @@ def test_solve_keypoints_vs_oracle():
     assert np.median(terr) < 0.05
 
 
-def test_g2o_shim_runs_the_reference_optimize_flow():
-    """The reference's own optimize() body (lib/object_slam.py:706-896, single-view: objects free, camera
-    fixed) driven through the ``g2o`` drop-in module, against the oracle's restatement of the same flow."""
-    from suo_slam_b200 import g2o
-    n_obj, n_kp = 6, 12
-    pr = synth.make_ba_problem(21, n_obj, n_kp, noise_px=0.7, outlier_frac=0.1)
-    pr["T_init"] = pr["T_gt"].copy()
-    pr["T_init"][:, :, 3] += np.random.default_rng(1).normal(scale=0.5, size=(n_obj, 3))
-    optimizer = g2o.SparseOptimizer()
-    optimizer.set_algorithm(g2o.OptimizationAlgorithmLevenberg(g2o.BlockSolverSE3(g2o.LinearSolverCholmodSE3())))
-    obj_v = []
-    for j in range(n_obj):
-        v = g2o.VertexSE3Expmap()
-        v.set_id(j)
-        v.set_estimate(g2o.SE3Quat(pr["T_init"][j][:, :3], pr["T_init"][j][:, 3]))
-        optimizer.add_vertex(v)
-        obj_v.append(v)
-    cam = g2o.VertexSE3Expmap()
-    cam.set_id(n_obj)
-    cam.set_estimate(g2o.SE3Quat(np.eye(3), np.zeros(3)))
-    cam.set_fixed(True)
-    optimizer.add_vertex(cam)
-    edges, inl = [], np.ones(n_obj * n_kp, bool)
-    for j in range(n_obj):
-        for k in range(n_kp):
-            e = g2o.EdgeSE3ProjectFromObject(pr["cam_k"], pr["p_O"][j, k])
-            e.set_vertex(0, obj_v[j]); e.set_vertex(1, cam)
-            e.set_measurement(pr["uv"][j, k]); e.set_information(pr["info"][j, k])
-            e.set_robust_kernel(g2o.RobustKernelHuber(np.sqrt(5.991)))
-            e.set_level(0)
-            edges.append(e); optimizer.add_edge(e)
-    its = [10] * 4
+def _reference_optimize_loop(optimizer, edges, its):
+    """lib/object_slam.py:856-896 verbatim in structure: chi2 classification, 4 rounds, Huber stripped half-way."""
+    inl = np.ones(len(edges), bool)
     num_good = 0
     for i, e in enumerate(edges):                       # :856-866
         e.compute_error()
@@ -245,11 +288,76 @@ def test_g2o_shim_runs_the_reference_optimize_flow():
                 num_good += 1; e.set_level(0); inl[i] = True
             if it == max(1, len(its) // 2):
                 e.set_robust_kernel(None)
+    return inl
+
+
+def test_g2o_shim_runs_the_reference_optimize_flow():
+    """The reference's own optimize() body (lib/object_slam.py:706-896, single-view: objects free, camera
+    fixed) driven through the ``g2o`` drop-in module, against the oracle's restatement of the same flow."""
+    from suo_slam_b200 import g2o
+    n_obj, n_kp = 6, 12
+    pr = synth.make_ba_problem(21, n_obj, n_kp, noise_px=0.7, outlier_frac=0.1)
+    pr["T_init"] = pr["T_gt"].copy()
+    pr["T_init"][:, :, 3] += np.random.default_rng(1).normal(scale=0.5, size=(n_obj, 3))
+    optimizer = g2o.SparseOptimizer()
+    optimizer.set_algorithm(g2o.OptimizationAlgorithmLevenberg(g2o.BlockSolverSE3(g2o.LinearSolverCholmodSE3())))
+    obj_v = []
+    for j in range(n_obj):
+        v = g2o.VertexSE3Expmap()
+        v.set_id(j)
+        v.set_estimate(g2o.SE3Quat(pr["T_init"][j][:, :3], pr["T_init"][j][:, 3]))
+        optimizer.add_vertex(v)
+        obj_v.append(v)
+    cam = g2o.VertexSE3Expmap()
+    cam.set_id(n_obj)
+    cam.set_estimate(g2o.SE3Quat(np.eye(3), np.zeros(3)))
+    cam.set_fixed(True)
+    optimizer.add_vertex(cam)
+    edges = []
+    for j in range(n_obj):
+        for k in range(n_kp):
+            e = g2o.EdgeSE3ProjectFromObject(pr["cam_k"], pr["p_O"][j, k])
+            e.set_vertex(0, obj_v[j]); e.set_vertex(1, cam)
+            e.set_measurement(pr["uv"][j, k]); e.set_information(pr["info"][j, k])
+            e.set_robust_kernel(g2o.RobustKernelHuber(np.sqrt(5.991)))
+            e.set_level(0)
+            edges.append(e); optimizer.add_edge(e)
+    its = [10] * 4
+    inl = _reference_optimize_loop(optimizer, edges, its)
     got = np.stack([v.estimate().matrix()[:3] for v in obj_v])
     poses, fixed, e_obj, e_cam, cam_k, _, _ = _pack(pr, n_obj, n_kp, False)
     Po, io, _ = geom.ba_optimize(poses, fixed, e_obj, e_cam, cam_k, pr["p_O"], pr["uv"], pr["info"], np.ones(n_obj * n_kp), its)
     assert np.array_equal(inl, io)
     np.testing.assert_allclose(got, Po[:n_obj], rtol=1e-6, atol=1e-5)
-    with pytest.raises(NotImplementedError):            # free camera + free objects: row f3
-        cam.set_fixed(False)
-        optimizer.optimize(1)
+
+
+def test_g2o_shim_global_graph():
+    """optimize(curr_only=False) in SLAM mode through the ``g2o`` drop-in: objects and cameras free (first camera
+    fixed), CHOLMOD solver requested (lib/object_slam.py:708-778), its = [10, 10, 40, 40] (:843-844)."""
+    from suo_slam_b200 import g2o
+    n_views, n_obj = 10, 5
+    g = synth.make_global_graph(77, n_views, n_obj, perturb=0.05)
+    optimizer = g2o.SparseOptimizer()
+    optimizer.set_algorithm(g2o.OptimizationAlgorithmLevenberg(g2o.BlockSolverSE3(g2o.LinearSolverCholmodSE3())))
+    verts = []
+    for i, T in enumerate(g["poses"]):
+        v = g2o.VertexSE3Expmap()
+        v.set_id(i)
+        v.set_estimate(g2o.SE3Quat(T[:, :3], T[:, 3]))
+        v.set_fixed(bool(g["fixed"][i]))
+        optimizer.add_vertex(v)
+        verts.append(v)
+    edges = []
+    for k in range(len(g["e_obj"])):
+        e = g2o.EdgeSE3ProjectFromObject(g["cam_k"][k], g["p"][k])
+        e.set_vertex(0, verts[g["e_obj"][k]]); e.set_vertex(1, verts[g["e_cam"][k]])
+        e.set_measurement(g["uv"][k]); e.set_information(g["info"][k].reshape(2, 2))
+        e.set_robust_kernel(g2o.RobustKernelHuber(np.sqrt(5.991)))
+        e.set_level(0)
+        edges.append(e); optimizer.add_edge(e)
+    its = [10, 10, 40, 40]
+    inl = _reference_optimize_loop(optimizer, edges, its)
+    got = np.stack([v.estimate().matrix()[:3] for v in verts])
+    Po, io, _ = geom.ba_optimize(*_global_args(g), its)
+    assert np.array_equal(inl, io)
+    np.testing.assert_allclose(got, Po, rtol=1e-6, atol=1e-4)

@@ -175,3 +175,48 @@ def test_ba_curr_only_unary_edges():
     np.testing.assert_allclose(P[0][:, :3], Tgt[:, :3], atol=5e-3)      # estimation noise, not solver error
     np.testing.assert_allclose(P[0][:, 3], Tgt[:, 3], atol=5.0)
     assert inl.sum() > 50
+
+
+def test_ba_global_graph_reaches_the_least_squares_optimum():
+    """Coupled camera+object graph (global BA, lib/object_slam.py:736-778): the oracle's g2o restatement
+    (dense solve of the full system, as CHOLMOD would) against an independent optimiser on the same cost."""
+    from scipy.optimize import least_squares
+    n_views, n_obj = 5, 3
+    g = synth.make_global_graph(5, n_views, n_obj, kp_range=(6, 8), noise_px=0.2, outlier_frac=0.0, perturb=0.3)
+    ne = len(g["e_obj"])
+    g["info"][:] = np.array([1.5, 0.3, 0.3, 0.8])                    # every chi2 stays far below 5.991: Huber is quadratic there
+    P, inl, st = geom.ba_optimize(g["poses"], g["fixed"], g["e_obj"], g["e_cam"], g["cam_k"], g["p"], g["uv"], g["info"],
+                                  np.ones(ne), [60], init_with_outliers=True)
+    assert inl.all()
+    free = np.nonzero(g["fixed"] == 0)[0]
+    Lw = np.linalg.cholesky(g["info"].reshape(-1, 2, 2))            # info = L L^T: chi2 = |L^T e|^2
+
+    def poses_of(x):
+        T = g["poses"].copy()
+        for i, v in enumerate(free):
+            T[v] = geom.se3_oplus(g["poses"][v], x[6 * i:6 * i + 6])
+        return T
+
+    def resid(x):
+        T = poses_of(x)
+        To, Tc = T[g["e_obj"]], T[g["e_cam"]]
+        pw = np.einsum("eij,ej->ei", To[:, :, :3], g["p"]) + To[:, :, 3]
+        pc = np.einsum("eij,ej->ei", Tc[:, :, :3], pw) + Tc[:, :, 3]
+        e = g["uv"] - np.c_[g["cam_k"][:, 0] * pc[:, 0] / pc[:, 2] + g["cam_k"][:, 2], g["cam_k"][:, 1] * pc[:, 1] / pc[:, 2] + g["cam_k"][:, 3]]
+        return np.einsum("eji,ej->ei", Lw, e).ravel()
+
+    sol = least_squares(resid, np.zeros(6 * len(free)), xtol=1e-15, ftol=1e-15, gtol=1e-15, x_scale="jac")
+    Ps = poses_of(sol.x)
+    cost_oracle = 0.5 * np.sum(_global_chi2(g, P))
+    assert abs(cost_oracle - sol.cost) <= 1e-9 * max(1.0, sol.cost)
+    np.testing.assert_allclose(P[:, :, :3], Ps[:, :, :3], atol=1e-6)
+    np.testing.assert_allclose(P[:, :, 3], Ps[:, :, 3], atol=1e-3)   # mm; the optimum is flat along the depth direction
+    np.testing.assert_allclose(P[n_obj], g["poses"][n_obj], atol=1e-10)   # first camera fixed (object_slam.py:771); R -> q -> R round trip only
+
+
+def _global_chi2(g, T):
+    To, Tc = T[g["e_obj"]], T[g["e_cam"]]
+    pw = np.einsum("eij,ej->ei", To[:, :, :3], g["p"]) + To[:, :, 3]
+    pc = np.einsum("eij,ej->ei", Tc[:, :, :3], pw) + Tc[:, :, 3]
+    e = g["uv"] - np.c_[g["cam_k"][:, 0] * pc[:, 0] / pc[:, 2] + g["cam_k"][:, 2], g["cam_k"][:, 1] * pc[:, 1] / pc[:, 2] + g["cam_k"][:, 3]]
+    return np.einsum("ei,eij,ej->e", e, g["info"].reshape(-1, 2, 2), e)
