@@ -85,6 +85,23 @@ int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W,
                 float* mask_logits, float* mask, int32_t* argmax,
                 int on_device, void* stream);
 
+/* suo_forward with the priors given as KEYPOINTS instead of dense planes: prior_uv [L,K,2] f32
+ * (NDC, as ObjectSLAM builds prior_uv_full, lib/object_slam.py:510-512) and prior_mask [L,K] u8.  The planes that
+ * utils.make_prior_kp_input (lib/utils/utils.py:398-411) would have produced are stamped straight into the network
+ * input on the device: identical result, no 10.75 MB / crop of prior planes built on the CPU and copied over. */
+int suo_forward_kp_priors(suo_ctx* ctx, const float* images, int n_img, int H, int W,
+                          const float* boxes, const int32_t* box_img, int L,
+                          const float* prior_uv, const uint8_t* prior_mask,
+                          float* uv, float* cov, float* logits, float* prob,
+                          float* mask_logits, float* mask, int32_t* argmax,
+                          int on_device, void* stream);
+
+/* Replaces utils.make_prior_kp_input(kp_uv, kp_uv_mask, img_shape, ndc) (lib/utils/utils.py:398-411 ->
+ * draw_gaussian_2d :364-385 -> gaussian_2d :356-361) for a batch: prior_uv [L,K,2] f32, prior_mask [L,K] u8 ->
+ * out [L,K,height,width] f32, bit-identical to the reference (same 91x91 cv2.GaussianBlur stamp, same rounding). */
+int suo_render_priors(suo_ctx* ctx, const float* prior_uv, const uint8_t* prior_mask, int L, int K,
+                      int height, int width, int ndc, float* out, int on_device, void* stream);
+
 /* Stand-alone heat-map reduction (spatial_softmax + post_process_kp + classifier,
  * lib/models/pkpnet.py:13-63,74-78,106-118).  logits [B,K,H,W] f32; cls_w [K,K],
  * cls_b [K] may be NULL (then mask outputs are skipped). */

@@ -24,7 +24,8 @@ def exported_symbols():
     """Every entry point include/suo_b200.h declares (tests check the .so exports them all)."""
     return ["suo_create", "suo_destroy", "suo_last_error", "suo_set_option", "suo_kernel_launches",
             "suo_load_weights", "suo_forward", "suo_heatmap_reduce", "suo_crop_concat", "suo_conv2d",
-            "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range"]
+            "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range",
+            "suo_forward_kp_priors", "suo_render_priors"]
 
 
 def lib():
@@ -43,6 +44,8 @@ def lib():
         L.suo_kernel_launches.restype = C.c_longlong
         L.suo_load_weights.argtypes = [vp, vp, C.c_size_t]
         L.suo_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp] + [vp] * 7 + [C.c_int, vp]
+        L.suo_forward_kp_priors.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp] + [vp] * 7 + [C.c_int, vp]
+        L.suo_render_priors.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
         L.suo_heatmap_reduce.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp] + [vp] * 6 + [C.c_int, vp]
         L.suo_crop_concat.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int,
                                       C.c_int, vp]

@@ -716,9 +716,10 @@ int suo_check_range(suo_ctx* ctx) {
   return SUO_OK;
 }
 
-int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
-                int L, const float* priors, float* uv, float* cov, float* logits, float* prob, float* mask_logits,
-                float* mask, int32_t* argmax, int on_device, void* stream) {
+// priors (dense planes) and prior_uv / prior_mask (keypoint priors rendered on the device) are mutually exclusive.
+static int forward_impl(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                        int L, const float* priors, const float* prior_uv, const uint8_t* prior_mask, float* uv, float* cov,
+                        float* logits, float* prob, float* mask_logits, float* mask, int32_t* argmax, int on_device, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
@@ -730,15 +731,16 @@ int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   NetState& N = x->net;
   const int R = ctx->crop_res, K = ctx->num_kp, HM = R / N.h.heat_div;
-  const int variant = priors ? 1 : 0;
-  const int in_buf = priors ? N.h.in_buf_prior : N.h.in_buf_noprior;
+  const int variant = (priors || prior_uv) ? 1 : 0;
+  const int in_buf = variant ? N.h.in_buf_prior : N.h.in_buf_noprior;
   const size_t n_im = (size_t)n_img * 3 * H * W, n_pr = priors ? (size_t)L * K * R * R : 0;
   const size_t n_hm = (size_t)L * K * HM * HM, LK = (size_t)L * K;
-  const float *d_im = images, *d_box = boxes, *d_pr = priors;
+  const float *d_im = images, *d_box = boxes, *d_pr = priors, *d_puv = prior_uv;
+  const uint8_t* d_pm = prior_mask;
   const int32_t* d_bi = box_img;
   float* d_prob = prob;
   if (!on_device) {
-    rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0)) * sizeof(float) + 4096);
+    rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0) + 3 * LK) * sizeof(float) + 8192);
     if (rc) return rc;
     Bump bp{static_cast<uint8_t*>(x->io.d)};
     float* a = bp.take<float>(n_im);
@@ -746,13 +748,25 @@ int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, cons
     int32_t* c = bp.take<int32_t>(L);
     float* d = priors ? bp.take<float>(n_pr) : nullptr;
     d_prob = prob ? bp.take<float>(n_hm) : nullptr;
+    if (prior_uv) {
+      float* e = bp.take<float>(2 * LK); uint8_t* f = bp.take<uint8_t>(LK);
+      SUO_CUDA_TRY(ctx, cudaMemcpyAsync(e, prior_uv, 2 * LK * sizeof(float), cudaMemcpyHostToDevice, s));
+      SUO_CUDA_TRY(ctx, cudaMemcpyAsync(f, prior_mask, LK, cudaMemcpyHostToDevice, s));
+      d_puv = e; d_pm = f;
+    }
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(a, images, n_im * sizeof(float), cudaMemcpyHostToDevice, s));
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b, boxes, 4 * (size_t)L * sizeof(float), cudaMemcpyHostToDevice, s));
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(c, box_img, L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     if (d) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d, priors, n_pr * sizeof(float), cudaMemcpyHostToDevice, s));
     d_im = a; d_box = b; d_bi = c; d_pr = d;
   }
-  rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
+  if (d_puv) {   // keypoint priors: RGB by roi_align, prior channels stamped straight into the NHWC input (prior.cu)
+    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, nullptr, -1, R, N.act[in_buf], N.bufs[in_buf].C, s);
+    if (rc) return rc;
+    rc = launch_render_priors_nhwc(ctx, d_puv, d_pm, L, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
+  } else {
+    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
+  }
   if (rc) return rc;
   rc = run_network(ctx, L, variant, s);
   if (rc) return rc;
@@ -776,6 +790,43 @@ int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, cons
   if (prob) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(prob, d_prob, n_hm * sizeof(float), cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return suo_check_range(ctx);
+}
+
+int suo_forward(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                int L, const float* priors, float* uv, float* cov, float* logits, float* prob, float* mask_logits,
+                float* mask, int32_t* argmax, int on_device, void* stream) {
+  return forward_impl(ctx, images, n_img, H, W, boxes, box_img, L, priors, nullptr, nullptr, uv, cov, logits, prob, mask_logits,
+                      mask, argmax, on_device, stream);
+}
+
+int suo_forward_kp_priors(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                          int L, const float* prior_uv, const uint8_t* prior_mask, float* uv, float* cov, float* logits,
+                          float* prob, float* mask_logits, float* mask, int32_t* argmax, int on_device, void* stream) {
+  if (!prior_uv || !prior_mask) { if (ctx) ctx->set_error("suo_forward_kp_priors: prior_uv / prior_mask are required", __FILE__, __LINE__); return SUO_E_INVALID; }
+  return forward_impl(ctx, images, n_img, H, W, boxes, box_img, L, nullptr, prior_uv, prior_mask, uv, cov, logits, prob,
+                      mask_logits, mask, argmax, on_device, stream);
+}
+
+int suo_render_priors(suo_ctx* ctx, const float* prior_uv, const uint8_t* prior_mask, int L, int K, int height, int width, int ndc,
+                      float* out, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (L <= 0 || K <= 0 || height <= 0 || width <= 0 || !prior_uv || !prior_mask || !out) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (on_device) return launch_render_priors_planes(ctx, prior_uv, prior_mask, L, K, height, width, ndc, out, s);
+  CtxExtra* x = X(ctx);
+  const size_t LK = (size_t)L * K, n_out = LK * height * width;
+  rc = x->io.grow(ctx, (n_out + 2 * LK) * sizeof(float) + LK + 4096);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  float* a = bp.take<float>(2 * LK); uint8_t* b = bp.take<uint8_t>(LK); float* c = bp.take<float>(n_out);
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(a, prior_uv, 2 * LK * sizeof(float), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b, prior_mask, LK, cudaMemcpyHostToDevice, s));
+  rc = launch_render_priors_planes(ctx, a, b, L, K, height, width, ndc, c, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(out, c, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
 }
 
 int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj, double threshold,

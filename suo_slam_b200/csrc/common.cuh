@@ -92,6 +92,10 @@ int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H
 int launch_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes,
                        const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
                        cudaStream_t s);
+int launch_render_priors_planes(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int vh, int vw, int ndc,
+                                float* out, cudaStream_t s);
+int launch_render_priors_nhwc(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int R, float* out, int out_c,
+                              cudaStream_t s);
 int launch_maxpool2(suo_ctx* ctx, const float* in, int B, int H, int W, int C, float* out, cudaStream_t s);
 int launch_upsample_add(suo_ctx* ctx, const float* up1, const float* low, int B, int H, int W, int C, float* out,
                         cudaStream_t s);

@@ -124,7 +124,7 @@ int launch_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int 
   dim3 g((R * R + 255) / 256, L);
   roi_align_kernel<<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
   ctx->launches++;
-  if (out_c == 48) {
+  if (out_c == 48 && num_kp >= 0) {   // num_kp < 0: RGB only, the caller renders the prior channels itself (prior.cu)
     dim3 g2(R * R / 64, L);
     prior_to_nhwc_kernel<<<g2, 256, 0, s>>>(priors, num_kp, R * R, out, out_c);
     ctx->launches++;

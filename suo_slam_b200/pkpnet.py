@@ -43,6 +43,14 @@ class PkpNet:
         self._ctx = None
         return self
 
+    def load_packed(self, blob: bytes):
+        """Weights already folded and packed (suo_slam_b200.checkpoint.convert / weights.pack_state_dict)."""
+        h = np.frombuffer(blob[:64], np.int32)
+        if h[0] != weights.MAGIC or h[2] != self.num_kp:
+            raise RuntimeError("not a packed PkpNet weight blob for this keypoint vocabulary")
+        self._sd, self._blob, self._ctx = None, bytes(blob), None
+        return self
+
     def state_dict(self):
         return dict(self._sd) if self._sd is not None else {}
 
@@ -80,9 +88,14 @@ class PkpNet:
         return self._ctx
 
     # ---- forward ---------------------------------------------------------------------
-    def forward(self, images, boxes, prior_kp=None):
+    def forward(self, images, boxes, prior_kp=None, prior_uv=None):
         """images [B,3,H,W] f32; boxes: list (len B) of [L_i,4] xyxy; prior_kp: list of
-        [L_i,41,R,R] or None.  Returns the reference's dict of torch tensors on images.device."""
+        [L_i,41,R,R] or None.  Returns the reference's dict of torch tensors on images.device.
+
+        Extension: instead of the dense ``prior_kp`` planes the caller may pass
+        ``prior_uv`` = list (len B) of ``(uv [L_i,41,2] f32 NDC, mask [L_i,41] bool)`` — what ObjectSLAM has
+        in hand before it calls utils.make_prior_kp_input (lib/object_slam.py:510-514); the planes are then
+        stamped into the network input on the device (bit-identical to the reference's planes)."""
         assert type(boxes) == list and len(boxes) == images.shape[0]          # pkpnet.py:91
         ctx = self.context()
         dev = images.device
@@ -98,6 +111,14 @@ class PkpNet:
         if prior_kp is not None:
             priors = torch.cat(list(prior_kp)).to(**f32).contiguous()
             assert priors.shape == (L, self.num_kp, *self.input_res), priors.shape
+        puv = pmask = None
+        if prior_uv is not None:
+            if prior_kp is not None:
+                raise ValueError("give prior_kp (planes) or prior_uv (keypoints), not both")
+            assert len(prior_uv) == len(boxes)
+            puv = torch.cat([torch.as_tensor(u).reshape(-1, self.num_kp, 2) for u, _ in prior_uv]).to(**f32).contiguous()
+            pmask = torch.cat([torch.as_tensor(m).reshape(-1, self.num_kp) for _, m in prior_uv]).to(dtype=torch.uint8, device=dev).contiguous()
+            assert puv.shape[0] == L and pmask.shape[0] == L
         K, HM = self.num_kp, self.input_res[0] // 4
         out = {
             "uv": torch.empty((L, K, 2), **f32),
@@ -110,11 +131,14 @@ class PkpNet:
         prob = torch.empty((L, K, HM, HM), **f32) if self.return_prob else None
         stream = torch.cuda.current_stream(dev).cuda_stream if on_dev else None
         B, _, H, W = images.shape
-        ctx.check(_lib.lib().suo_forward(
-            ctx.handle, _lib.ptr(images), B, H, W, _lib.ptr(boxes_t), _lib.ptr(box_img), L, _lib.ptr(priors),
-            _lib.ptr(out["uv"]), _lib.ptr(cov), _lib.ptr(out["prob_logits"]), _lib.ptr(prob),
-            _lib.ptr(out["kp_mask_logits"]), _lib.ptr(out["kp_mask"]), _lib.ptr(out["argmax"]),
-            1 if on_dev else 0, stream))
+        outs = (_lib.ptr(out["uv"]), _lib.ptr(cov), _lib.ptr(out["prob_logits"]), _lib.ptr(prob),
+                _lib.ptr(out["kp_mask_logits"]), _lib.ptr(out["kp_mask"]), _lib.ptr(out["argmax"]), 1 if on_dev else 0, stream)
+        if puv is not None:
+            ctx.check(_lib.lib().suo_forward_kp_priors(ctx.handle, _lib.ptr(images), B, H, W, _lib.ptr(boxes_t), _lib.ptr(box_img), L,
+                                                       _lib.ptr(puv), _lib.ptr(pmask), *outs))
+        else:
+            ctx.check(_lib.lib().suo_forward(ctx.handle, _lib.ptr(images), B, H, W, _lib.ptr(boxes_t), _lib.ptr(box_img), L,
+                                             _lib.ptr(priors), *outs))
         if cov is not None:
             out["cov"] = cov
         if prob is not None:

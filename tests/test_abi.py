@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from suo_slam_b200 import _lib, arch, synth, weights
 
@@ -68,3 +69,30 @@ def test_pkpnet_rejects_bad_state_dict():
     with pytest.raises(RuntimeError):
         PkpNet().load_state_dict(bad)
     PkpNet().load_state_dict(sd)        # packs without a GPU
+
+
+def test_checkpoint_converter_roundtrip(tmp_path):
+    """Row f4: a checkpoint in the reference's format (train.py:173-181: {'model', 'epoch', 'args'}, keys prefixed
+    with 'module.' when trained under DataParallelWrapper) -> packed weights file -> the same blob
+    PkpNet.load_state_dict would have built."""
+    import argparse
+    import torch
+    from suo_slam_b200 import checkpoint, synth, weights
+    from suo_slam_b200.pkpnet import PkpNet
+    sd = synth.make_synthetic_state_dict(seed=3)
+    ck = tmp_path / "checkpoint-7.pth.tar"
+    torch.save({"model": {"module." + k: v for k, v in sd.items()}, "epoch": 7, "best_result": 0.5,
+                "args": argparse.Namespace(dataset="ycbv", lr=1e-3)}, ck)
+    sd2, epoch, args = checkpoint.load_checkpoint(str(ck))
+    assert epoch == 7 and args.dataset == "ycbv" and set(sd2) == set(sd)
+    meta = checkpoint.convert(str(ck), str(tmp_path / "m.suo"))
+    blob, meta2 = checkpoint.load_packed(str(tmp_path / "m.suo"))
+    assert meta2 == meta and meta["epoch"] == 7 and meta["n_convs"] == 187
+    assert blob == weights.pack_state_dict(sd)
+    m = PkpNet().load_packed(blob)
+    assert m._blob == blob
+    with pytest.raises(ValueError):
+        torch.save({"epoch": 1}, tmp_path / "bad.pth.tar")
+        checkpoint.load_checkpoint(str(tmp_path / "bad.pth.tar"))
+    with pytest.raises(RuntimeError):
+        PkpNet().load_packed(b"\\0" * 128)

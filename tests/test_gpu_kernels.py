@@ -132,3 +132,31 @@ def test_crop_concat_vs_torchvision(gpu_ctx, with_prior):
         assert not out[..., 44:].any()
     else:
         assert not out[..., 3].any()
+
+
+def test_render_priors_vs_reference_golden(gpu_ctx, golden_dir):
+    """Row f2: prior planes rendered on the GPU == planes produced by the unmodified reference
+    utils.make_prior_kp_input (tests/golden/prior.npz), bit for bit — .5 ties, clamping, NaN/inf, masked
+    keypoints, windows clipped by every border, NDC and pixel input."""
+    import os
+    from suo_slam_b200 import utils
+    g = np.load(os.path.join(golden_dir, "prior.npz"))
+    for name in "abc":
+        uv, mask, shape, ndc = g[name + "_uv"], g[name + "_mask"], tuple(int(v) for v in g[name + "_shape"]), bool(g[name + "_ndc"])
+        got = utils.make_prior_kp_input_batch(uv, mask, shape, ndc=ndc, ctx=gpu_ctx)
+        assert got.dtype == np.float32 and np.array_equal(got, g[name + "_planes"]), name
+    one = utils.make_prior_kp_input(g["a_uv"][1], g["a_mask"][1], (256, 256), ctx=gpu_ctx)      # the reference's single-object form
+    assert np.array_equal(one, g["a_planes"][1])
+
+
+def test_render_priors_vs_oracle_full_size(gpu_ctx):
+    """A whole frame's worth at the reference's size: 8 objects x 41 keypoints x 256 x 256."""
+    from oracle import prior_oracle
+    from suo_slam_b200 import utils
+    rng = np.random.default_rng(3)
+    uv = rng.uniform(-1.1, 1.1, size=(8, 41, 2)).astype(np.float32)
+    mask = rng.random((8, 41)) < 0.5
+    got = utils.make_prior_kp_input_batch(uv, mask, (256, 256), ctx=gpu_ctx)
+    ref = np.stack([prior_oracle.make_prior_kp_input(uv[i], mask[i], (256, 256)) for i in range(8)])
+    assert np.array_equal(got, ref)
+    assert not got[~mask].any() and (got[mask].reshape(mask.sum(), -1).max(1) > 0.99).all()   # centre may sit on the clipped row 256

@@ -128,3 +128,29 @@ def test_forward_errors(sd):
         m(torch.zeros(1, 3, 32, 32), [torch.tensor([[0.0, 0.0, 8.0, 8.0]] * 3)])       # more crops than max_crops
     with pytest.raises(AssertionError):
         m(torch.zeros(2, 3, 32, 32), [torch.tensor([[0.0, 0.0, 8.0, 8.0]])])           # len(boxes) != batch (pkpnet.py:91)
+
+
+def test_forward_with_keypoint_priors_equals_dense_priors(sd):
+    """Row f2 fused: model(images, boxes, prior_uv=[(uv, mask)]) stamps the prior planes into the network input on
+    the device; the result must be IDENTICAL to feeding the reference's dense planes through prior_kp."""
+    from oracle import prior_oracle
+    rng = np.random.default_rng(12)
+    img = torch.from_numpy(rng.random((2, 3, 120, 160), dtype=np.float32))
+    boxes = [torch.tensor([[10.0, 8.0, 90.0, 100.0], [40.5, 20.25, 150.0, 110.0]]), torch.tensor([[30.0, 30.0, 112.0, 95.0]])]
+    uv = rng.uniform(-1.1, 1.1, size=(3, 41, 2)).astype(np.float32)
+    mask = rng.random((3, 41)) < 0.4
+    mask[1] = False                                  # a non-symmetric object in the same batch: all-zero prior planes
+    planes = np.stack([prior_oracle.make_prior_kp_input(uv[i], mask[i], (64, 64)) for i in range(3)])
+    m = _model(sd, 2, 3)
+    dense = m(img.cuda(), [b.cuda() for b in boxes], [torch.from_numpy(planes[:2]).cuda(), torch.from_numpy(planes[2:]).cuda()])
+    fused = m(img.cuda(), [b.cuda() for b in boxes], prior_uv=[(uv[:2], mask[:2]), (uv[2:], mask[2:])])
+    host = m(img, boxes, prior_uv=[(uv[:2], mask[:2]), (uv[2:], mask[2:])])          # host tensors: staged by the C ABI
+    torch.cuda.synchronize()
+    for k in ("prob_logits", "uv", "cov", "kp_mask", "argmax"):
+        assert torch.equal(dense[k], fused[k]), k
+        assert torch.equal(dense[k].cpu(), host[k]), k
+    ref = net_oracle.pkpnet_forward(sd, img, boxes, [torch.from_numpy(planes[:2]), torch.from_numpy(planes[2:])], (64, 64))
+    np.testing.assert_allclose(fused["uv"].cpu().numpy(), ref["uv"].numpy(), atol=5e-5)
+    with pytest.raises(ValueError):
+        m(img.cuda(), [b.cuda() for b in boxes], [torch.from_numpy(planes[:2]).cuda(), torch.from_numpy(planes[2:]).cuda()],
+          prior_uv=[(uv[:2], mask[:2]), (uv[2:], mask[2:])])

@@ -1,5 +1,7 @@
 """CPU: the net oracle (oracle/net_oracle.py) against fixtures produced by the UNMODIFIED
 reference modules (oracle/gen_golden_net.py), and live against the reference when mounted."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -74,3 +76,39 @@ def test_oracle_vs_live_reference(sd):
     b = net_oracle.pkpnet_forward(sd, img, boxes, None, (64, 64))
     for k in ("uv", "cov", "kp_mask", "prob_logits"):
         np.testing.assert_allclose(b[k].numpy(), a[k].numpy(), atol=2e-4 if k == "prob_logits" else 1e-5)
+
+
+def test_prior_oracle_reproduces_reference_golden(golden_dir):
+    """Row f2: the restated make_prior_kp_input against planes produced by the unmodified reference function."""
+    from oracle import prior_oracle
+    g = np.load(os.path.join(golden_dir, "prior.npz"))
+    for name in "abc":
+        uv, mask, shape, ndc = g[name + "_uv"], g[name + "_mask"], tuple(g[name + "_shape"]), bool(g[name + "_ndc"])
+        got = np.stack([prior_oracle.make_prior_kp_input(uv[i], mask[i], shape, ndc=ndc) for i in range(len(uv))])
+        assert np.array_equal(got, g[name + "_planes"]), name
+
+
+def test_prior_stamp_table_is_the_reference_stamp():
+    """The committed device table (csrc/prior_gauss_table.inc) == the stamp OpenCV produces for the reference call."""
+    from oracle import prior_oracle
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "suo_slam_b200", "csrc", "prior_gauss_table.inc")
+    words = []
+    for line in open(path):
+        if line.startswith("0x"):
+            words += [int(w.strip().rstrip("u"), 16) for w in line.strip().rstrip(",").split(",")]
+    q = np.array(words, np.uint32).view(np.float32).reshape(46, 46)
+    g = prior_oracle.gaussian_2d(91)
+    idx = np.minimum(np.arange(91), 90 - np.arange(91))
+    assert np.array_equal(q[np.ix_(idx, idx)], g)
+    assert g[45, 45] == 1.0 and g[0, 45] > g[1, 45]        # BORDER_REFLECT_101 doubles the outermost tap
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not mounted")
+def test_prior_oracle_vs_live_reference():
+    from oracle import prior_oracle
+    ref_utils = ref_shims.import_reference_utils()
+    rng = np.random.default_rng(1)
+    for dt in (np.float32, np.float64):
+        uv = rng.uniform(-1.2, 1.2, size=(41, 2)).astype(dt)
+        m = rng.random(41) < 0.7
+        assert np.array_equal(prior_oracle.make_prior_kp_input(uv, m, (256, 256)), ref_utils.make_prior_kp_input(uv, m, (256, 256)))
