@@ -182,6 +182,19 @@ int suo_solve_keypoints(suo_ctx* ctx, const float* uv, const float* cov, const f
                         const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
                         double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, int on_device, void* stream);
 
+/* ---- hypothesis scoring -------------------------------------- */
+/* The chi2 inlier count that ObjectSLAM.__estimate_camera_pose (lib/object_slam.py:1030-1066, camera-pose voting) and
+ * __maybe_reinit_objects (:645-680) evaluate in nested Python loops, for a batch of (pose, detection) pairs:
+ *   T_pairs [n_pairs,12] f64 row-major [R|t] = T_OtoC hypothesis of each pair, pair_det[n_pairs] its detection
+ *   det_off[n_det+1] keypoint rows of each detection; model_kp [N,3] f64; K [n_det,9] f64 (the detection's bbox-NDC
+ *   camera matrix); uv [N,2] f32; cov [N,4] f32 or NULL (then inf = I / manual_kp_std^2, :1059-1061);
+ *   use [N] u8 or NULL (the detection's "inliers" mask, :1035)
+ *   counts[n_pairs]: keypoints in front of the camera whose chi2 (cov diagonal floored at 1e-4) is <= chi2_gate. */
+int suo_chi2_inlier_counts(suo_ctx* ctx, int n_pairs, const double* T_pairs, const int32_t* pair_det, int n_det,
+                           const int32_t* det_off, const double* model_kp, const double* K, const float* uv,
+                           const float* cov, const uint8_t* use, double manual_kp_std, double chi2_gate,
+                           int32_t* counts, int on_device, void* stream);
+
 /* ---- fused per-frame pipeline -------------------------------------------------- */
 /* One call for a batch of single-view frames: forward -> keypoint gating
  * (lib/object_slam.py:1100-1115) -> per-object PnP (:1123-1165) -> single-view BA

@@ -25,7 +25,7 @@ def exported_symbols():
     return ["suo_create", "suo_destroy", "suo_last_error", "suo_set_option", "suo_kernel_launches",
             "suo_load_weights", "suo_forward", "suo_heatmap_reduce", "suo_crop_concat", "suo_conv2d",
             "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range",
-            "suo_forward_kp_priors", "suo_render_priors"]
+            "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts"]
 
 
 def lib():
@@ -46,6 +46,7 @@ def lib():
         L.suo_forward.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp] + [vp] * 7 + [C.c_int, vp]
         L.suo_forward_kp_priors.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp] + [vp] * 7 + [C.c_int, vp]
         L.suo_render_priors.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp]
+        L.suo_chi2_inlier_counts.argtypes = [vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double, vp, C.c_int, vp]
         L.suo_heatmap_reduce.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp] + [vp] * 6 + [C.c_int, vp]
         L.suo_crop_concat.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, C.c_int,
                                       C.c_int, vp]

@@ -1172,6 +1172,38 @@ int suo_solve_keypoints(suo_ctx* ctx, const float* uv, const float* cov, const f
   return SUO_OK;
 }
 
+int suo_chi2_inlier_counts(suo_ctx* ctx, int n_pairs, const double* T_pairs, const int32_t* pair_det, int n_det,
+                           const int32_t* det_off, const double* model_kp, const double* K, const float* uv, const float* cov,
+                           const uint8_t* use, double manual_kp_std, double chi2_gate, int32_t* counts, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (n_pairs <= 0 || n_det <= 0 || !T_pairs || !pair_det || !det_off || !model_kp || !K || !uv || !counts || !(manual_kp_std > 0)) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (on_device) return launch_chi2_counts(ctx, n_pairs, T_pairs, pair_det, det_off, model_kp, K, uv, cov, use, manual_kp_std, chi2_gate, counts, s);
+  const size_t N = (size_t)det_off[n_det];
+  for (int p = 0; p < n_pairs; ++p)
+    if (pair_det[p] < 0 || pair_det[p] >= n_det) { ctx->set_error("suo_chi2_inlier_counts: pair_det out of range", __FILE__, __LINE__); return SUO_E_INVALID; }
+  CtxExtra* x = X(ctx);
+  rc = x->io.grow(ctx, (size_t)n_pairs * (12 * 8 + 4 + 4) + (size_t)(n_det + 1) * 4 + (size_t)n_det * 72 + N * (24 + 8 + 16 + 1) + 16 * 256);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  double* d_T = bp.take<double>(12 * (size_t)n_pairs); int32_t* d_pd = bp.take<int32_t>(n_pairs); int32_t* d_off = bp.take<int32_t>(n_det + 1);
+  double* d_mk = bp.take<double>(3 * N); double* d_K = bp.take<double>(9 * (size_t)n_det); float* d_uv = bp.take<float>(2 * N);
+  float* d_cov = cov ? bp.take<float>(4 * N) : nullptr; uint8_t* d_use = use ? bp.take<uint8_t>(N) : nullptr;
+  int32_t* d_cnt = bp.take<int32_t>(n_pairs);
+#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+  H2D(d_T, T_pairs, 96 * (size_t)n_pairs); H2D(d_pd, pair_det, 4 * (size_t)n_pairs); H2D(d_off, det_off, 4 * (size_t)(n_det + 1));
+  H2D(d_mk, model_kp, 24 * N); H2D(d_K, K, 72 * (size_t)n_det); H2D(d_uv, uv, 8 * N);
+  if (cov) H2D(d_cov, cov, 16 * N);
+  if (use) H2D(d_use, use, N);
+#undef H2D
+  rc = launch_chi2_counts(ctx, n_pairs, d_T, d_pd, d_off, d_mk, d_K, d_uv, d_cov, d_use, manual_kp_std, chi2_gate, d_cnt, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(counts, d_cnt, 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
 int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
                int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
                const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,

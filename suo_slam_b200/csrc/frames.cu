@@ -158,6 +158,51 @@ __global__ void ba_scatter_kernel(const int32_t* __restrict__ frame_start, const
   }
 }
 
+// ---- f1: chi2 inlier counting of keypoint detections under pose hypotheses ----
+// The inner loop shared by ObjectSLAM.__estimate_camera_pose (lib/object_slam.py:1030-1066: every camera-pose
+// hypothesis is scored by the keypoints it explains over ALL objects) and __maybe_reinit_objects (:645-680: PnP pose
+// vs current estimate over the last 15 views).  One warp per (pose, detection) pair:
+//   p_C = R p_O + t (utils.transform_pts), uvw = K p_C, keep w > 0, res = uv - uvw.xy / w,
+//   cov diagonal floored at 1e-4 (:1054, :669) then inverted — or 1 / manual_kp_std^2 when there is no network
+//   covariance (:1059-1061) — chi2 = res^T inf res, count chi2 <= gate.
+// The reference inverts the float32 covariance in float32 (np.linalg.inv); here the float32 inputs are widened and
+// the 2x2 inverse is closed-form FP64: identical counts unless a chi2 sits within ~1e-6 relative of the gate.
+__global__ void chi2_count_kernel(const double* __restrict__ T, const int32_t* __restrict__ pair_det,
+                                  const int32_t* __restrict__ det_off, const double* __restrict__ model_kp,
+                                  const double* __restrict__ Kmat, const float* __restrict__ uv, const float* __restrict__ cov,
+                                  const uint8_t* __restrict__ use, double inv_manual_var, double gate, int n_pairs,
+                                  int32_t* __restrict__ counts) {
+  const int pair = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pair >= n_pairs) return;
+  const double* P = T + 12 * (size_t)pair;
+  const int d = pair_det[pair];
+  const double* Kd = Kmat + 9 * (size_t)d;
+  int cnt = 0;
+  for (int r = det_off[d] + lane; r < det_off[d + 1]; r += 32) {
+    if (use && !use[r]) continue;
+    const double x = model_kp[3 * r], y = model_kp[3 * r + 1], z = model_kp[3 * r + 2];
+    const double pc0 = P[0] * x + P[1] * y + P[2] * z + P[3];
+    const double pc1 = P[4] * x + P[5] * y + P[6] * z + P[7];
+    const double pc2 = P[8] * x + P[9] * y + P[10] * z + P[11];
+    const double w = Kd[6] * pc0 + Kd[7] * pc1 + Kd[8] * pc2;
+    if (!(w > 0)) continue;
+    const double r0 = (double)uv[2 * r] - (Kd[0] * pc0 + Kd[1] * pc1 + Kd[2] * pc2) / w;
+    const double r1 = (double)uv[2 * r + 1] - (Kd[3] * pc0 + Kd[4] * pc1 + Kd[5] * pc2) / w;
+    double chi2;
+    if (cov) {
+      const double a = fmax((double)cov[4 * r], 1e-4), b = (double)cov[4 * r + 1], c = (double)cov[4 * r + 2], e = fmax((double)cov[4 * r + 3], 1e-4);
+      const double det = a * e - b * c;
+      chi2 = (r0 * (e * r0 - b * r1) + r1 * (-c * r0 + a * r1)) / det;
+    } else {
+      chi2 = (r0 * r0 + r1 * r1) * inv_manual_var;
+    }
+    cnt += (chi2 <= gate) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) counts[pair] = cnt;
+}
+
 }  // namespace
 
 int launch_gate_compact(suo_ctx* ctx, const float* uv, const float* cov, const float* kp_mask, const uint8_t* model_mask,
@@ -194,6 +239,17 @@ int launch_ba_scatter(suo_ctx* ctx, int n_img, const int32_t* frame_start, const
                       const uint8_t* inliers, const double* poses, const uint8_t* accepted, int K, double* T_ba,
                       uint8_t* ba_inliers, cudaStream_t s) {
   ba_scatter_kernel<<<n_img, 64, 0, s>>>(frame_start, edge_cnt, edge_src, inliers, poses, accepted, K, T_ba, ba_inliers);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
+}
+
+int launch_chi2_counts(suo_ctx* ctx, int n_pairs, const double* T, const int32_t* pair_det, const int32_t* det_off,
+                       const double* model_kp, const double* K, const float* uv, const float* cov, const uint8_t* use,
+                       double manual_kp_std, double gate, int32_t* counts, cudaStream_t s) {
+  if (n_pairs <= 0) return SUO_OK;
+  chi2_count_kernel<<<(n_pairs + 7) / 8, 256, 0, s>>>(T, pair_det, det_off, model_kp, K, uv, cov, use,
+                                                      1.0 / (manual_kp_std * manual_kp_std), gate, n_pairs, counts);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;

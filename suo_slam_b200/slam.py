@@ -1,0 +1,112 @@
+"""Hypothesis scoring between the three hot-path calls of a SLAM-mode frame: the camera-pose
+vote (ObjectSLAM.__estimate_camera_pose, reference lib/object_slam.py:975-1072) and the re-initialisation test
+(__maybe_reinit_objects, :595-697).  Both are nested Python loops around one primitive — count the keypoints a pose
+hypothesis explains (chi2 <= 5.991) — which runs here as ONE kernel launch over all (hypothesis, detection) pairs
+(``suo_chi2_inlier_counts``, csrc/frames.cu).  The few 4x4 products that compose the hypotheses stay in numpy, written
+exactly as the reference writes them (including its float32 staging of the object / camera poses).
+
+A *detection* is the reference's ``detections[view][obj]`` dict: keys ``pose`` (4x4 T_OtoC from PnP or None),
+``model_kp`` [n,3], ``K`` [3,3], ``uv_pred`` [n,2], ``cov_pred`` [n,2,2] or None, ``inliers`` [n] bool.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, runtime
+
+CHI2_GATE = 5.991
+
+
+def invert_SE3(T):
+    """utils.invert_SE3 (lib/utils/utils.py:431-435)."""
+    T = np.asarray(T)
+    out = np.eye(4, dtype=T.dtype)
+    out[:3, :3] = T[:3, :3].T
+    out[:3, 3] = -T[:3, :3].T @ T[:3, 3]
+    return out
+
+
+def _as44(T, dtype=np.float64):
+    out = np.zeros((4, 4), dtype)
+    out[:3, :] = np.asarray(T)[:3, :]
+    out[3, 3] = 1
+    return out
+
+
+def chi2_inlier_counts(T_pairs, pair_det, dets, use_inlier_mask, manual_kp_std=0.05, gate=CHI2_GATE, ctx=None):
+    """counts[p] = #keypoints of detection dets[pair_det[p]] explained by T_pairs[p] (a T_OtoC)."""
+    ctx = ctx or runtime.get_context()
+    T = np.ascontiguousarray(np.asarray(T_pairs, np.float64)[:, :3, :4]).reshape(-1, 12)
+    pd = np.ascontiguousarray(pair_det, np.int32)
+    off = np.zeros(len(dets) + 1, np.int32)
+    off[1:] = np.cumsum([len(d["uv_pred"]) for d in dets])
+    mk = np.ascontiguousarray(np.concatenate([np.asarray(d["model_kp"], np.float64).reshape(-1, 3) for d in dets]))
+    K = np.ascontiguousarray(np.stack([np.asarray(d["K"], np.float64) for d in dets])).reshape(-1, 9)
+    uv = np.ascontiguousarray(np.concatenate([np.asarray(d["uv_pred"], np.float32).reshape(-1, 2) for d in dets]))
+    has_cov = [d.get("cov_pred") is not None for d in dets]
+    if any(has_cov) and not all(has_cov):
+        raise ValueError("either every detection carries cov_pred or none does (ObjectSLAM.no_network_cov is global)")
+    cov = np.ascontiguousarray(np.concatenate([np.asarray(d["cov_pred"], np.float32).reshape(-1, 4) for d in dets])) if all(has_cov) else None
+    use = np.ascontiguousarray(np.concatenate([np.asarray(d["inliers"]).astype(np.uint8) for d in dets])) if use_inlier_mask else None
+    counts = np.zeros(len(pd), np.int32)
+    ctx.check(_lib.lib().suo_chi2_inlier_counts(ctx.handle, len(pd), _lib.ptr(T), _lib.ptr(pd), len(dets), _lib.ptr(off), _lib.ptr(mk),
+                                                _lib.ptr(K), _lib.ptr(uv), _lib.ptr(cov), _lib.ptr(use), float(manual_kp_std), float(gate),
+                                                _lib.ptr(counts), 0, None))
+    return counts
+
+
+def estimate_camera_pose(obj_poses, curr_det, min_num_inliers=4, manual_kp_std=0.05, ctx=None, return_counts=False):
+    """ObjectSLAM.__estimate_camera_pose (:975-1072).  obj_poses: {obj_id: T_OtoG [>=3,4]}, curr_det: {obj_id: detection}.
+    Every object with a PnP pose votes T_GtoC = T_OtoC_pnp @ inv(T_OtoG); the hypothesis explaining the most keypoints
+    over all voting objects wins (first one on ties, and only with >= min_num_inliers).  Returns T_GtoC [4,4] or None."""
+    obj_ids = [o for o in curr_det if curr_det[o].get("pose") is not None and o in obj_poses]
+    if not obj_ids:
+        return (None, None) if return_counts else None
+    n = len(obj_ids)
+    Ts_GtoO = np.stack([invert_SE3(_as44(obj_poses[o])) for o in obj_ids])
+    Ts_OtoG = np.stack([_as44(obj_poses[o], np.float32) for o in obj_ids])          # float32 staging, :1005-1008
+    Ts_OtoC_pnp = np.stack([np.asarray(curr_det[o]["pose"]) for o in obj_ids])
+    Ts_hyp = Ts_OtoC_pnp @ Ts_GtoO                                                  # :1011
+    Ts_OtoC_hyp = Ts_hyp[:, None] @ Ts_OtoG[None]                                   # [hypothesis, object], :1030
+    dets = [curr_det[o] for o in obj_ids]
+    counts = chi2_inlier_counts(Ts_OtoC_hyp.reshape(n * n, 4, 4), np.tile(np.arange(n, dtype=np.int32), n), dets, True,
+                                manual_kp_std, ctx=ctx).reshape(n, n).sum(1)
+    best, best_n = None, -1
+    for i in range(n):                                                              # :1068-1070
+        if counts[i] >= min_num_inliers and counts[i] > best_n:
+            best, best_n = Ts_hyp[i], int(counts[i])
+    return (best, counts) if return_counts else best
+
+
+def maybe_reinit_objects(obj_poses, cam_poses, detections, view_ids, view_id, check_n_views=15, manual_kp_std=0.05, ctx=None,
+                         return_counts=False):
+    """ObjectSLAM.__maybe_reinit_objects (:595-697).  For every mapped object with a PnP pose in the current view, count
+    the keypoints explained over the last ``check_n_views`` views by (a) the PnP pose moved to the world frame and
+    (b) the current estimate; re-initialise when pnp >= 3 and pnp > 3 * estim.  Returns {obj_id: new T_OtoG [4,4]}
+    (the caller assigns them to obj_poses, :687)."""
+    if len(view_ids) < 2 or view_id not in cam_poses:
+        return ({}, {}) if return_counts else {}
+    check_n_views = min(len(view_ids), check_n_views)
+    curr_det = detections[view_id]
+    obj_ids = [o for o in obj_poses if curr_det.get(o, {}).get("pose") is not None]
+    if not obj_ids:
+        return ({}, {}) if return_counts else {}
+    Ts_estim = np.stack([_as44(obj_poses[o], np.float32) for o in obj_ids])         # :619-622
+    Ts_pnp_G = invert_SE3(_as44(cam_poses[view_id]))[None] @ np.stack([np.asarray(curr_det[o]["pose"]) for o in obj_ids])   # :627
+    views = [view_ids[-(i + 1)] for i in range(check_n_views)]
+    Ts_GtoCi = np.stack([_as44(cam_poses[v], np.float32) for v in views])           # :630-633
+    T_key = {"pnp": Ts_GtoCi[:, None] @ Ts_pnp_G[None], "estim": Ts_GtoCi[:, None] @ Ts_estim[None]}
+    dets, T_pairs, owner = [], [], []
+    for j, o in enumerate(obj_ids):
+        for i, v in enumerate(views):
+            if o in detections[v]:
+                dets.append(detections[v][o])
+                for key in ("pnp", "estim"):
+                    T_pairs.append(T_key[key][i, j]); owner.append((j, key, len(dets) - 1))
+    num = {o: {"pnp": 0, "estim": 0} for o in obj_ids}
+    if T_pairs:
+        c = chi2_inlier_counts(np.stack(T_pairs), np.array([d for _, _, d in owner], np.int32), dets, False, manual_kp_std, ctx=ctx)
+        for (j, key, _), v in zip(owner, c):
+            num[obj_ids[j]][key] += int(v)
+    new = {o: Ts_pnp_G[j] for j, o in enumerate(obj_ids) if num[o]["pnp"] >= 3 and num[o]["pnp"] > 3 * num[o]["estim"]}   # :683-687
+    return (new, num) if return_counts else new

@@ -209,7 +209,7 @@ def make_global_graph(seed: int, n_views: int = 12, n_obj: int = 6, kp_range=(8,
             m += rng.normal(scale=noise_px, size=m.shape)
             out = rng.random(len(m)) < outlier_frac
             m[out] += rng.uniform(-80, 80, size=(int(out.sum()), 2))
-            sig = rng.uniform(0.5, 2.0, size=(len(m), 2)) * noise_px
+            sig = rng.uniform(0.5, 2.0, size=(len(m), 2)) * max(noise_px, 1e-3)
             rho = rng.uniform(-0.5, 0.5, size=len(m))
             for k in range(len(m)):
                 cov = np.array([[sig[k, 0] ** 2, rho[k] * sig[k, 0] * sig[k, 1]], [rho[k] * sig[k, 0] * sig[k, 1], sig[k, 1] ** 2]])
@@ -230,3 +230,52 @@ def make_global_graph(seed: int, n_views: int = 12, n_obj: int = 6, kp_range=(8,
     return dict(poses=poses, poses_gt=np.concatenate([T_wo, T_cw], 0), fixed=fixed, e_obj=np.asarray(e_obj, np.int32),
                 e_cam=np.asarray(e_cam, np.int32), cam_k=np.tile(cam_k, (n_e, 1)), p=np.asarray(p), uv=np.asarray(uv),
                 info=np.asarray(info), n_obj=n_obj, n_views=n_views)
+
+
+def make_slam_scene(seed: int, n_views: int = 6, n_obj: int = 6, kp_range=(8, 16), noise_ndc: float = 0.01,
+                    bad_pnp=(1,), bad_estimate=(2,), with_cov: bool = True):
+    """SLAM-mode state as ObjectSLAM keeps it (lib/object_slam.py:100-123): ``obj_poses`` {obj: T_OtoG [4,4]},
+    ``cam_poses`` {view: T_GtoC [4,4]}, ``detections`` {view: {obj: {pose, model_kp, K, uv_pred, cov_pred, inliers,
+    bbox}}} with bbox-NDC keypoints (utils.fix_K_for_bbox_ndc) and the reference's debug noise (:1131).  Objects in
+    ``bad_pnp`` get a wrong PnP pose in the LAST view (a bad camera-pose vote); objects in ``bad_estimate`` get a wrong
+    map pose (candidates for re-initialisation).  The last view is the "current" one."""
+    rng = np.random.default_rng(seed)
+    g = make_global_graph(seed, n_views, n_obj, kp_range=kp_range, see_prob=1.0, noise_px=0.0, outlier_frac=0.0, perturb=0.0)
+    T_wo, T_cw = g["poses_gt"][:n_obj], g["poses_gt"][n_obj:]
+    kps = [g["p"][(g["e_obj"] == o) & (g["e_cam"] == n_obj)] for o in range(n_obj)]
+    to44 = lambda T: np.vstack([T, [0, 0, 0, 1.0]])
+    obj_poses, cam_poses, detections = {}, {}, {}
+    for o in range(n_obj):
+        T = to44(T_wo[o])
+        if o in bad_estimate:
+            T[:3, 3] += [60.0, -40.0, 30.0]
+            T[:3, :3] = so3_exp(np.array([0.3, -0.2, 0.25])) @ T[:3, :3]
+        obj_poses[10 + o] = T
+    for v in range(n_views):
+        cam_poses[100 + v] = to44(T_cw[v])
+        detections[100 + v] = {}
+        for o in range(n_obj):
+            T_oc = to44(T_cw[v]) @ to44(T_wo[o])
+            pc = kps[o] @ T_oc[:3, :3].T + T_oc[:3, 3]
+            px = np.c_[K_YCBV[0, 0] * pc[:, 0] / pc[:, 2] + K_YCBV[0, 2], K_YCBV[1, 1] * pc[:, 1] / pc[:, 2] + K_YCBV[1, 2]]
+            lo, hi = px.min(0), px.max(0)
+            c, half = 0.5 * (lo + hi), 0.55 * np.maximum(hi - lo, 10.0)
+            bbox = np.array([c[0] - half[0], c[1] - half[1], c[0] + half[0], c[1] + half[1]])
+            Kb = fix_K_for_bbox_ndc(K_YCBV, bbox)
+            h = pc @ Kb.T
+            uv = (h[:, :2] / h[:, 2:3] + rng.normal(scale=noise_ndc, size=(len(pc), 2))).astype(np.float32)
+            out = rng.random(len(uv)) < 0.1
+            uv[out] += rng.uniform(-0.5, 0.5, size=(int(out.sum()), 2)).astype(np.float32)
+            sig = rng.uniform(0.7, 1.5, size=(len(uv), 2)) * noise_ndc
+            rho = rng.uniform(-0.4, 0.4, size=len(uv))
+            cov = np.zeros((len(uv), 2, 2), np.float32)
+            cov[:, 0, 0], cov[:, 1, 1] = sig[:, 0] ** 2, sig[:, 1] ** 2
+            cov[:, 0, 1] = cov[:, 1, 0] = rho * sig[:, 0] * sig[:, 1]
+            pose = T_oc.copy()
+            pose[:3, 3] += rng.normal(scale=1.0, size=3)
+            if v == n_views - 1 and o in bad_pnp:
+                pose[:3, 3] += [80.0, 50.0, -120.0]
+                pose[:3, :3] = so3_exp(np.array([-0.4, 0.3, 0.2])) @ pose[:3, :3]
+            detections[100 + v][10 + o] = dict(pose=pose, model_kp=kps[o].copy(), K=Kb, uv_pred=uv, cov_pred=cov if with_cov else None,
+                                               inliers=~out | (rng.random(len(uv)) < 0.3), bbox=bbox)
+    return dict(obj_poses=obj_poses, cam_poses=cam_poses, detections=detections, view_ids=[100 + v for v in range(n_views)])
