@@ -52,10 +52,11 @@ def parse():
 def make_batch(seed0, n_frames):
     """n_frames synthetic frames -> flat per-crop arrays (host)."""
     from suo_slam_b200 import frames, synth
-    imgs, boxes, bi, mk, mm, kb, diam = [], [], [], [], [], [], []
+    imgs, imgs_u8, boxes, bi, mk, mm, kb, diam = [], [], [], [], [], [], [], []
     for f in range(n_frames):
         fr = synth.make_frame(seed0 + f, n_obj=CROPS, H=H, W=W)
-        imgs.append(fr["img"].transpose(2, 0, 1).astype(np.float32) / 255.0)     # object_slam.py:1092
+        imgs_u8.append(fr["img"])                                                # [H,W,3] u8, what process_view receives
+        imgs.append(fr["img"].transpose(2, 0, 1).astype(np.float32) / 255.0)     # object_slam.py:1092 (CPU reference arm)
         bb = [o["bbox"] for o in fr["objs"]]
         boxes += bb
         bi += [f] * CROPS
@@ -63,7 +64,7 @@ def make_batch(seed0, n_frames):
         mm += [o["model_kps_mask"] for o in fr["objs"]]
         diam += [o["diameter"] for o in fr["objs"]]
         kb.append(frames.k_bbox_for(fr["K"], bb))
-    return dict(images=np.ascontiguousarray(np.stack(imgs)), boxes=np.stack(boxes).astype(np.float32), box_img=np.asarray(bi, np.int32),
+    return dict(images=np.ascontiguousarray(np.stack(imgs)), images_u8=np.ascontiguousarray(np.stack(imgs_u8)), boxes=np.stack(boxes).astype(np.float32), box_img=np.asarray(bi, np.int32),
                 model_kps=np.stack(mk), model_mask=np.stack(mm).astype(np.uint8), K_bbox=np.concatenate(kb),
                 diameter=np.asarray(diam, np.float64))
 
@@ -205,7 +206,7 @@ def run_native(args):
     # distinct input sets per rank (disjoint frames of the stream), rotated between steps
     sets_h = [make_batch(10_000 * rank + 100 * s, F) for s in range(args.input_sets)]
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    sets_pin = [{k: pin(v) for k, v in b.items()} for b in sets_h]
+    sets_pin = [{k: pin(v) for k, v in b.items() if k != "images"} for b in sets_h]      # "images" (f32) is the CPU arm's input
     sets_dev = [{k: v.to(dev) for k, v in b.items()} for b in sets_pin]
     f64 = dict(dtype=torch.float64, device=dev)
     outs_dev = dict(T_pnp=torch.zeros((L, 16), **f64), T_ba=torch.zeros((L, 12), **f64),
@@ -219,8 +220,9 @@ def run_native(args):
 
     def step(b, on_device, o):
         p = _lib.ptr
-        ctx.check(lib.suo_frames(hdl, p(b["images"]), F, H, W, p(b["boxes"]), p(b["box_img"]), L, None, p(b["model_kps"]),
-                                 p(b["model_mask"]), p(b["K_bbox"]), p(b["diameter"]), 0.2, 0.9, 0, 1,
+        # the camera's u8 frames go in as they are (lib/object_slam.py:327-328); float32(img)/255 (:1092) happens per tap on the GPU
+        ctx.check(lib.suo_frames_u8(hdl, p(b["images_u8"]), F, H, W, p(b["boxes"]), p(b["box_img"]), L, None, p(b["model_kps"]),
+                                    p(b["model_mask"]), p(b["K_bbox"]), p(b["diameter"]), 0.2, 0.9, 0, 1,
                                  p(o["T_pnp"]), p(o["T_ba"]), p(o["used"]), p(o["bain"]),
                                  p(o.get("uv")), p(o.get("cov")), 1 if on_device else 0, sp))
         if world > 1:   # the single exchange of the step: fixed-size pose records of every rank's crops

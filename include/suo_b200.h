@@ -211,6 +211,18 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W,
                double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
                float* uv, float* cov, int on_device, void* stream);
 
+/* suo_frames on the camera's own frames: images_hwc [n_img,H,W,3] u8, as ObjectSLAM.process_view receives them
+ * (lib/object_slam.py:327-328).  The reference converts the frame on the host, float32(img) / 255 (:1092), and copies
+ * 4 bytes per value to the GPU; here the same division is applied per bilinear tap inside the crop kernel (identical
+ * crop values), so a frame costs a quarter of the PCIe bytes.  Everything else as suo_frames. */
+int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int W,
+                  const float* boxes, const int32_t* box_img, int L, const float* priors,
+                  const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                  const double* diameter, double kp_var_thresh, double bbox_thresh,
+                  uint64_t seed, int run_ba,
+                  double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
+                  float* uv, float* cov, int on_device, void* stream);
+
 /* ---- measurement ----------------------------------------------------------------- */
 /* Per-op CUDA-event timing of the network program on the current input buffer (eager launches):
  * average ms per forward in the conv kernels and in the pool / up-sample kernels.  bench.py uses it

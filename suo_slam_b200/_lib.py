@@ -25,7 +25,7 @@ def exported_symbols():
     return ["suo_create", "suo_destroy", "suo_last_error", "suo_set_option", "suo_kernel_launches",
             "suo_load_weights", "suo_forward", "suo_heatmap_reduce", "suo_crop_concat", "suo_conv2d",
             "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range",
-            "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts"]
+            "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts", "suo_frames_u8"]
 
 
 def lib():
@@ -59,6 +59,7 @@ def lib():
                                           C.c_uint64, C.c_int, vp, vp, vp, vp, C.c_int, vp]
         L.suo_frames.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.c_double,
                                  C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [C.c_int, vp]
+        L.suo_frames_u8.argtypes = L.suo_frames.argtypes
         L.suo_check_range.argtypes = [vp]
         L.suo_profile_network.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
         _lib = L

@@ -717,9 +717,10 @@ int suo_check_range(suo_ctx* ctx) {
 }
 
 // priors (dense planes) and prior_uv / prior_mask (keypoint priors rendered on the device) are mutually exclusive.
-static int forward_impl(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+static int forward_impl(suo_ctx* ctx, const void* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
                         int L, const float* priors, const float* prior_uv, const uint8_t* prior_mask, float* uv, float* cov,
-                        float* logits, float* prob, float* mask_logits, float* mask, int32_t* argmax, int on_device, void* stream) {
+                        float* logits, float* prob, float* mask_logits, float* mask, int32_t* argmax, int on_device, void* stream,
+                        int images_u8 = 0) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
@@ -735,12 +736,13 @@ static int forward_impl(suo_ctx* ctx, const float* images, int n_img, int H, int
   const int in_buf = variant ? N.h.in_buf_prior : N.h.in_buf_noprior;
   const size_t n_im = (size_t)n_img * 3 * H * W, n_pr = priors ? (size_t)L * K * R * R : 0;
   const size_t n_hm = (size_t)L * K * HM * HM, LK = (size_t)L * K;
-  const float *d_im = images, *d_box = boxes, *d_pr = priors, *d_puv = prior_uv;
+  const void* d_im = images;
+  const float *d_box = boxes, *d_pr = priors, *d_puv = prior_uv;
   const uint8_t* d_pm = prior_mask;
   const int32_t* d_bi = box_img;
   float* d_prob = prob;
   if (!on_device) {
-    rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0) + 3 * LK) * sizeof(float) + 8192);
+    rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0) + 3 * LK) * sizeof(float) + 8192);   // (u8 images need a quarter of n_im floats)
     if (rc) return rc;
     Bump bp{static_cast<uint8_t*>(x->io.d)};
     float* a = bp.take<float>(n_im);
@@ -754,18 +756,18 @@ static int forward_impl(suo_ctx* ctx, const float* images, int n_img, int H, int
       SUO_CUDA_TRY(ctx, cudaMemcpyAsync(f, prior_mask, LK, cudaMemcpyHostToDevice, s));
       d_puv = e; d_pm = f;
     }
-    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(a, images, n_im * sizeof(float), cudaMemcpyHostToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(a, images, n_im * (images_u8 ? 1 : sizeof(float)), cudaMemcpyHostToDevice, s));
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b, boxes, 4 * (size_t)L * sizeof(float), cudaMemcpyHostToDevice, s));
     SUO_CUDA_TRY(ctx, cudaMemcpyAsync(c, box_img, L * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     if (d) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d, priors, n_pr * sizeof(float), cudaMemcpyHostToDevice, s));
     d_im = a; d_box = b; d_bi = c; d_pr = d;
   }
   if (d_puv) {   // keypoint priors: RGB by roi_align, prior channels stamped straight into the NHWC input (prior.cu)
-    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, nullptr, -1, R, N.act[in_buf], N.bufs[in_buf].C, s);
+    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, nullptr, -1, R, N.act[in_buf], N.bufs[in_buf].C, s, images_u8);
     if (rc) return rc;
     rc = launch_render_priors_nhwc(ctx, d_puv, d_pm, L, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
   } else {
-    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
+    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s, images_u8);
   }
   if (rc) return rc;
   rc = run_network(ctx, L, variant, s);
@@ -1204,11 +1206,11 @@ int suo_chi2_inlier_counts(suo_ctx* ctx, int n_pairs, const double* T_pairs, con
   return SUO_OK;
 }
 
-int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
-               int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
-               const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
-               double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
-               int on_device, void* stream) {
+static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                       int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                       const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+                       double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
+                       int on_device, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
@@ -1226,7 +1228,8 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const
   rc = x->fr.grow(ctx, bytes);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->fr.d)};
-  const float *d_im = images, *d_box = boxes, *d_pr = priors;
+  const void* d_im = images;
+  const float *d_box = boxes, *d_pr = priors;
   const int32_t* d_bi = box_img;
   const double *d_mk = model_kps, *d_kb = K_bbox, *d_diam = diameter;
   const uint8_t* d_mm = model_mask;
@@ -1236,15 +1239,15 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const
     float* d = priors ? bp.take<float>(n_pr) : nullptr;
     double* e = bp.take<double>(3 * LK); uint8_t* f = bp.take<uint8_t>(LK); double* g = bp.take<double>(9 * (size_t)L); double* h = bp.take<double>(L);
 #define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
-    H2D(a, images, n_im * 4); H2D(b, boxes, 16 * (size_t)L); H2D(c, box_img, 4 * (size_t)L);
+    H2D(a, images, n_im * (images_u8 ? 1 : 4)); H2D(b, boxes, 16 * (size_t)L); H2D(c, box_img, 4 * (size_t)L);
     if (d) H2D(d, priors, n_pr * 4);
     H2D(e, model_kps, 24 * LK); H2D(f, model_mask, LK); H2D(g, K_bbox, 72 * (size_t)L); H2D(h, diameter, 8 * (size_t)L);
 #undef H2D
     d_im = a; d_box = b; d_bi = c; d_pr = d; d_mk = e; d_mm = f; d_kb = g; d_diam = h;
   }
   // forward (device path): results land in the executor's own uv / cov / mask buffers
-  rc = suo_forward(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, N.d_uv, N.d_cov, nullptr, nullptr, N.d_mask_logits, N.d_mask,
-                   N.d_argmax, 1, stream);
+  rc = forward_impl(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, nullptr, nullptr, N.d_uv, N.d_cov, nullptr, nullptr, N.d_mask_logits,
+                    N.d_mask, N.d_argmax, 1, stream, images_u8);
   if (rc) return rc;
   double* d_Tpnp = (on_device && T_pnp) ? T_pnp : bp.take<double>(16 * (size_t)L);
   double* d_Tba = (on_device && T_ba) ? T_ba : bp.take<double>(12 * (size_t)L);
@@ -1265,6 +1268,24 @@ int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const
 #undef D2H
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return SUO_OK;
+}
+
+int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+               int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+               const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+               double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
+               int on_device, void* stream) {
+  return frames_impl(ctx, images, 0, n_img, H, W, boxes, box_img, L, priors, model_kps, model_mask, K_bbox, diameter, kp_var_thresh,
+                     bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, on_device, stream);
+}
+
+int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
+                  int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                  const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+                  double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
+                  int on_device, void* stream) {
+  return frames_impl(ctx, images_hwc, 1, n_img, H, W, boxes, box_img, L, priors, model_kps, model_mask, K_bbox, diameter, kp_var_thresh,
+                     bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, on_device, stream);
 }
 
 // Per-op device timing of the network program (eager launches, one CUDA event pair per op) on

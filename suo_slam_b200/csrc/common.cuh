@@ -89,9 +89,9 @@ void conv_tc_host_join_f16(const uint16_t* hi, const uint16_t* lo, size_t n, flo
 int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H, int W, const float* cls_w,
                           const float* cls_b, float* pooled_scratch, float* uv, float* cov, float* prob,
                           float* mask_logits, float* mask, int32_t* argmax, cudaStream_t s);
-int launch_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes,
+int launch_crop_concat(suo_ctx* ctx, const void* images, int n_img, int H, int W, const float* boxes,
                        const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
-                       cudaStream_t s);
+                       cudaStream_t s, int images_u8 = 0);
 int launch_render_priors_planes(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int vh, int vw, int ndc,
                                 float* out, cudaStream_t s);
 int launch_render_priors_nhwc(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int R, float* out, int out_c,

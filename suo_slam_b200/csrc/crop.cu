@@ -12,7 +12,17 @@
 
 namespace {
 
-__device__ __forceinline__ float bilinear(const float* __restrict__ plane, int H, int W, float y, float x) {
+// Image taps: FP32 NCHW planes (what the reference's model(...) receives) or the camera's u8 HWC frame, converted
+// per tap exactly like the reference converts the whole frame on the host, float32(img) / 255
+// (lib/object_slam.py:1092) — same value, a quarter of the bytes over PCIe.
+template <bool U8>
+__device__ __forceinline__ float tap(const void* __restrict__ img, int H, int W, int c, int y, int x) {
+  if (U8) return __fdiv_rn((float)static_cast<const unsigned char*>(img)[((size_t)y * W + x) * 3 + c], 255.f);
+  return static_cast<const float*>(img)[((size_t)c * H + y) * W + x];
+}
+
+template <bool U8>
+__device__ __forceinline__ float bilinear(const void* __restrict__ img, int c, int H, int W, float y, float x) {
   if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) return 0.f;
   if (y <= 0.f) y = 0.f;
   if (x <= 0.f) x = 0.f;
@@ -20,8 +30,8 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ plane, int H
   if (y_low >= H - 1) { y_high = y_low = H - 1; y = (float)y_low; } else { y_high = y_low + 1; }
   if (x_low >= W - 1) { x_high = x_low = W - 1; x = (float)x_low; } else { x_high = x_low + 1; }
   const float ly = y - (float)y_low, lx = x - (float)x_low, hy = 1.f - ly, hx = 1.f - lx;
-  const float v1 = plane[y_low * W + x_low], v2 = plane[y_low * W + x_high];
-  const float v3 = plane[y_high * W + x_low], v4 = plane[y_high * W + x_high];
+  const float v1 = tap<U8>(img, H, W, c, y_low, x_low), v2 = tap<U8>(img, H, W, c, y_low, x_high);
+  const float v3 = tap<U8>(img, H, W, c, y_high, x_low), v4 = tap<U8>(img, H, W, c, y_high, x_high);
   const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
   return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
 }
@@ -29,8 +39,9 @@ __device__ __forceinline__ float bilinear(const float* __restrict__ plane, int H
 // One thread per output pixel: 3 roi-aligned colour values (+ channel 3 = prior plane 0 or 0).
 // out_c == 4 : write one float4 per pixel.  out_c == 48: write channels 0..2 only; the prior
 // planes are transposed in by prior_to_nhwc_kernel.
+template <bool U8>
 __global__ void __launch_bounds__(256)
-roi_align_kernel(const float* __restrict__ images, int H, int W, const float* __restrict__ boxes,
+roi_align_kernel(const void* __restrict__ images, int H, int W, const float* __restrict__ boxes,
                  const int32_t* __restrict__ box_img, int R, float* __restrict__ out, int out_c) {
   const int crop = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,14 +53,15 @@ roi_align_kernel(const float* __restrict__ images, int H, int W, const float* __
   const float bin_h = roi_h / (float)R, bin_w = roi_w / (float)R;
   const int grid_h = (int)ceilf(roi_h / (float)R), grid_w = (int)ceilf(roi_w / (float)R);
   const float count = fmaxf((float)(grid_h * grid_w), 1.0f);
-  const float* __restrict__ img = images + (size_t)box_img[crop] * 3 * H * W;
+  const void* __restrict__ img = U8 ? static_cast<const void*>(static_cast<const unsigned char*>(images) + (size_t)box_img[crop] * 3 * H * W)
+                                    : static_cast<const void*>(static_cast<const float*>(images) + (size_t)box_img[crop] * 3 * H * W);
   float acc[3] = {0.f, 0.f, 0.f};
   for (int iy = 0; iy < grid_h; ++iy) {
     const float y = roi_start_h + (float)ph * bin_h + ((float)iy + 0.5f) * bin_h / (float)grid_h;
     for (int ix = 0; ix < grid_w; ++ix) {
       const float x = roi_start_w + (float)pw * bin_w + ((float)ix + 0.5f) * bin_w / (float)grid_w;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) acc[c] += bilinear(img + (size_t)c * H * W, H, W, y, x);
+      for (int c = 0; c < 3; ++c) acc[c] += bilinear<U8>(img, c, H, W, y, x);
     }
   }
   float* __restrict__ o = out + ((size_t)crop * R * R + pix) * out_c;
@@ -113,16 +125,17 @@ upsample_add_kernel(const float4* __restrict__ up1, const float4* __restrict__ l
 
 }  // namespace
 
-int launch_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes,
+int launch_crop_concat(suo_ctx* ctx, const void* images, int n_img, int H, int W, const float* boxes,
                        const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
-                       cudaStream_t s) {
+                       cudaStream_t s, int images_u8) {
   (void)n_img;
   if (!(out_c == 4 || out_c == 48) || (out_c == 4 && priors) || num_kp > 45 || (R * R) % 64) {
     ctx->set_error("crop_concat: out_c must be 4 (no priors) or 48", __FILE__, __LINE__);
     return SUO_E_INVALID;
   }
   dim3 g((R * R + 255) / 256, L);
-  roi_align_kernel<<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
+  if (images_u8) roi_align_kernel<true><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
+  else roi_align_kernel<false><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
   ctx->launches++;
   if (out_c == 48 && num_kp >= 0) {   // num_kp < 0: RGB only, the caller renders the prior channels itself (prior.cu)
     dim3 g2(R * R / 64, L);

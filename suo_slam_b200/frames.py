@@ -26,13 +26,18 @@ class FramePipeline:
 
     def run(self, images, boxes, box_img, model_kps, model_mask, K_bbox, diameter, priors=None, run_ba=True):
         """Host arrays in (numpy or pinned torch CPU tensors), host numpy out.
-        images [n_img,3,H,W] f32 in [0,1]; boxes [L,4]; box_img [L] sorted; model_kps [L,K,3] f64;
+        images [n_img,3,H,W] f32 in [0,1] (what model(...) takes) or [n_img,H,W,3] uint8 (what process_view receives,
+        lib/object_slam.py:327-328; converted per tap on the GPU); boxes [L,4]; box_img [L] sorted; model_kps [L,K,3] f64;
         model_mask [L,K] bool; K_bbox [L,3,3] f64; diameter [L]."""
         ctx = self.model.context()
-        n_img, _, H, W = images.shape
+        u8 = str(images.dtype).endswith("uint8")
+        if u8:
+            n_img, H, W, _ = images.shape
+        else:
+            n_img, _, H, W = images.shape
         L, K = model_mask.shape
         c = lambda a, dt: a if (hasattr(a, "data_ptr") and not isinstance(a, np.ndarray)) else np.ascontiguousarray(a, dtype=dt)
-        images = c(images, np.float32)
+        images = c(images, np.uint8 if u8 else np.float32)
         boxes, box_img = c(boxes, np.float32), c(box_img, np.int32)
         model_kps, K_bbox, diameter = c(model_kps, np.float64), c(K_bbox, np.float64), c(diameter, np.float64)
         model_mask = np.ascontiguousarray(model_mask, dtype=np.uint8)
@@ -40,7 +45,8 @@ class FramePipeline:
         out = dict(T_pnp=np.zeros((L, 4, 4)), T_ba=np.zeros((L, 3, 4)), kp_used=np.zeros((L, K), np.uint8),
                    ba_inliers=np.zeros((L, K), np.uint8), uv=np.zeros((L, K, 2), np.float32),
                    cov=np.zeros((L, K, 2, 2), np.float32))
-        ctx.check(_lib.lib().suo_frames(
+        entry = _lib.lib().suo_frames_u8 if u8 else _lib.lib().suo_frames
+        ctx.check(entry(
             ctx.handle, _lib.ptr(images), n_img, H, W, _lib.ptr(boxes), _lib.ptr(box_img), L, _lib.ptr(pri),
             _lib.ptr(model_kps), _lib.ptr(model_mask), _lib.ptr(K_bbox), _lib.ptr(diameter),
             float(self.kp_var_thresh), float(self.bbox_thresh), int(self.seed), int(run_ba),
