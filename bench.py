@@ -69,6 +69,36 @@ def make_batch(seed0, n_frames):
                 diameter=np.asarray(diam, np.float64))
 
 
+def conv_classes(dump_path, L):
+    """Per-op table of suo_profile_network -> kernel classes (which conv_tc_persistent_kernel instance runs the op).
+    bytes = ALGORITHMIC bytes: every input, skip and output tensor of the layer once, 4 B per element, plus weights."""
+    import csv
+    names = {  # (mode, pre, res) -> (ncu class of the 128-wide instance, description, bound)
+        (1, 0, 0): ("conv_tc_persistent_kernel<128, 1, 0, 1, 1, 1>", "3x3 convs (TMA-fed A, tcgen05 fp16x3)", "tensor"),
+        (0, 0, 1): ("conv_tc_persistent_kernel<128, 0, 0, 1, 1, 2>", "1x1 convs + skip add (TMA-fed A, skip prefetched by TMA)", "hbm"),
+        (0, 1, 0): ("conv_tc_persistent_kernel<128, 0, 1, 1, 0, 3>", "1x1 convs with BN+ReLU prologue (raw FP32 by TMA)", "hbm"),
+        (0, 0, 0): ("conv_tc_persistent_kernel<128, 0, 0, 1, 0, 3>", "plain 1x1 convs", "hbm"),
+        (2, 0, 0): ("conv_tc_persistent_kernel<64, 2, 0, 1, 0, 1>", "7x7/2 stem", "hbm"),
+    }
+    out = {}
+    for r in csv.DictReader(open(dump_path)):
+        if int(r["type"]) != 0:
+            continue
+        key = (int(r["mode"]), int(r["pre"]), int(r["res"]))
+        ncu, desc, bound = names.get(key, ("conv_tc_persistent_kernel", "other convs", "hbm"))
+        side, cin, cout, K = int(r["side_out"]), int(r["Cin"]), int(r["Cout"]), int(r["K"])
+        px = L * side * side
+        px_in = px * 4 if key[0] == 2 else px
+        b = 4.0 * (px_in * cin + px * cout * (2 if key[2] else 1)) + 4.0 * K * cout
+        c = out.setdefault(desc, dict(name=f"{ncu}: {desc}", ncu_class=ncu, bound=bound, n=0, ms=0.0, gflop=0.0, bytes=0.0))
+        c["n"] += 1; c["ms"] += float(r["ms"]); c["gflop"] += float(r["gflop"]); c["bytes"] += b
+    try:
+        os.remove(dump_path)
+    except OSError:
+        pass
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -263,11 +293,16 @@ def run_native(args):
     ms_e2e, _ = timed(False, sets_pin, outs_host, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # roofline of the dominant kernel (tcgen05 conv engine): per-op events over the network program
+    # roofline: per-op CUDA events over the network program (eager launches on `stream`, after the timed region);
+    # the per-op table is dumped and grouped into kernel classes below
     import ctypes as C
+    import tempfile
     conv_ms, other_ms = C.c_float(0), C.c_float(0)
+    dump_path = os.path.join(tempfile.gettempdir(), f"suo_per_op_{os.getpid()}.csv")
+    os.environ["SUO_PROFILE_DUMP"] = dump_path
     ctx.check(lib.suo_profile_network(hdl, L, 0, 2, C.byref(conv_ms), C.byref(other_ms), sp))
     torch.cuda.synchronize(dev)
+    os.environ.pop("SUO_PROFILE_DUMP", None)
 
     if rank == 0:
         frames_total = F * world * args.steps
@@ -286,7 +321,16 @@ def run_native(args):
             tr = json.load(open(tr_path))
             if int(tr.get("crops_per_step", -1)) == L:
                 traffic = float(tr["conv_dram_bytes_per_step"])
-        achieved = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
+        achieved_all = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
+        classes = conv_classes(dump_path, L)
+        dom = max(classes.values(), key=lambda c: c["ms"])                     # the kernel with the largest share of the step
+        hbm_cls = max((c for c in classes.values() if c["bound"] == "hbm"), key=lambda c: c["ms"])
+        peak_bw = float(peaks.get("hbm_gbs", 6500.0))
+        tr_cls = (tr.get("classes", {}) if traffic is not None else {})
+
+        def cls_traffic(c):     # per-launch DRAM bytes of that kernel from the committed ncu launch list
+            t = tr_cls.get(c["ncu_class"])
+            return None if not t else t["dram_bytes"] / t["launches"]
         h2d = sum(v.numel() * v.element_size() for v in sets_pin[0].values())
         d2h = sum(v.numel() * v.element_size() for v in outs_host.values())
         if args.conv_math == "fp16x3":
@@ -310,14 +354,22 @@ def run_native(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": traffic, "traffic_unit": "bytes per step, DRAM read+write summed over the conv launches (ncu); algorithmic unfused bound 327.9 MB/crop",
-                         "kernel": "conv_tc_persistent_kernel (the 187 conv launches of one forward, all template instances)",
+            "roofline": {"bound": "tensor", "kernel": dom["name"], "launches_per_step": dom["n"], "share_of_step": dom["ms"] / (ms_dev / args.steps),
+                         "achieved": dom["gflop"] / dom["ms"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["gflop"] / dom["ms"] / peak_tf,
+                         "mma_achieved": 3 * dom["gflop"] / dom["ms"], "mma_frac": 3 * dom["gflop"] / dom["ms"] / peak_tf,
+                         "traffic": cls_traffic(dom), "algorithmic_bytes": dom["bytes"] / dom["n"],
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-                         "note": "algorithmic 31.495 GFLOP/crop x crops / summed conv-kernel time (CUDA events per launch, eager pass after the timed region); "
-                                 "each FP32-equivalent product costs 3 f16-kind MMAs (fp16x3), so tensor-pipe work is 3x the algorithmic FLOPs and the ceiling of frac is 1/3; "
-                                 "the 3x3 layers (68 % of the FLOPs) run at ~430 TFLOP/s algorithmic = 0.93 of that ceiling, the 1x1 layers are HBM-bound (5.3-5.9 TB/s, profiles/)",
-                         "conv_ms_per_step": conv_ms.value, "other_net_ms_per_step": other_ms.value},
+                         "note": "achieved = algorithmic FLOPs of these launches (2*M*N*K per conv, summing to 31.495 GFLOP/crop over the net) / their summed duration "
+                                 "(CUDA events per launch); the reference computes in FP32 and tcgen05 has no FP32 MMA, so each product is 3 f16-kind MMAs (fp16x3 split): "
+                                 "mma_achieved = 3 x achieved is what the tensor pipe executes, the ceiling of frac is 1/3; traffic / algorithmic_bytes are per launch (average)"},
+            "roofline_hbm": {"bound": "hbm", "kernel": hbm_cls["name"], "launches_per_step": hbm_cls["n"], "share_of_step": hbm_cls["ms"] / (ms_dev / args.steps),
+                             "achieved": hbm_cls["bytes"] / hbm_cls["ms"] * 1e-6, "peak": peak_bw, "unit": "GB/s",
+                             "frac": hbm_cls["bytes"] / hbm_cls["ms"] * 1e-6 / peak_bw, "traffic": cls_traffic(hbm_cls), "algorithmic_bytes": hbm_cls["bytes"] / hbm_cls["n"],
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6500 (of fallback)"},
+            "conv_engine": {"achieved_all_convs": achieved_all, "unit": "TFLOP/s", "frac": achieved_all / peak_tf, "conv_ms_per_step": conv_ms.value,
+                            "other_net_ms_per_step": other_ms.value, "dram_bytes_per_step": traffic,
+                            "classes": {k: {"n": c["n"], "ms": round(c["ms"], 4), "TFLOP/s": round(c["gflop"] / c["ms"], 1),
+                                            "GB/s": round(c["bytes"] / c["ms"] * 1e-6, 1), "bound": c["bound"]} for k, c in classes.items()}},
         }
         if not args.no_cpu_baseline and world == 1:
             cfps, n, cores, _ = cpu_reference_frames_per_s(args.cpu_baseline_seconds)
