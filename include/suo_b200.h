@@ -41,8 +41,10 @@ enum {
   SUO_OPT_USE_GRAPH = 3,    /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
   SUO_OPT_CONV_PERSISTENT = 4, /* 1 = persistent tcgen05 conv kernel with overlapped epilogue (default), 0 = one tile per CTA */
   SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
-  SUO_OPT_CONV_MATH = 6        /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
+  SUO_OPT_CONV_MATH = 6,       /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
                                   0 = TF32 split (SUO_OPT_TF32_PASSES) */
+  SUO_OPT_CONV_FUSE = 7        /* 1 = conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel;
+                                   0 (default) = two kernels. Results are identical either way. */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

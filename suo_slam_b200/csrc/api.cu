@@ -98,12 +98,13 @@ struct NetState {
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
   std::vector<std::array<unsigned char, 768>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip CUtensorMaps (split mode)
   std::vector<int> epi_ok, raw_ok;                      // per op: the output / skip maps, the FP32 input map are valid
+  std::vector<int> fuse_next;                           // per op: 1 = this 3x3 conv and the next op (1x1 + skip) can run as one fused kernel
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi, math; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi, math) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -178,6 +179,58 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   if (p.raw_tma) memcpy(p.tmap_raw, tm + 640, 128);
 }
 
+// true when op i (3x3, 128 -> 128) and op i+1 (1x1, 128 -> 256, + skip) run as ONE kernel under the current options
+bool op_fused(suo_ctx* ctx, const NetState& N, size_t i, int backend, int passes) {
+  return backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && passes == 3 && ctx->opt_epi_tma && ctx->opt_fuse &&
+         i < N.fuse_next.size() && N.fuse_next[i];
+}
+
+int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t st) {
+  const OpDesc& o2 = N.ops[i];
+  const OpDesc& o3 = N.ops[i + 1];
+  FusedParams f{};
+  memcpy(f.tmap_hi, N.tmaps[i].data(), 128);
+  memcpy(f.tmap_lo, N.tmaps[i].data() + 128, 128);
+  memcpy(f.tmap_out, N.tmaps[i + 1].data() + 256, 128);
+  f.w2 = N.packed16[i]; f.w3 = N.packed16[i + 1];
+  f.bias2 = N.pool + o2.b_off; f.bias3 = N.pool + o3.b_off;
+  f.skip = N.act[o3.res];
+  f.B = L; f.H = ctx->crop_res / N.bufs[o2.in].div; f.W = f.H;
+  f.range_flag = N.range_flag;
+  f.dbg = nullptr;
+  // developer tool: SUO_FUSED_TIMELINE=<csv> dumps the clock64 timeline of CTA 0 for the first fused launch of the process
+  static bool dumped = false;
+  const char* tl = getenv("SUO_FUSED_TIMELINE");
+  if (tl && !dumped) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap == cudaStreamCaptureStatusNone) {
+      dumped = true;
+      long long* d = nullptr;
+      SUO_CUDA_TRY(ctx, cudaMalloc(&d, 13 * 64 * sizeof(long long)));
+      SUO_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 13 * 64 * sizeof(long long), st));
+      f.dbg = d;
+      int rc = launch_conv_fused23(ctx, f, st);
+      if (rc) return rc;
+      std::vector<long long> h(13 * 64);
+      SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+      SUO_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+      cudaFree(d);
+      if (FILE* fp = fopen(tl, "w")) {
+        fprintf(fp, "tile,mma_start,mma_conv2_issued,mma_a3_ready,mma_h0_issued,mma_early_issued,mma_h1_start,mma_h1_issued,epi_acc2_full,epi_a3_done,epi_h0_full,epi_h0_done,epi_h1_full,epi_h1_done\n");
+        for (int i = 0; i < 64 && h[i]; ++i) {
+          fprintf(fp, "%d", i);
+          for (int r = 0; r < 13; ++r) fprintf(fp, ",%lld", h[r * 64 + i] - h[0]);
+          fprintf(fp, "\n");
+        }
+        fclose(fp);
+      }
+      return SUO_OK;
+    }
+  }
+  return launch_conv_fused23(ctx, f, st);
+}
+
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int R = ctx->crop_res;
@@ -209,7 +262,14 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
       }
     }
     int rc = SUO_OK;
-    if (o.type == OP_CONV) {
+    const bool fused = o.type == OP_CONV && op_fused(ctx, N, i, backend, passes);
+    if (fused) {
+      if (multi) {      // the pair's skip tensor may come from another level stream
+        const int b = N.ops[i + 1].res;
+        if (b >= 0 && writer[b] >= 0 && level_of(N.ops[writer[b]]) != lvl) SUO_CUDA_TRY(ctx, cudaStreamWaitEvent(st, N.op_done[writer[b]], 0));
+      }
+      rc = launch_fused_pair(ctx, N, i, L, st);
+    } else if (o.type == OP_CONV) {
       ConvParams p{};
       fill_conv_params(ctx, N, i, L, backend, passes, p);
       rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
@@ -223,14 +283,16 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
     }
     if (rc != SUO_OK) return rc;
     writer[o.out] = (int)i;
+    if (fused) { ++i; writer[N.ops[i].out] = (int)i; }      // the 1x1 of the pair ran inside the same kernel
     if (multi) {
       // record completion if a later op on another level stream consumes this output
+      const int produced = N.ops[i].out;
       bool cross = false;
       for (size_t k = i + 1; k < N.ops.size() && !cross; ++k) {
         const OpDesc& c = N.ops[k];
         if (c.variant != 2 && c.variant != variant) continue;
-        if ((c.in == o.out || c.res == o.out) && level_of(c) != lvl) cross = true;
-        if (c.out == o.out) break;
+        if ((c.in == produced || c.res == produced) && level_of(c) != lvl) cross = true;
+        if (c.out == produced) break;
       }
       if (cross) SUO_CUDA_TRY(ctx, cudaEventRecord(N.op_done[i], st));
     }
@@ -242,7 +304,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -273,7 +335,12 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   SUO_CUDA_TRY(ctx, cudaGraphLaunch(it->second, s));
   // count the kernels the graph replays
   long long n = 0;
-  for (const OpDesc& o : N.ops) if (o.variant == 2 || o.variant == variant) ++n;
+  for (size_t i = 0; i < N.ops.size(); ++i) {
+    const OpDesc& o = N.ops[i];
+    if (o.variant != 2 && o.variant != variant) continue;
+    ++n;
+    if (o.type == OP_CONV && op_fused(ctx, N, i, backend, passes)) ++i;    // the pair is one launch
+  }
   ctx->launches += n;
   return SUO_OK;
 }
@@ -306,6 +373,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
@@ -369,6 +437,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
+    case SUO_OPT_CONV_FUSE: ctx->opt_fuse = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -465,6 +534,22 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
       if (rc2) return rc2;
       N.raw_ok[i] = 1;
     }
+  }
+  // bottleneck tails that can run as one kernel (conv_fused.cu): op i = 3x3 128 -> 128 with ReLU on FP16-plane tensors,
+  // op i+1 = the 1x1 128 -> 256 that adds the skip tensor, and nothing else reads op i's output
+  N.fuse_next.assign(N.ops.size(), 0);
+  for (size_t i = 0; i + 1 < N.ops.size(); ++i) {
+    const OpDesc& a = N.ops[i];
+    const OpDesc& c = N.ops[i + 1];
+    if (a.type != OP_CONV || c.type != OP_CONV || a.variant != 2 || c.variant != 2) continue;
+    if (a.mode != CONV_3x3 || a.Cin != 128 || a.Cout != 128 || a.Cout_pad != 128 || !a.relu || a.res >= 0 || a.pre_off >= 0 || a.out_nchw) continue;
+    if (N.bufs[a.in].kind != 1 || N.bufs[a.in].C != 128 || N.bufs[a.out].kind != 1 || N.bufs[a.out].C != 128) continue;
+    if (c.mode != CONV_1x1 || c.in != a.out || c.Cin != 128 || c.Cout != 256 || c.Cout_pad != 256 || c.K != 128 || c.relu || c.res < 0 ||
+        c.pre_off >= 0 || c.out_nchw || N.bufs[c.out].kind != 0 || N.bufs[c.out].C != 256 || N.bufs[c.res].C != 256 || N.bufs[c.res].kind != 0) continue;
+    if (N.bufs[c.out].div != N.bufs[a.in].div || N.bufs[c.res].div != N.bufs[a.in].div || !N.epi_ok[i + 1] || !N.packed16[i] || !N.packed16[i + 1]) continue;
+    bool other_reader = false;
+    for (size_t k = 0; k < N.ops.size(); ++k) if (k != i + 1 && (N.ops[k].in == a.out || N.ops[k].res == a.out)) other_reader = true;
+    if (!other_reader) N.fuse_next[i] = 1;
   }
   const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
@@ -1312,7 +1397,11 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       const OpDesc& o = N.ops[idx[q]];
       const BufDesc& bi = N.bufs[o.in];
       const BufDesc& bo = N.bufs[o.out];
-      if (o.type == OP_CONV) {
+      if (q > 0 && N.ops[idx[q - 1]].type == OP_CONV && idx[q] == idx[q - 1] + 1 && op_fused(ctx, N, idx[q - 1], ctx->opt_backend, ctx->opt_passes)) {
+        rc = SUO_OK;                                      // ran inside the previous op's fused kernel
+      } else if (o.type == OP_CONV && op_fused(ctx, N, idx[q], ctx->opt_backend, ctx->opt_passes)) {
+        rc = launch_fused_pair(ctx, N, idx[q], L, s);
+      } else if (o.type == OP_CONV) {
         ConvParams p{};
         fill_conv_params(ctx, N, idx[q], L, ctx->opt_backend, ctx->opt_passes, p);
         rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
@@ -1335,9 +1424,14 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       (o.type == OP_CONV ? conv : other) += ms;
       if (dump) {
         const int side = R / N.bufs[o.out].div;
-        const double gf = o.type == OP_CONV ? 2.0 * L * side * side * (double)o.Cout_pad * o.K * 1e-9 : 0.0;
-        fprintf(dump, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", idx[q], o.type, o.mode, side, o.Cin, o.Cout, o.K, o.relu,
-                o.res >= 0, o.pre_off >= 0, ms, gf);
+        double gf = o.type == OP_CONV ? 2.0 * L * side * side * (double)o.Cout_pad * o.K * 1e-9 : 0.0;
+        const bool fused_head = o.type == OP_CONV && op_fused(ctx, N, idx[q], ctx->opt_backend, ctx->opt_passes);
+        const bool fused_tail = q > 0 && N.ops[idx[q - 1]].type == OP_CONV && idx[q] == idx[q - 1] + 1 && op_fused(ctx, N, idx[q - 1], ctx->opt_backend, ctx->opt_passes);
+        if (fused_tail) continue;                         // accounted for in the head's row
+        if (fused_head) { const OpDesc& c = N.ops[idx[q] + 1]; gf += 2.0 * L * side * side * (double)c.Cout_pad * c.K * 1e-9; }
+        // mode 3 = fused 3x3 + 1x1 + skip (Cout = the pair's output channels)
+        fprintf(dump, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", idx[q], o.type, fused_head ? 3 : o.mode, side, o.Cin,
+                fused_head ? N.ops[idx[q] + 1].Cout : o.Cout, o.K, o.relu, fused_head ? 1 : (o.res >= 0), o.pre_off >= 0, ms, gf);
       }
     }
     if (dump) fclose(dump);

@@ -74,7 +74,23 @@ struct ConvParams {
   alignas(64) unsigned char tmap_raw[128];     // FP32 input [rows, Cin], box 128 rows x 32 floats
 };
 
+// conv2 (3x3, 128 -> 128, ReLU) + conv3 (1x1, 128 -> 256, + skip) of one bottleneck as a single kernel (conv_fused.cu)
+struct FusedParams {
+  alignas(64) unsigned char tmap_hi[128];   // conv2 input, FP16 hi plane [B,H,W,128], box = one 128-pixel tile x 64 channels
+  alignas(64) unsigned char tmap_lo[128];   // lo' plane
+  alignas(64) unsigned char tmap_out[128];  // FP32 output [rows, 256], box 32 rows x 32 floats
+  const uint16_t* w2;                       // conv2 FP16x3 weight images (18 chunks x [hi | lo'])
+  const uint16_t* w3;                       // conv3 FP16x3 weight images ((half, chunk) x [hi | lo'])
+  const float* bias2;                       // [128]
+  const float* bias3;                       // [256]
+  const float* skip;                        // FP32 [rows, 256]
+  int B, H, W;
+  int* range_flag;
+  long long* dbg;                           // developer tool (SUO_FUSED_TIMELINE): [13][64] clock64 stamps of CTA 0, else nullptr
+};
+
 struct suo_ctx;
+int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);
 int launch_conv_simt(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
 int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s);
 // host-side packing of canonical [Cout_pad][K] weights into the tcgen05 smem images
@@ -135,6 +151,7 @@ struct suo_ctx {
   std::string err;
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
+  int opt_fuse = 0;     // 1 = run conv2 + conv3 of the 128-wide bottlenecks as one kernel (conv_fused.cu); SUO_FUSE=1 / SUO_OPT_CONV_FUSE turns it on
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
   int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
