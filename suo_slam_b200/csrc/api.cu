@@ -76,6 +76,25 @@ int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size
   memcpy(out128, &m, 128);
   return SUO_OK;
 }
+// CUtensorMap over the FP16x3 weight images of a layer viewed as rows of 64 halfs (128 B): box = 64 rows, NO swizzle —
+// the images are stored pre-swizzled, the copy must be verbatim.  Used by the CTA-pair kernel, where each CTA fetches
+// half of the rows of every image and the bytes complete on the leader CTA's mbarrier (conv_pair.cu).
+int make_weight_tmap(suo_ctx* ctx, void* out128, const uint16_t* base, size_t halfs) {
+  if (halfs % 64 || (reinterpret_cast<uintptr_t>(base) & 127)) { ctx->set_error("make_weight_tmap: images not 128-byte aligned", __FILE__, __LINE__); return SUO_E_INVALID; }
+  int rc = make_plane_tmap(ctx, nullptr, nullptr, 0, 0, 0, 0);   // resolves the driver entry point
+  if (rc) return rc;
+  CUtensorMap m;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)(halfs / 64)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled (weights) failed: " + std::to_string((int)r), __FILE__, __LINE__); return SUO_E_CUDA; }
+  memcpy(out128, &m, 128);
+  return SUO_OK;
+}
 enum OpType : int32_t { OP_CONV = 0, OP_MAXPOOL = 1, OP_UPADD = 2 };
 
 struct BlobHeader {
@@ -96,15 +115,15 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
-  std::vector<std::array<unsigned char, 768>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip CUtensorMaps (split mode)
-  std::vector<int> epi_ok, raw_ok;                      // per op: the output / skip maps, the FP32 input map are valid
+  std::vector<std::array<unsigned char, 896>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip / raw input / weight-image CUtensorMaps (split mode)
+  std::vector<int> epi_ok, raw_ok, wmap_ok;             // per op: the output / skip maps, the FP32 input map, the weight-image map are valid
   std::vector<int> fuse_next;                           // per op: 1 = this 3x3 conv and the next op (1x1 + skip) can run as one fused kernel
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -177,6 +196,8 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   p.raw_tma = p.epi_tma && ctx->opt_raw_tma && N.raw_ok[i] && !p.in_split;
   if (const char* e = getenv("SUO_RAW_ONLY_OP")) { if (atoi(e) >= 0 && atoi(e) != (int)i) p.raw_tma = 0; }   // developer bisect switch
   if (p.raw_tma) memcpy(p.tmap_raw, tm + 640, 128);
+  p.pair = p.epi_tma && ctx->opt_pair && N.wmap_ok[i];
+  if (p.pair) memcpy(p.tmap_w, tm + 768, 128);
 }
 
 // true when op i (3x3, 128 -> 128) and op i+1 (1x1, 128 -> 256, + skip) run as ONE kernel under the current options
@@ -304,7 +325,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -374,6 +395,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
@@ -438,6 +460,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
     case SUO_OPT_CONV_FUSE: ctx->opt_fuse = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -500,9 +523,15 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   N.tmaps.resize(N.ops.size());
   N.epi_ok.assign(N.ops.size(), 0);
   N.raw_ok.assign(N.ops.size(), 0);
+  N.wmap_ok.assign(N.ops.size(), 0);
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.type != OP_CONV) continue;
+    if (o.mode == CONV_3x3 && o.Cout_pad == 128 && N.packed16[i]) {      // weight images by TMA for the CTA-pair kernel
+      int rcw = make_weight_tmap(ctx, N.tmaps[i].data() + 768, N.packed16[i], conv_tc_packed16_halfs(o.Cout_pad, o.K));
+      if (rcw) return rcw;
+      N.wmap_ok[i] = 1;
+    }
     if (N.bufs[o.in].kind == 1) {
       const int side = R / N.bufs[o.in].div, C = N.bufs[o.in].C;
       const uint16_t* base = reinterpret_cast<const uint16_t*>(N.act[o.in]);
@@ -704,6 +733,9 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   p.out = d_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Ho = Ho; p.Wo = Wo; p.Cout = Cout; p.Cout_pad = Cout_pad;
   p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
   // backend 2..5: tcgen05 FP16x3; 3/5 feed A by TMA from pre-split FP16 planes, 4/5 write the output as FP16 planes
+  // backend 6 = 5 through the CTA-pair kernel (3x3, Cout = 128 only; other shapes run exactly as backend 5)
+  const bool want_pair = backend == 6;
+  if (backend == 6) backend = 5;
   const bool tma_in = backend == 3 || backend == 5, split_out = backend == 4 || backend == 5;
   p.math = backend >= 2 ? 1 : 0; p.w_packed16 = d_wp16; p.range_flag = d_flag;
   if (backend >= 2) backend = 1;
@@ -737,6 +769,11 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
     }
     if (r2) { if (d_in16) cudaFree(d_in16); return r2; }
     p.epi_tma = 1;
+    if (want_pair && p.mode == CONV_3x3 && Cout_pad == 128 && d_wp16) {
+      r2 = make_weight_tmap(ctx, p.tmap_w, d_wp16, wp16.size());
+      if (r2) { if (d_in16) cudaFree(d_in16); return r2; }
+      p.pair = 1;
+    }
   }
   long long* d_dbg = nullptr;
   const char* dbg_path = getenv("SUO_CONV_TIMELINE");

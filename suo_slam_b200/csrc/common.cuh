@@ -72,6 +72,8 @@ struct ConvParams {
   unsigned long long* trace;  // developer tool (SUO_TRACE): [0] = launch counter, then {globaltimer start, end, grid, smid} per persistent conv launch
   int raw_tma;            // tmap_raw is valid: a register-fed 1x1 conv may fetch its FP32 input by TMA (plan 3)
   alignas(64) unsigned char tmap_raw[128];     // FP32 input [rows, Cin], box 128 rows x 32 floats
+  int pair;               // tmap_w is valid and the CTA-pair kernel (conv_pair.cu) may run this layer
+  alignas(64) unsigned char tmap_w[128];       // FP16x3 weight images as rows of 64 halfs (128 B), box 64 rows, no swizzle (the images are pre-swizzled)
 };
 
 // conv2 (3x3, 128 -> 128, ReLU) + conv3 (1x1, 128 -> 256, + skip) of one bottleneck as a single kernel (conv_fused.cu)
@@ -91,6 +93,9 @@ struct FusedParams {
 
 struct suo_ctx;
 int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);
+// 3x3 conv as a CTA pair (tcgen05.mma.cta_group::2, conv_pair.cu): eligibility test and launch
+bool conv_pair_eligible(const ConvParams& p, int passes);
+int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
 int launch_conv_simt(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
 int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s);
 // host-side packing of canonical [Cout_pad][K] weights into the tcgen05 smem images
@@ -152,6 +157,7 @@ struct suo_ctx {
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
   int opt_fuse = 0;     // 1 = run conv2 + conv3 of the 128-wide bottlenecks as one kernel (conv_fused.cu); SUO_FUSE=1 / SUO_OPT_CONV_FUSE turns it on
+  int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
   int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA

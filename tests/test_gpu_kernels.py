@@ -77,6 +77,36 @@ def test_conv_engine_vs_fp64_reference(gpu_ctx, case, backend, passes, tol):
     assert err < tol, f"rel-to-max error {err:.3e} (backend {backend}, passes {passes})"
 
 
+PAIR_CASES = [
+    # B, H, W, Cin — 3x3, Cout = 128, ReLU, FP16-plane input and output (the bottleneck's conv2)
+    (2, 16, 16, 128),     # 4 tiles = 2 pair tiles
+    (24, 32, 32, 128),    # 192 tiles: several pair tiles per cluster (ring wrap, both accumulators recycled)
+    (3, 64, 64, 128),     # tile = 2 image rows of 64
+    (5, 8, 8, 128),       # 2.5 tiles: odd tile count, the last tile half outside the tensor
+    (3, 4, 4, 128),       # M = 48: the second CTA of the only pair has no pixels at all
+    (2, 16, 16, 64),      # one K chunk per tap
+    (1, 128, 128, 128),   # tile = one image row
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_pair_kernel_equals_single_cta_kernel(gpu_ctx, case):
+    """csrc/conv_pair.cu (two CTAs, one tcgen05.mma.cta_group::2 of M = 256, each CTA loads half of the weight rows) forms the
+    same products in the same order as the single-CTA kernel: outputs must be IDENTICAL, and right against FP64."""
+    B, H, W, Cin = case
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    x = rng.normal(size=(B, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(size=(128, 3, 3, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.normal(size=128).astype(np.float32)
+    n0 = gpu_ctx.kernel_launches()
+    pair = pkpnet.conv2d(gpu_ctx, x, w, b, 3, 1, None, None, True, backend=6)
+    single = pkpnet.conv2d(gpu_ctx, x, w, b, 3, 1, None, None, True, backend=5)
+    assert gpu_ctx.kernel_launches() - n0 == 2
+    assert np.array_equal(pair, single)
+    ref = _conv_ref(x, w, b, 3, 1, None, None, True)
+    assert np.abs(pair - ref).max() / np.abs(ref).max() < 8e-6
+
+
 def test_heatmap_reduce_vs_reference_golden(gpu_ctx, golden_dir):
     g = np.load(f"{golden_dir}/reduce.npz")
     out = pkpnet.heatmap_reduce(gpu_ctx, g["logits"])

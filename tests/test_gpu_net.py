@@ -223,3 +223,21 @@ def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, monkeypatc
     lr = ref["prob_logits"].numpy()
     err = np.abs(outs[1][0]["prob_logits"].cpu().numpy() - lr).max()
     assert err < 5e-4 * max(1.0, np.abs(lr).max() / 10), err
+
+
+def test_cta_pair_conv_kernel_equals_single_cta_kernels(sd):
+    """The 3x3 convs as CTA pairs (csrc/conv_pair.cu, the default) vs one CTA per tile: identical network output."""
+    rng = np.random.default_rng(22)
+    img = torch.from_numpy(rng.random((1, 3, 240, 320), dtype=np.float32)).cuda()
+    boxes = [torch.tensor([[10.0, 20.0, 200.0, 230.0], [100.0, 5.0, 310.0, 200.0], [50.0, 50.0, 120.0, 140.0]]).cuda()]
+    m = _model(sd, 2, 3, res=256, max_crops=3)
+    outs = {}
+    for pair in (1, 0):
+        m.context().set_option(_lib.SUO_OPT_CONV_PAIR, pair)
+        n0 = m.context().kernel_launches()
+        o = m(img, boxes)
+        torch.cuda.synchronize()
+        outs[pair] = (o, m.context().kernel_launches() - n0)
+    assert outs[1][1] == outs[0][1]
+    for k in ("prob_logits", "uv", "cov", "kp_mask", "argmax"):
+        assert torch.equal(outs[1][0][k], outs[0][0][k]), k
