@@ -69,7 +69,7 @@ def make_batch(seed0, n_frames):
                 diameter=np.asarray(diam, np.float64))
 
 
-def conv_classes(dump_path, L):
+def conv_classes(dump_path, L, pair=True):
     """Per-op table of suo_profile_network -> kernel classes (which conv_tc_persistent_kernel instance runs the op).
     bytes = ALGORITHMIC bytes: every input, skip and output tensor of the layer once, 4 B per element, plus weights."""
     import csv
@@ -87,6 +87,10 @@ def conv_classes(dump_path, L):
         key = (int(r["mode"]), int(r["pre"]), int(r["res"]))
         ncu, desc, bound = names.get(key, ("conv_tc_persistent_kernel", "other convs", "hbm"))
         side, cin, cout, K = int(r["side_out"]), int(r["Cin"]), int(r["Cout"]), int(r["K"])
+        if key == (1, 0, 0) and cout == 128 and pair:        # the bottleneck's conv2 runs as a CTA pair (csrc/conv_pair.cu)
+            ncu, desc = "conv3x3_pair_kernel", "3x3 convs (CTA pair: tcgen05.mma.cta_group::2 of M = 256, TMA-fed, fp16x3)"
+        elif key == (3, 0, 1):                               # SUO_FUSE: conv2 + conv3 + skip in one kernel
+            ncu, desc, bound = "conv_fused23", "fused 3x3 + 1x1 + skip (SUO_FUSE)", "tensor"
         px = L * side * side
         px_in = px * 4 if key[0] == 2 else px
         b = 4.0 * (px_in * cin + px * cout * (2 if key[2] else 1)) + 4.0 * K * cout
@@ -322,7 +326,10 @@ def run_native(args):
             if int(tr.get("crops_per_step", -1)) == L:
                 traffic = float(tr["conv_dram_bytes_per_step"])
         achieved_all = GFLOP_PER_CROP * L / max(conv_ms.value, 1e-6)          # GFLOP / ms == TFLOP/s
-        classes = conv_classes(dump_path, L)
+        if os.environ.get("SUO_BENCH_PER_OP"):            # keep the per-op table (profiles/)
+            import shutil
+            shutil.copy(dump_path, os.environ["SUO_BENCH_PER_OP"])
+        classes = conv_classes(dump_path, L, pair=os.environ.get("SUO_PAIR", "1") != "0")
         dom = max(classes.values(), key=lambda c: c["ms"])                     # the kernel with the largest share of the step
         hbm_cls = max((c for c in classes.values() if c["bound"] == "hbm"), key=lambda c: c["ms"])
         peak_bw = float(peaks.get("hbm_gbs", 6500.0))

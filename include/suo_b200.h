@@ -43,8 +43,8 @@ enum {
   SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
   SUO_OPT_CONV_MATH = 6,       /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
                                   0 = TF32 split (SUO_OPT_TF32_PASSES) */
-  SUO_OPT_CONV_FUSE = 7,       /* 1 = conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel;
-                                   0 (default) = two kernels. Results are identical either way. */
+  SUO_OPT_CONV_FUSE = 7,       /* conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel: 1 = single-CTA
+                                   kernel, 2 = CTA-pair kernel (tcgen05.mma.cta_group::2); 0 = two kernels. Results are identical. */
   SUO_OPT_CONV_PAIR = 8        /* 1 (default) = 3x3 convs on FP16-plane tensors run as CTA pairs (tcgen05.mma.cta_group::2: each CTA of
                                    a 2-CTA cluster loads half of the weight rows); 0 = one CTA per tile. Results are identical. */
 };

@@ -214,6 +214,16 @@ int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t s
   memcpy(f.tmap_lo, N.tmaps[i].data() + 128, 128);
   memcpy(f.tmap_out, N.tmaps[i + 1].data() + 256, 128);
   f.w2 = N.packed16[i]; f.w3 = N.packed16[i + 1];
+  const bool as_pair = ctx->opt_fuse == 2 && N.wmap_ok[i] && N.wmap_ok[i + 1];
+  if (as_pair) { memcpy(f.tmap_w2, N.tmaps[i].data() + 768, 128); memcpy(f.tmap_w3, N.tmaps[i + 1].data() + 768, 128); }
+  {
+    const int side = ctx->crop_res / N.bufs[o2.in].div;
+    f.in_hi = reinterpret_cast<const uint16_t*>(N.act[o2.in]);
+    f.in_lo = f.in_hi + (size_t)ctx->max_crops * side * side * N.bufs[o2.in].C;
+    static const int pf = getenv("SUO_FUSE_PREFETCH") ? atoi(getenv("SUO_FUSE_PREFETCH")) : 1;
+    f.prefetch = pf;
+  }
+  auto launch = [&](const FusedParams& fp) { return as_pair ? launch_conv_fused23_pair(ctx, fp, st) : launch_conv_fused23(ctx, fp, st); };
   f.bias2 = N.pool + o2.b_off; f.bias3 = N.pool + o3.b_off;
   f.skip = N.act[o3.res];
   f.B = L; f.H = ctx->crop_res / N.bufs[o2.in].div; f.W = f.H;
@@ -228,12 +238,12 @@ int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t s
     if (cap == cudaStreamCaptureStatusNone) {
       dumped = true;
       long long* d = nullptr;
-      SUO_CUDA_TRY(ctx, cudaMalloc(&d, 13 * 64 * sizeof(long long)));
-      SUO_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 13 * 64 * sizeof(long long), st));
+      SUO_CUDA_TRY(ctx, cudaMalloc(&d, 16 * 64 * sizeof(long long)));
+      SUO_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16 * 64 * sizeof(long long), st));
       f.dbg = d;
-      int rc = launch_conv_fused23(ctx, f, st);
+      int rc = launch(f);
       if (rc) return rc;
-      std::vector<long long> h(13 * 64);
+      std::vector<long long> h(16 * 64);
       SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
       SUO_CUDA_TRY(ctx, cudaStreamSynchronize(st));
       cudaFree(d);
@@ -244,12 +254,17 @@ int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t s
           for (int r = 0; r < 13; ++r) fprintf(fp, ",%lld", h[r * 64 + i] - h[0]);
           fprintf(fp, "\n");
         }
+        // rows 13 / 14 (CTA-pair version): per conv2 chunk of tiles 3 and 4, clock when its operands had landed / when its MMAs were issued
+        if (h[13 * 64]) {
+          fprintf(fp, "# chunk,operands_landed,mmas_issued (tiles 3 and 4, relative to tile 3's first entry)\n");
+          for (int c = 0; c < 64 && h[13 * 64 + c]; ++c) fprintf(fp, "# %d,%lld,%lld\n", c, h[13 * 64 + c] - h[13 * 64], h[14 * 64 + c] - h[13 * 64]);
+        }
         fclose(fp);
       }
       return SUO_OK;
     }
   }
-  return launch_conv_fused23(ctx, f, st);
+  return launch(f);
 }
 
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
@@ -394,7 +409,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
@@ -459,7 +474,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
-    case SUO_OPT_CONV_FUSE: ctx->opt_fuse = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_CONV_FUSE: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_fuse = value; return SUO_OK;
     case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
@@ -527,7 +542,7 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.type != OP_CONV) continue;
-    if (o.mode == CONV_3x3 && o.Cout_pad == 128 && N.packed16[i]) {      // weight images by TMA for the CTA-pair kernel
+    if (o.Cout_pad % 128 == 0 && N.packed16[i]) {                        // weight images by TMA for the CTA-pair kernels
       int rcw = make_weight_tmap(ctx, N.tmaps[i].data() + 768, N.packed16[i], conv_tc_packed16_halfs(o.Cout_pad, o.K));
       if (rcw) return rcw;
       N.wmap_ok[i] = 1;

@@ -89,10 +89,16 @@ struct FusedParams {
   int B, H, W;
   int* range_flag;
   long long* dbg;                           // developer tool (SUO_FUSED_TIMELINE): [13][64] clock64 stamps of CTA 0, else nullptr
+  alignas(64) unsigned char tmap_w2[128];   // CTA-pair version (conv_fused2.cu): conv2 / conv3 weight images as rows of 64 halfs, box 64 rows
+  alignas(64) unsigned char tmap_w3[128];
+  const uint16_t* in_hi;                    // conv2 input planes (what tmap_hi / tmap_lo describe): L2 prefetch of the next tile
+  const uint16_t* in_lo;
+  int prefetch;                             // pace L2 prefetches of the next tile's HBM reads with the main loop (developer switch SUO_FUSE_PREFETCH)
 };
 
 struct suo_ctx;
 int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);
+int launch_conv_fused23_pair(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);     // the same as a CTA pair (conv_fused2.cu)
 // 3x3 conv as a CTA pair (tcgen05.mma.cta_group::2, conv_pair.cu): eligibility test and launch
 bool conv_pair_eligible(const ConvParams& p, int passes);
 int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
@@ -156,7 +162,7 @@ struct suo_ctx {
   std::string err;
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
-  int opt_fuse = 0;     // 1 = run conv2 + conv3 of the 128-wide bottlenecks as one kernel (conv_fused.cu); SUO_FUSE=1 / SUO_OPT_CONV_FUSE turns it on
+  int opt_fuse = 0;     // run conv2 + conv3 of the 128-wide bottlenecks as one kernel: 1 = single CTA (conv_fused.cu), 2 = CTA pair (conv_fused2.cu); SUO_FUSE / SUO_OPT_CONV_FUSE
   int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)

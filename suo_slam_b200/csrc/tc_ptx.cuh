@@ -61,6 +61,10 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                ::"l"(tmap), "r"(c0), "r"(c1), "r"(src) : "memory");
 }
+// contiguous global bytes -> L2 only (no shared-memory destination, no completion to wait for); addr / bytes multiples of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -198,11 +198,13 @@ def test_frame_pipeline_fused_call_vs_oracle_and_u8_frames(sd):
     assert np.array_equal(a["kp_used"][~near], ref["kp_used"][~near])
 
 
+@pytest.mark.parametrize("fuse_mode", [1, 2])
 @pytest.mark.parametrize("grid_cap", [0, 3])
-def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, monkeypatch):
+def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, fuse_mode, monkeypatch):
     """conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck as one kernel (csrc/conv_fused.cu) performs the same
     floating-point operations in the same order as the two separate kernels: the whole network output must be IDENTICAL.
-    grid_cap = 3 forces ~43+ tiles per CTA at 64x64 (software pipeline across tiles, both TMEM accumulators recycled)."""
+    grid_cap = 3 forces ~43+ tiles per CTA at 64x64 (software pipeline across tiles, both TMEM accumulators recycled).
+    fuse_mode 1 = single-CTA kernel (conv_fused.cu), 2 = CTA-pair kernel (conv_fused2.cu, tcgen05.mma.cta_group::2)."""
     if grid_cap:
         monkeypatch.setenv("SUO_GRID_CAP", str(grid_cap))
     rng = np.random.default_rng(21)
@@ -211,7 +213,7 @@ def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, monkeypatc
     m = _model(sd, 2, 3, res=256, max_crops=3)
     outs = {}
     for fuse in (1, 0):
-        m.context().set_option(_lib.SUO_OPT_CONV_FUSE, fuse)
+        m.context().set_option(_lib.SUO_OPT_CONV_FUSE, fuse_mode if fuse else 0)
         n0 = m.context().kernel_launches()
         o = m(img, boxes)
         torch.cuda.synchronize()

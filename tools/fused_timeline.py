@@ -22,7 +22,8 @@ img = torch.from_numpy(rng.random((1, 3, 480, 640), dtype=np.float32)).cuda()
 boxes = torch.tensor(np.tile([[50.0, 40.0, 400.0, 380.0]], (L, 1)).astype(np.float32)).cuda()
 m(img, [boxes])
 torch.cuda.synchronize()
-d = np.loadtxt(out, delimiter=",", skiprows=1)
+d = np.loadtxt(out, delimiter=",", skiprows=1, comments="#")
+print("".join(l for l in open(out) if l.startswith("#")))
 print("tiles", len(d))
 names = open(out).readline().strip().split(",")
 np.set_printoptions(linewidth=250, suppress=True)

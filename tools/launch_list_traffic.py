@@ -31,7 +31,7 @@ w["ms"] = w["gpu__time_duration.sum"] * scale
 w["bytes"] = (w["dram__bytes_read.sum"] + w["dram__bytes_write.sum"]) * bscale
 g = w.groupby("cls").agg(launches=("ms", "size"), ms=("ms", "sum"), dram_bytes=("bytes", "sum")).sort_values("ms", ascending=False)
 g["share_pct"] = 100 * g.ms / g.ms.sum()
-conv = g[g.index.str.startswith("conv_tc")]
+conv = g[g.index.str.startswith("conv")]
 blob = {"crops_per_step": crops, "source": src + " (ncu, one timed step; cold-cache serialised launches: shares, not absolutes)",
         "conv_dram_bytes_per_step": float(conv.dram_bytes.sum()), "conv_launches": int(conv.launches.sum()),
         "classes": {k: {"launches": int(r.launches), "ms": float(r.ms), "dram_bytes": float(r.dram_bytes), "share_pct": float(r.share_pct)}
