@@ -698,6 +698,7 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   int K, cpr = 0;
   if (p.mode == CONV_1x1) K = Cin;
   else if (p.mode == CONV_3x3) K = 9 * Cin;
+  else if (7 * Cin <= 32) { cpr = 1; K = 8 * 32; }              // RGB-only layout: one 32-float chunk per kernel row, an eighth zero row pads K to 256 (weights.py)
   else { cpr = 2 * ((7 * Cin + 63) / 64); K = 7 * cpr * 32; }   // kernel-row stride: multiple of 64 floats (both chunk widths)
   // canonical weights [Cout_pad][K] in gather order from [Cout][kh][kw][Cin]
   std::vector<float> wc((size_t)Cout_pad * K, 0.f), bc(Cout_pad, 0.f);

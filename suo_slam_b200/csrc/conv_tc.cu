@@ -893,6 +893,9 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     const int g8 = pt & 7;                      // float4 group inside the 128-byte row
     const int r0 = pt >> 3;                     // rows r0 + 32*i
     const int cpc = p.Cin / KC, cpr = p.chunks_per_row * 32 / KC;     // sub-chunks per tap / per stem kernel row
+    // RGB-only stem in FP16 chunks: a kernel row is ONE 32-float chunk (chunks_per_row == 1), so a 64-wide chunk is TWO kernel
+    // rows: slots g8 0..3 = row 2j, pixels 2 g8 and 2 g8 + 1; slots 4..7 = row 2j + 1 (row 7 does not exist: mask bit 7 is never set)
+    const bool stem2 = MODE == CONV_STEM7 && KC == 64 && p.chunks_per_row == 1;
     auto advance = [&](LoadCursor& c) {
       if (++c.j == nchunks) {      // next tile: decode out of line into a scratch copy so that `c` itself stays in registers
         LoadCursor tmp;
@@ -905,6 +908,8 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
       else if (MODE == CONV_3x3) {
         if (++c.cc == cpc) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)((c.tap / 3 - 1) * p.W + (c.tap % 3 - 1)) * p.Cin; }
         else c.off += KC;
+      } else if (stem2) {
+        c.tap += 2; c.off = (ptrdiff_t)c.tap * p.W * p.Cin;
       } else {
         if (++c.cc == cpr) { c.cc = 0; ++c.tap; c.off = (ptrdiff_t)c.tap * p.W * p.Cin; }
         else c.off += KC;
@@ -924,8 +929,11 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     auto load_chunk = [&](const LoadCursor& c, float4 (&dst)[4 * NV], uint32_t& bits) {
       // this thread's K elements of the chunk: [ (KC/8) * g8, +KC/8 ) -> one 16-byte slot of the 128-byte operand row
       uint32_t pixbit = 0;                      // stem only: which input pixel of the kernel row these elements belong to
+      int srow = 0;                             // stem2 only: 0 / 1 = first / second kernel row of the chunk
+      ptrdiff_t toff = (KC / 8) * g8;           // this thread's float offset inside the chunk's source row
       if (MODE == CONV_STEM7) {
-        const int x = KC * c.cc + (KC / 8) * g8;
+        int x = KC * c.cc + (KC / 8) * g8;
+        if (stem2) { srow = g8 >> 2; x = 8 * (g8 & 3); toff = (ptrdiff_t)srow * p.W * p.Cin + x; }
         const int pix = (p.Cin == 4) ? (x >> 2) : ((x * 1366) >> 16);   // x / Cin for Cin in {4, 48}
         pixbit = pix < 7 ? (1u << (8 + pix)) : 0u;
       }
@@ -935,15 +943,15 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
         bool ok;
         if (MODE == CONV_1x1) ok = c.mask[i] & 1u;
         else if (MODE == CONV_3x3) ok = (c.mask[i] >> c.tap) & 1u;
-        else ok = ((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pixbit);
-        const float* __restrict__ q = c.base[i] + c.off + (KC / 8) * g8;
+        else ok = ((c.mask[i] >> (c.tap + srow)) & 1u) && (c.mask[i] & pixbit);
+        const float* __restrict__ q = c.base[i] + c.off + toff;
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
           dst[i * NV + u] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (MODE == CONV_STEM7 && NV == 2 && u == 1 && p.Cin == 4) {
             // 4-float pixels: the second float4 is the NEXT pixel of the kernel row
             const uint32_t pb2 = (pixbit << 1) & 0x7F00u;
-            if (((c.mask[i] >> c.tap) & 1u) && (c.mask[i] & pb2)) dst[i * NV + u] = __ldg(reinterpret_cast<const float4*>(q) + u);
+            if (((c.mask[i] >> (c.tap + srow)) & 1u) && (c.mask[i] & pb2)) dst[i * NV + u] = __ldg(reinterpret_cast<const float4*>(q) + u);
           } else if (ok) {
             dst[i * NV + u] = __ldg(reinterpret_cast<const float4*>(q) + u);
           }
