@@ -45,6 +45,9 @@ class FramePipeline:
         out = dict(T_pnp=np.zeros((L, 4, 4)), T_ba=np.zeros((L, 3, 4)), kp_used=np.zeros((L, K), np.uint8),
                    ba_inliers=np.zeros((L, K), np.uint8), uv=np.zeros((L, K, 2), np.float32),
                    cov=np.zeros((L, K, 2, 2), np.float32))
+        if L == 0:                                  # frames without a single detection: nothing to run (process_view returns early)
+            out["kp_used"], out["ba_inliers"] = out["kp_used"].astype(bool), out["ba_inliers"].astype(bool)
+            return out
         entry = _lib.lib().suo_frames_u8 if u8 else _lib.lib().suo_frames
         ctx.check(entry(
             ctx.handle, _lib.ptr(images), n_img, H, W, _lib.ptr(boxes), _lib.ptr(box_img), L, _lib.ptr(pri),
@@ -64,11 +67,14 @@ def solve_keypoints(ctx, uv, cov, kp_mask, box_img, model_kps, model_mask, K_bbo
     uv, cov, kp_mask = c(uv, np.float32), c(cov, np.float32), c(kp_mask, np.float32)
     box_img = c(box_img, np.int32)
     L, K = kp_mask.shape
-    n_img = int(box_img.max()) + 1
+    n_img = int(box_img.max()) + 1 if L else 0
     model_kps, K_bbox, diameter = c(model_kps, np.float64), c(K_bbox, np.float64), c(diameter, np.float64)
     model_mask = c(model_mask, np.uint8)
     out = dict(T_pnp=np.zeros((L, 4, 4)), T_ba=np.zeros((L, 3, 4)), kp_used=np.zeros((L, K), np.uint8),
                ba_inliers=np.zeros((L, K), np.uint8))
+    if L == 0:
+        out["kp_used"], out["ba_inliers"] = out["kp_used"].astype(bool), out["ba_inliers"].astype(bool)
+        return out
     ctx.check(_lib.lib().suo_solve_keypoints(
         ctx.handle, _lib.ptr(uv), _lib.ptr(cov), _lib.ptr(kp_mask), _lib.ptr(box_img), n_img, L, _lib.ptr(model_kps),
         _lib.ptr(model_mask), _lib.ptr(K_bbox), _lib.ptr(diameter), float(kp_var_thresh), float(bbox_thresh), int(seed),

@@ -120,6 +120,17 @@ class PkpNet:
             pmask = torch.cat([torch.as_tensor(m).reshape(-1, self.num_kp) for _, m in prior_uv]).to(dtype=torch.uint8, device=dev).contiguous()
             assert puv.shape[0] == L and pmask.shape[0] == L
         K, HM = self.num_kp, self.input_res[0] // 4
+        if L == 0:
+            # no boxes at all: the reference's roi_align returns an empty batch and every output is an empty tensor
+            # (lib/models/pkpnet.py:93-119 on K = 0 crops); nothing to launch
+            out = {"uv": torch.empty((0, K, 2), **f32), "prob_logits": torch.empty((0, K, HM, HM), **f32),
+                   "kp_mask_logits": torch.empty((0, K), **f32), "kp_mask": torch.empty((0, K), **f32),
+                   "argmax": torch.empty((0, K), dtype=torch.int32, device=dev)}
+            if self.calc_cov:
+                out["cov"] = torch.empty((0, K, 2, 2), **f32)
+            if self.return_prob:
+                out["prob"] = torch.empty((0, K, HM, HM), **f32)
+            return out
         out = {
             "uv": torch.empty((L, K, 2), **f32),
             "prob_logits": torch.empty((L, K, HM, HM), **f32),

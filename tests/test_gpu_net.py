@@ -243,3 +243,61 @@ def test_cta_pair_conv_kernel_equals_single_cta_kernels(sd):
     assert outs[1][1] == outs[0][1]
     for k in ("prob_logits", "uv", "cov", "kp_mask", "argmax"):
         assert torch.equal(outs[1][0][k], outs[0][0][k]), k
+
+
+def test_forward_ragged_and_empty_box_lists(sd):
+    """Ragged per-image box lists (one image without any box) and a call with no boxes at all: same crops, same order as the
+    reference (torchvision roi_align over the list, lib/models/pkpnet.py:93), empty tensors when there is nothing to do."""
+    rng = np.random.default_rng(23)
+    img = torch.from_numpy(rng.random((3, 3, 96, 128), dtype=np.float32)).cuda()
+    boxes = [torch.tensor([[4.0, 6.0, 90.0, 80.0], [30.0, 10.0, 120.0, 70.0]]).cuda(), torch.zeros((0, 4)).cuda(),
+             torch.tensor([[10.0, 20.0, 60.0, 90.0]]).cuda()]
+    m = _model(sd, 2, 3, res=64, max_crops=4)
+    out = m(img, boxes)
+    torch.cuda.synchronize()
+    ref = net_oracle.pkpnet_forward(sd, img.cpu(), [b.cpu() for b in boxes], None, (64, 64))
+    lr = ref["prob_logits"].numpy()
+    assert out["prob_logits"].shape == lr.shape == (3, 41, 16, 16)
+    assert np.abs(out["prob_logits"].cpu().numpy() - lr).max() < 5e-4 * max(1.0, np.abs(lr).max() / 10)
+    assert np.abs(out["uv"].cpu().numpy() - ref["uv"].numpy()).max() < 5e-5
+    empty = m(img, [torch.zeros((0, 4)).cuda()] * 3)
+    assert empty["uv"].shape == (0, 41, 2) and empty["cov"].shape == (0, 41, 2, 2) and empty["prob_logits"].shape == (0, 41, 16, 16)
+    assert empty["uv"].device == img.device
+
+
+def test_frame_pipeline_ragged_frames(sd):
+    """Frames with different numbers of detections, one frame with none (its BA graph is empty), and a batch without any
+    detection.  A frame without detections must not disturb the others: the batch gives exactly the results of the same
+    detections with that frame removed (the RANSAC stream is keyed by the detection's index in the batch, so the comparison
+    keeps the order); an empty batch gives empty arrays."""
+    from suo_slam_b200 import frames
+    counts = [3, 0, 1, 4]
+    per_frame, imgs_u8 = [], []
+    for f, n in enumerate(counts):
+        fr = synth.make_frame(60 + f, n_obj=max(n, 1), H=120, W=160)
+        imgs_u8.append(fr["img"])
+        objs = fr["objs"][:n]
+        bb = [o["bbox"] for o in objs]
+        per_frame.append(dict(boxes=np.asarray(bb, np.float32).reshape(-1, 4), mk=np.asarray([o["model_kps"] for o in objs], np.float64).reshape(-1, 41, 3),
+                              mm=np.asarray([o["model_kps_mask"] for o in objs]).reshape(-1, 41), kb=frames.k_bbox_for(fr["K"], bb).reshape(-1, 3, 3),
+                              diam=np.asarray([o["diameter"] for o in objs], np.float64)))
+    imgs_u8 = np.stack(imgs_u8)
+    cat = lambda k: np.concatenate([p[k] for p in per_frame])
+    bi = np.concatenate([np.full(n, f, np.int32) for f, n in enumerate(counts)])
+    m = _model(sd, 2, 3, max_crops=16)
+    pipe = frames.FramePipeline(m, kp_var_thresh=0.5, bbox_thresh=0.95, seed=2)
+    full = pipe.run(imgs_u8, cat("boxes"), bi, cat("mk"), cat("mm"), cat("kb"), cat("diam"))
+    assert full["T_pnp"].shape == (sum(counts), 4, 4)
+    keep = [f for f, n in enumerate(counts) if n]
+    bi_compact = np.concatenate([np.full(counts[f], i, np.int32) for i, f in enumerate(keep)])
+    compact = pipe.run(imgs_u8[keep], cat("boxes"), bi_compact, cat("mk"), cat("mm"), cat("kb"), cat("diam"))
+    for k in ("uv", "cov", "kp_used", "T_pnp", "T_ba", "ba_inliers"):
+        assert np.array_equal(compact[k], full[k]), k
+    # the first frame alone (detection indices 0..2 in both runs): identical, i.e. frames do not leak into each other
+    p = per_frame[0]
+    alone = pipe.run(imgs_u8[:1], p["boxes"], np.zeros(counts[0], np.int32), p["mk"], p["mm"], p["kb"], p["diam"])
+    for k in ("uv", "cov", "kp_used", "T_pnp", "T_ba", "ba_inliers"):
+        assert np.array_equal(alone[k], full[k][:counts[0]]), k
+    none = pipe.run(imgs_u8, np.zeros((0, 4), np.float32), np.zeros(0, np.int32), np.zeros((0, 41, 3)), np.zeros((0, 41), bool),
+                    np.zeros((0, 3, 3)), np.zeros(0))
+    assert none["T_pnp"].shape == (0, 4, 4) and none["kp_used"].shape == (0, 41) and none["kp_used"].dtype == bool
