@@ -45,8 +45,11 @@ enum {
                                   0 = TF32 split (SUO_OPT_TF32_PASSES) */
   SUO_OPT_CONV_FUSE = 7,       /* conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel: 1 = single-CTA
                                    kernel, 2 = CTA-pair kernel (tcgen05.mma.cta_group::2); 0 = two kernels. Results are identical. */
-  SUO_OPT_CONV_PAIR = 8        /* 1 (default) = 3x3 convs on FP16-plane tensors run as CTA pairs (tcgen05.mma.cta_group::2: each CTA of
+  SUO_OPT_CONV_PAIR = 8,       /* 1 (default) = 3x3 convs on FP16-plane tensors run as CTA pairs (tcgen05.mma.cta_group::2: each CTA of
                                    a 2-CTA cluster loads half of the weight rows); 0 = one CTA per tile. Results are identical. */
+  SUO_OPT_PDL = 9              /* 1 (default) = the persistent conv kernels use programmatic dependent launch (the next kernel's CTAs are
+                                   scheduled and run their prologue while the previous kernel drains; griddepcontrol.wait before any
+                                   activation is touched); 0 = plain stream order */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

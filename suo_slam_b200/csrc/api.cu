@@ -122,8 +122,8 @@ struct NetState {
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair, o.pdl); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -340,7 +340,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair, ctx->opt_pdl};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -411,6 +411,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_PDL")) c->opt_pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
@@ -476,6 +477,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
     case SUO_OPT_CONV_FUSE: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_fuse = value; return SUO_OK;
     case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_PDL: ctx->opt_pdl = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }

@@ -164,6 +164,7 @@ struct suo_ctx {
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
   int opt_fuse = 0;     // run conv2 + conv3 of the 128-wide bottlenecks as one kernel: 1 = single CTA (conv_fused.cu), 2 = CTA pair (conv_fused2.cu); SUO_FUSE / SUO_OPT_CONV_FUSE
   int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
+  int opt_pdl = 1;      // 1 = the persistent conv kernels are launched with programmatic stream serialization (SUO_PDL / SUO_OPT_PDL)
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
   int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA

@@ -60,6 +60,16 @@ conv3x3_pair_kernel(const __grid_constant__ ConvParams p, const int num_m_tiles)
   const int M = p.B * p.Ho * p.Wo;
   const int nchunks = p.K / 64;
 
+  unsigned long long trace_slot = 0;          // developer tool (SUO_TRACE): globaltimer at the start / end of CTA 0
+  if (p.trace && threadIdx.x == 0 && blockIdx.x == 0) {
+    trace_slot = atomicAdd(p.trace, 1ull);
+    if (trace_slot < 8192) {
+      unsigned long long t; uint32_t smid;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[1 + 4 * trace_slot] = t; p.trace[1 + 4 * trace_slot + 2] = gridDim.x; p.trace[1 + 4 * trace_slot + 3] = smid;
+    }
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < P_NS; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 8); }
@@ -71,6 +81,11 @@ conv3x3_pair_kernel(const __grid_constant__ ConvParams p, const int num_m_tiles)
   cluster_sync_all();                               // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Programmatic dependent launch (SUO_OPT_PDL): every CTA of this grid is resident (grid <= #SMs, one CTA per SM), so the next
+  // conv kernel may be scheduled onto an SM the moment this kernel's CTA leaves it and run its own prologue (barriers, TMEM) there;
+  // nothing above touched an activation tensor — from here on the previous kernel must have completed and flushed.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== producer (both CTAs) =====================
@@ -208,6 +223,11 @@ conv3x3_pair_kernel(const __grid_constant__ ConvParams p, const int num_m_tiles)
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                 // no CTA leaves while the peer may still signal its barriers / read its operands
+  if (p.trace && threadIdx.x == 0 && blockIdx.x == 0 && trace_slot < 8192) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[1 + 4 * trace_slot + 1] = t;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc2(tmem_base, 512);
@@ -240,11 +260,13 @@ int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s) {
   cfg.blockDim = dim3(P_THREADS);
   cfg.dynamicSmemBytes = P_TOTAL;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ctx->opt_pdl ? 2 : 1;
   SUO_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, p, mt));
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());

@@ -420,6 +420,11 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Programmatic dependent launch (SUO_OPT_PDL): every CTA of this grid is resident (grid <= #SMs, one CTA per SM), so the next
+  // conv kernel may be scheduled onto an SM the moment this kernel's CTA leaves it and run its own prologue (barriers, TMEM) there;
+  // nothing above touched an activation tensor — from here on the previous kernel must have completed and flushed.
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== weight producer =====================
@@ -1079,7 +1084,17 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms);
-  conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI><<<grid, A_TMA ? 192 : (EPI == 3 ? P_NUM_THREADS + 32 : P_NUM_THREADS), PSmem<BN, EPI>::TOTAL, s>>>(p, passes, mt, nt);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(A_TMA ? 192 : (EPI == 3 ? P_NUM_THREADS + 32 : P_NUM_THREADS));
+  cfg.dynamicSmemBytes = PSmem<BN, EPI>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+  SUO_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI>, p, passes, mt, nt));
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
