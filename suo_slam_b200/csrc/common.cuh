@@ -97,6 +97,17 @@ struct FusedParams {
 };
 
 struct suo_ctx;
+// cudaFuncSetAttribute is per device: one flag per (kernel instance, device) so that several contexts on different GPUs of one
+// process configure each kernel on each of them.  `flags` is the launcher's own static array.
+inline bool first_use_on_device(bool (&flags)[64], int* num_sms) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (num_sms) cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, dev);
+  dev &= 63;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);
 int launch_conv_fused23_pair(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);     // the same as a CTA pair (conv_fused2.cu)
 // 3x3 conv as a CTA pair (tcgen05.mma.cta_group::2, conv_pair.cu): eligibility test and launch

@@ -304,15 +304,9 @@ conv_fused23_kernel(const __grid_constant__ FusedParams p, const int num_tiles) 
 }  // namespace
 
 int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s) {
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL));
-    int dev = 0;
-    SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
-    SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  int num_sms = 148;
+  if (first_use_on_device(configured, &num_sms)) SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused23_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_TOTAL));
   const int M = p.B * p.H * p.W;
   const int tiles = (M + FM - 1) / FM;
   const int grid = std::min(tiles, ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms);

@@ -360,15 +360,9 @@ conv_fused23_pair_kernel(const __grid_constant__ FusedParams p, const int num_m_
 }  // namespace
 
 int launch_conv_fused23_pair(suo_ctx* ctx, const FusedParams& p, cudaStream_t s) {
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused23_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_TOTAL));
-    int dev = 0;
-    SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
-    SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  int num_sms = 148;
+  if (first_use_on_device(configured, &num_sms)) SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_fused23_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_TOTAL));
   const int M = p.B * p.H * p.W;
   const int mt = (M + GM - 1) / GM, pairs = (mt + 1) / 2;
   int cap = ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms;

@@ -242,15 +242,9 @@ bool conv_pair_eligible(const ConvParams& p, int passes) {
 }
 
 int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s) {
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_TOTAL));
-    int dev = 0;
-    SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
-    SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  int num_sms = 148;
+  if (first_use_on_device(configured, &num_sms)) SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_TOTAL));
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + PM - 1) / PM, pairs = (mt + 1) / 2;
   int cap = ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms;

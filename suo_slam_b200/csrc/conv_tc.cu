@@ -1072,15 +1072,9 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
 
 template <int BN, int MODE, bool PRE, int MATH, bool A_TMA, int EPI>
 int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<BN, EPI>::TOTAL));
-    int dev = 0;
-    SUO_CUDA_TRY(ctx, cudaGetDevice(&dev));
-    SUO_CUDA_TRY(ctx, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  int num_sms = 148;
+  if (first_use_on_device(configured, &num_sms)) SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PSmem<BN, EPI>::TOTAL));
   const int M = p.B * p.Ho * p.Wo;
   const int mt = (M + BLOCK_M - 1) / BLOCK_M, nt = p.Cout_pad / BN;
   const int grid = std::min(mt * nt, ctx->opt_grid_cap > 0 ? std::min(num_sms, ctx->opt_grid_cap) : num_sms);
@@ -1137,11 +1131,8 @@ int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_
 
 template <int BN>
 int launch_bn(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
-    configured = true;
-  }
+  static bool configured[64] = {};
+  if (first_use_on_device(configured, nullptr)) SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::TOTAL));
   const int M = p.B * p.Ho * p.Wo;
   dim3 grid((M + BLOCK_M - 1) / BLOCK_M, p.Cout_pad / BN);
   conv_tc_kernel<BN><<<grid, NUM_THREADS, Smem<BN>::TOTAL, s>>>(p, passes);
