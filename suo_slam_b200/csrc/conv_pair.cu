@@ -260,7 +260,7 @@ int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->opt_pdl ? 2 : 1;
+  cfg.numAttrs = (ctx->opt_pdl && !ctx->opt_multistream) ? 2 : 1;
   SUO_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv3x3_pair_kernel, p, mt));
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());

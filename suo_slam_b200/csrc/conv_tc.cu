@@ -1087,7 +1087,7 @@ int launch_persistent_inst(suo_ctx* ctx, const ConvParams& p, int passes, cudaSt
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+  cfg.numAttrs = (ctx->opt_pdl && !ctx->opt_multistream) ? 1 : 0;      // level streams join through events: keep those launches plain
   SUO_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, conv_tc_persistent_kernel<BN, MODE, PRE, MATH, A_TMA, EPI>, p, passes, mt, nt));
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
