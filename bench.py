@@ -191,6 +191,40 @@ def cpu_reference_frames_per_s(seconds, steps=None, warmup=1):
     return 1.0 / float(np.median(times)), len(times), best_n, times
 
 
+def pose_parity(ctx, n_frames=4):
+    """BASELINE.json's "pose L2 err": the CUDA solver path (gating -> PnP -> single-view BA) against the CPU oracle on IDENTICAL
+    keypoints — the reference's own debug recipe (ground-truth projections + N(0, 0.01^2) noise, lib/object_slam.py:1131; random SPD
+    covariances, 10 % gross outliers) for n_frames x 8 objects.  The synthetic random-init network cannot place
+    keypoints, so the network stage is compared on its own outputs (tests/, smoke) and the solver stage here."""
+    from oracle import frame_oracle
+    from suo_slam_b200 import frames, synth
+    K = NUM_KP
+    uv, cov, km, mk, mm, Kb, diam, bi, tgt = [], [], [], [], [], [], [], [], []
+    for f in range(n_frames):
+        fr = synth.make_frame(100 + f, n_obj=CROPS)
+        rng = np.random.default_rng(f)
+        for o in fr["objs"]:
+            uv.append(o["uv_meas"].astype(np.float32)); cov.append(o["cov"].astype(np.float32))
+            km.append(np.where(rng.random(K) < 0.9, 0.9, 0.1).astype(np.float32))
+            mk.append(o["model_kps"]); mm.append(o["model_kps_mask"]); diam.append(o["diameter"]); bi.append(f); tgt.append(o["T_OtoC"])
+        Kb.append(frames.k_bbox_for(fr["K"], [o["bbox"] for o in fr["objs"]]))
+    uv, cov, km, mk, mm, Kb = np.stack(uv), np.stack(cov), np.stack(km), np.stack(mk), np.stack(mm), np.concatenate(Kb)
+    diam, bi = np.asarray(diam), np.asarray(bi, np.int32)
+    got = frames.solve_keypoints(ctx, uv, cov, km, bi, mk, mm, Kb, diam, seed=3)
+    ref = frame_oracle.solve_from_keypoints(uv, cov, km, mk, mm, Kb, diam, bi, seed=3)
+    acc = np.nonzero(ref["accepted"])[0]
+    rel = lambda a, b: float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+    d_pnp = [rel(got["T_pnp"][c][:3], ref["T_pnp"][c][:3]) for c in acc]
+    d_ba = [rel(got["T_ba"][c], ref["T_ba"][c]) for c in acc]
+    t_gt = [rel(got["T_ba"][c][:, 3], tgt[c][:3, 3]) for c in acc]
+    return {"objects": int(len(bi)), "accepted_by_both": int(len(acc)), "same_gating": bool(np.array_equal(got["kp_used"], ref["kp_used"])),
+            "same_ba_inliers": bool(np.array_equal(got["ba_inliers"], ref["ba_inliers"])),
+            "pnp_rel_l2_vs_oracle_max": max(d_pnp) if d_pnp else None, "ba_rel_l2_vs_oracle_max": max(d_ba) if d_ba else None,
+            "translation_rel_l2_vs_ground_truth_median": float(np.median(t_gt)) if t_gt else None,
+            "inputs": "ground-truth projections + N(0, 0.01^2) NDC noise, random SPD covariances, 10 % gross outliers (SURVEY.md §8d); "
+                      "north_star bar: 1e-4 relative"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -382,6 +416,10 @@ def run_native(args):
             cfps, n, cores, _ = cpu_reference_frames_per_s(args.cpu_baseline_seconds)
             out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
                                    "sample": f"{n} timed frames (8 crops each) of the same workload through oracle/ on the host cores"}
+            try:
+                out["pose_err"] = pose_parity(ctx)
+            except Exception as e:      # the checker must never take the bench line down
+                out["pose_err"] = {"error": repr(e)}
         else:
             out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "skipped (N>1 or --no-cpu-baseline)"}
         print(json.dumps(out))
