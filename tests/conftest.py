@@ -13,6 +13,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run by the driver with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that deadlocks a kernel must fail, not hang the run: 300 s per test (the slowest takes ~10 s) when
+    pytest-timeout is installed (it is in this image; without it the marker is inert)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(300, method="thread"))    # a hung kernel blocks inside a C call: SIGALRM would never be served
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
