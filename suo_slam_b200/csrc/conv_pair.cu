@@ -1,12 +1,14 @@
 // CTA-pair 3x3 convolution for sm_100a: the bottleneck's conv2 (3x3, pad 1, Cin -> 128, folded BN + ReLU; reference
 // lib/models/layers/Residual.py:13-15,28-31) as a cluster of two CTAs that run ONE tcgen05.mma.cta_group::2 of M = 256.
 //
-// Why: the single-CTA kernel (conv_tc.cu, <128, 3x3, TMA-fed>) is operand-feed bound, not tensor-pipe bound: every
-// 64-wide K chunk brings 32 KB of activations AND 32 KB of weight images through L2 into shared memory, a 3 x 64 KB ring
-// cannot keep that many bytes in flight over the loaded L2 latency (measured 1121 cycles per chunk against 768 cycles
-// of MMA issue; a 2-stage ring ran at 1.7k), and all 148 CTAs pull the same weight lines at the same time.  As a pair, each
-// CTA loads its own 128 pixels of A but only HALF of the weight rows (the tensor cores of both SMs read both halves),
-// so a stage is 48 KB, the ring is four deep in the same 192 KB, and the weight traffic per SM halves.
+// Why: per 64-wide K chunk the single-CTA kernel (conv_tc.cu, <128, 3x3, TMA-fed>) brings 32 KB of activations AND 32 KB of weight
+// images through L2 into shared memory, and all 148 CTAs pull the same weight lines at the same time.  As a pair, each CTA loads
+// its own 128 pixels of A but only HALF of the weight rows (the tensor cores of both SMs read both halves), so a stage is 48 KB,
+// the ring is four deep in the same 192 KB, and the L2 -> SM weight traffic halves (ncu: 14 % fewer L2 sectors per layer).
+// Measured (profiles/r1_pair_vs_single_probe_ncu.txt): 1.7 % faster on an isolated 64x64 layer, +2.2 % frames/s end to end; both
+// kernels keep the tensor pipe busy 64.8 % of the cycles (1236 cycles per chunk against ~800 of MMA) = 0.955 of the sustained
+// cuBLAS bf16 rate under the board power cap — what is left is the shared-memory traffic of the operands themselves
+// (72-80 KB read by the tensor core + 48-64 KB written by TMA per chunk against 128 B/clk), not load latency.
 //
 // Pair tile = 256 consecutive output pixels: CTA rank r owns pixels [256 t + 128 r, +128), i.e. accumulator rows
 // [128 r, +128) of the M = 256 MMA, which live in its own TMEM.  Per K chunk (64 input channels of one tap):
