@@ -117,6 +117,11 @@ struct NetState {
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
   std::vector<std::array<unsigned char, 896>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip / raw input / weight-image CUtensorMaps (split mode)
   std::vector<int> epi_ok, raw_ok, wmap_ok;             // per op: the output / skip maps, the FP32 input map, the weight-image map are valid
+  // TMA-fed stem (RGB-only layout): a second copy of the network input with a 3-pixel zero border, rows of stem_wp pixels, stem_hp rows
+  // per crop, and the 4-D tensor map of its overlapping kernel-row windows
+  float* stem_pad = nullptr;
+  int stem_wp = 0, stem_hp = 0, stem_ok = 0;
+  alignas(64) unsigned char stem_tmap[128];
   std::vector<int> fuse_next;                           // per op: 1 = this 3x3 conv and the next op (1x1 + skip) can run as one fused kernel
   std::vector<float*> act;                   // per buffer: device activation tensor
   float* pooled = nullptr;                   // [max_crops, K] channel means
@@ -196,6 +201,8 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   p.raw_tma = p.epi_tma && ctx->opt_raw_tma && N.raw_ok[i] && !p.in_split;
   if (const char* e = getenv("SUO_RAW_ONLY_OP")) { if (atoi(e) >= 0 && atoi(e) != (int)i) p.raw_tma = 0; }   // developer bisect switch
   if (p.raw_tma) memcpy(p.tmap_raw, tm + 640, 128);
+  p.stem_raw = p.epi_tma && ctx->opt_stem_tma && N.stem_ok && o.mode == CONV_STEM7 && o.Cin == 4 && o.cpr == 1 && p.H == R;
+  if (p.stem_raw) memcpy(p.tmap_raw, N.stem_tmap, 128);
   p.pair = p.epi_tma && ctx->opt_pair && N.wmap_ok[i];
   if (p.pair) memcpy(p.tmap_w, tm + 768, 128);
 }
@@ -412,6 +419,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_PDL")) c->opt_pdl = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_STEM_TMA")) c->opt_stem_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
@@ -449,6 +457,7 @@ void suo_destroy(suo_ctx* ctx) {
     for (float* p : N.packed) if (p) cudaFree(p);
     for (uint16_t* p : N.packed16) if (p) cudaFree(p);
     if (N.range_flag) cudaFree(N.range_flag);
+    if (N.stem_pad) cudaFree(N.stem_pad);
     for (float* p : N.act) if (p) cudaFree(p);
     if (N.pool) cudaFree(N.pool);
     if (N.pooled) cudaFree(N.pooled);
@@ -579,6 +588,26 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
       rc2 = make_rows_tmap(ctx, N.tmaps[i].data() + 640, N.act[o.in], false, (size_t)ctx->max_crops * si * si, o.Cin, 128);
       if (rc2) return rc2;
       N.raw_ok[i] = 1;
+    }
+  }
+  // TMA-fed stem: zero-bordered input copy + tensor map of the overlapping windows (dimension 1 = output column, stride 2 pixels = 32 B,
+  // 32 floats = one kernel row of 7 pixels + 1; dimension 2 = bordered input row).  Needs whole output rows per 128-pixel tile.
+  N.stem_ok = 0;
+  if ((R / 2) % 128 == 0) {
+    N.stem_wp = R + 8; N.stem_hp = R + 6;
+    const size_t nb = (size_t)ctx->max_crops * N.stem_hp * N.stem_wp * 16;
+    SUO_CUDA_TRY(ctx, cudaMalloc(&N.stem_pad, nb));
+    SUO_CUDA_TRY(ctx, cudaMemset(N.stem_pad, 0, nb));
+    int rcs = make_plane_tmap(ctx, nullptr, nullptr, 0, 0, 0, 0);   // resolves the driver entry point
+    if (!rcs) {
+      CUtensorMap m;
+      const cuuint64_t dims[4] = {32, (cuuint64_t)(R / 2), (cuuint64_t)N.stem_hp, (cuuint64_t)ctx->max_crops};
+      const cuuint64_t strides[3] = {32, (cuuint64_t)N.stem_wp * 16, (cuuint64_t)N.stem_hp * N.stem_wp * 16};
+      const cuuint32_t box[4] = {32, 128, 1, 1};
+      const cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N.stem_pad, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) { memcpy(N.stem_tmap, &m, 128); N.stem_ok = 1; }     // a driver that rejects overlapping strides: register-gather stem
     }
   }
   // bottleneck tails that can run as one kernel (conv_fused.cu): op i = 3x3 128 -> 128 with ReLU on FP16-plane tensors,
@@ -907,7 +936,9 @@ static int forward_impl(suo_ctx* ctx, const void* images, int n_img, int H, int 
     if (rc) return rc;
     rc = launch_render_priors_nhwc(ctx, d_puv, d_pm, L, K, R, N.act[in_buf], N.bufs[in_buf].C, s);
   } else {
-    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s, images_u8);
+    const bool pad = N.stem_ok && N.bufs[in_buf].C == 4;
+    rc = launch_crop_concat(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, K, R, N.act[in_buf], N.bufs[in_buf].C, s, images_u8,
+                            pad ? N.stem_pad : nullptr, N.stem_wp, N.stem_hp);
   }
   if (rc) return rc;
   rc = run_network(ctx, L, variant, s);

@@ -72,6 +72,8 @@ struct ConvParams {
   unsigned long long* trace;  // developer tool (SUO_TRACE): [0] = launch counter, then {globaltimer start, end, grid, smid} per persistent conv launch
   int raw_tma;            // tmap_raw is valid: a register-fed 1x1 conv may fetch its FP32 input by TMA (plan 3)
   alignas(64) unsigned char tmap_raw[128];     // FP32 input [rows, Cin], box 128 rows x 32 floats
+  int stem_raw;           // CONV_STEM7 on the RGB-only layout: tmap_raw is a 4-D map over the zero-bordered input copy whose rows are the
+                          // OVERLAPPING 32-float windows of one kernel row (stride 2 pixels): the stem runs on the raw-TMA plan (3)
   int pair;               // tmap_w is valid and the CTA-pair kernel (conv_pair.cu) may run this layer
   alignas(64) unsigned char tmap_w[128];       // FP16x3 weight images as rows of 64 halfs (128 B), box 64 rows, no swizzle (the images are pre-swizzled)
 };
@@ -129,7 +131,7 @@ int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H
                           float* mask_logits, float* mask, int32_t* argmax, cudaStream_t s);
 int launch_crop_concat(suo_ctx* ctx, const void* images, int n_img, int H, int W, const float* boxes,
                        const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
-                       cudaStream_t s, int images_u8 = 0);
+                       cudaStream_t s, int images_u8 = 0, float* out_pad = nullptr, int pad_w = 0, int pad_h = 0);
 int launch_render_priors_planes(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int vh, int vw, int ndc,
                                 float* out, cudaStream_t s);
 int launch_render_priors_nhwc(suo_ctx* ctx, const float* uv, const uint8_t* mask, int L, int K, int R, float* out, int out_c,
@@ -175,6 +177,7 @@ struct suo_ctx {
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
   int opt_fuse = 0;     // run conv2 + conv3 of the 128-wide bottlenecks as one kernel: 1 = single CTA (conv_fused.cu), 2 = CTA pair (conv_fused2.cu); SUO_FUSE / SUO_OPT_CONV_FUSE
   int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
+  int opt_stem_tma = 1; // 1 = the RGB-only stem fetches its operand by TMA from a zero-bordered input copy (SUO_STEM_TMA=0: register gathers)
   int opt_pdl = 1;      // 1 = the persistent conv kernels are launched with programmatic stream serialization (SUO_PDL / SUO_OPT_PDL)
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)

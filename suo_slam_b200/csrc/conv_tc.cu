@@ -811,7 +811,17 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
             const uint32_t slot = x % RAW_BOXES;
             mbar_wait(raw_empty(slot), ((x / RAW_BOXES) & 1) ^ 1);
             mbar_arrive_expect_tx(raw_full(slot), RAW_BOX_BYTES);
-            tma_load_2d(smem_base + S::RAW_OFFSET + slot * RAW_BOX_BYTES, p.tmap_raw, 64 * j + 32 * h, m_tile * BLOCK_M, raw_full(slot));
+            const uint32_t dst = smem_base + S::RAW_OFFSET + slot * RAW_BOX_BYTES;
+            if (p.stem_raw) {
+              // 7x7/2 stem: the tile is 128 consecutive pixels of ONE output row (Wo % 128 == 0); box h of chunk j = kernel row
+              // ky = 2j + h: for output pixel ox the 32 floats starting at input pixel 2 ox - 3 of input row 2 oy + ky - 3, i.e. at
+              // pixel 2 ox of row 2 oy + ky of the zero-bordered copy (dimension 1 of the map strides by 2 pixels = 32 bytes)
+              const int m0 = m_tile * BLOCK_M, hw = p.Ho * p.Wo;
+              const int b0 = m0 / hw, rem = m0 - b0 * hw, oy = rem / p.Wo, ox0 = rem - oy * p.Wo;
+              tma_load_4d(dst, p.tmap_raw, 0, ox0, 2 * oy + 2 * j + h, b0, raw_full(slot));
+            } else {
+              tma_load_2d(dst, p.tmap_raw, 64 * j + 32 * h, m_tile * BLOCK_M, raw_full(slot));
+            }
           }
       }
     }
@@ -1123,6 +1133,8 @@ int launch_persistent(suo_ctx* ctx, const ConvParams& p, int passes, cudaStream_
     if (epi_tma) {
       if (p.residual && p.in_split && p.mode == CONV_1x1 && p.K <= 256) return launch_persistent_epi<BN, MATH_F16, 2>(ctx, p, passes, s);
       if (p.raw_tma && !p.in_split && p.mode == CONV_1x1 && p.Cin % 64 == 0) return launch_persistent_epi<BN, MATH_F16, 3>(ctx, p, passes, s);
+      if (p.stem_raw && p.mode == CONV_STEM7 && !p.residual && passes == 3 && p.K == 256 && p.Wo % BLOCK_M == 0)   // TMA-fed stem on plan 3
+        return launch_persistent_inst<BN, CONV_1x1, false, MATH_F16, false, 3>(ctx, p, passes, s);
       return launch_persistent_epi<BN, MATH_F16, 1>(ctx, p, passes, s);
     }
   }

@@ -42,7 +42,8 @@ __device__ __forceinline__ float bilinear(const void* __restrict__ img, int c, i
 template <bool U8>
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const void* __restrict__ images, int H, int W, const float* __restrict__ boxes,
-                 const int32_t* __restrict__ box_img, int R, float* __restrict__ out, int out_c) {
+                 const int32_t* __restrict__ box_img, int R, float* __restrict__ out, int out_c,
+                 float* __restrict__ out_pad, int pad_w, int pad_h) {
   const int crop = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= R * R) return;
@@ -66,7 +67,10 @@ roi_align_kernel(const void* __restrict__ images, int H, int W, const float* __r
   }
   float* __restrict__ o = out + ((size_t)crop * R * R + pix) * out_c;
   if (out_c == 4) {
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0] / count, acc[1] / count, acc[2] / count, 0.f);
+    const float4 v = make_float4(acc[0] / count, acc[1] / count, acc[2] / count, 0.f);
+    *reinterpret_cast<float4*>(o) = v;
+    // second copy with a 3-pixel zero border (rows of pad_w pixels, pad_h rows per crop): what the TMA-fed stem reads (conv_tc.cu)
+    if (out_pad) *reinterpret_cast<float4*>(out_pad + (((size_t)crop * pad_h + ph + 3) * pad_w + pw + 3) * 4) = v;
   } else {
     o[0] = acc[0] / count; o[1] = acc[1] / count; o[2] = acc[2] / count;
   }
@@ -127,15 +131,15 @@ upsample_add_kernel(const float4* __restrict__ up1, const float4* __restrict__ l
 
 int launch_crop_concat(suo_ctx* ctx, const void* images, int n_img, int H, int W, const float* boxes,
                        const int32_t* box_img, int L, const float* priors, int num_kp, int R, float* out, int out_c,
-                       cudaStream_t s, int images_u8) {
+                       cudaStream_t s, int images_u8, float* out_pad, int pad_w, int pad_h) {
   (void)n_img;
   if (!(out_c == 4 || out_c == 48) || (out_c == 4 && priors) || num_kp > 45 || (R * R) % 64) {
     ctx->set_error("crop_concat: out_c must be 4 (no priors) or 48", __FILE__, __LINE__);
     return SUO_E_INVALID;
   }
   dim3 g((R * R + 255) / 256, L);
-  if (images_u8) roi_align_kernel<true><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
-  else roi_align_kernel<false><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c);
+  if (images_u8) roi_align_kernel<true><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c, out_pad, pad_w, pad_h);
+  else roi_align_kernel<false><<<g, 256, 0, s>>>(images, H, W, boxes, box_img, R, out, out_c, out_pad, pad_w, pad_h);
   ctx->launches++;
   if (out_c == 48 && num_kp >= 0) {   // num_kp < 0: RGB only, the caller renders the prior channels itself (prior.cu)
     dim3 g2(R * R / 64, L);
