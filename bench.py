@@ -78,7 +78,8 @@ def conv_classes(dump_path, L, pair=True):
         (0, 0, 1): ("conv_tc_persistent_kernel<128, 0, 0, 1, 1, 2>", "1x1 convs + skip add (TMA-fed A, skip prefetched by TMA)", "hbm"),
         (0, 1, 0): ("conv_tc_persistent_kernel<128, 0, 1, 1, 0, 3>", "1x1 convs with BN+ReLU prologue (raw FP32 by TMA)", "hbm"),
         (0, 0, 0): ("conv_tc_persistent_kernel<128, 0, 0, 1, 0, 3>", "plain 1x1 convs", "hbm"),
-        (2, 0, 0): ("conv_tc_persistent_kernel<64, 2, 0, 1, 0, 1>", "7x7/2 stem", "hbm"),
+        (2, 0, 0): ("conv_tc_persistent_kernel<64, 0, 0, 1, 0, 3>" if os.environ.get("SUO_STEM_TMA", "1") != "0" else "conv_tc_persistent_kernel<64, 2, 0, 1, 0, 1>",
+                    "7x7/2 stem (TMA-fed from the zero-bordered input copy)" if os.environ.get("SUO_STEM_TMA", "1") != "0" else "7x7/2 stem", "hbm"),
     }
     out = {}
     for r in csv.DictReader(open(dump_path)):

@@ -6,10 +6,10 @@ rm -f gpurun_out/summary.txt gpurun_out/trace.*.csv
 run alltests 1200 python -m pytest tests -q -m gpu -x
 run smoke 300 python -c "import __graft_entry__ as g; g.smoke()"
 SUO_BENCH_PER_OP=gpurun_out/per_op.csv run bench 900 python bench.py
-run bench64 600 python bench.py --no-cpu-baseline --frames-per-step 64
+
 run bench_ref 600 python bench.py --impl reference --steps 3 --warmup 1
 run ncu_list 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 636 -c 215 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:"conv3x3_pair|conv_tc" -s 584 -c 12 -f -o gpurun_out/prof_conv python bench.py --steps 1 --warmup 3 --no-cpu-baseline
-SUO_TRACE=gpurun_out/trace run bench_trace 600 python bench.py --no-cpu-baseline --steps 20
-for f in gpurun_out/trace.*.csv; do python tools/trace_gaps.py $f | tee -a gpurun_out/summary.txt; done
+
+
+
 ls -la gpurun_out >> gpurun_out/summary.txt
