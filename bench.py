@@ -88,7 +88,9 @@ def conv_classes(dump_path, L, pair=True):
         key = (int(r["mode"]), int(r["pre"]), int(r["res"]))
         ncu, desc, bound = names.get(key, ("conv_tc_persistent_kernel", "other convs", "hbm"))
         side, cin, cout, K = int(r["side_out"]), int(r["Cin"]), int(r["Cout"]), int(r["K"])
-        if key == (1, 0, 0) and cout == 128 and pair:        # the bottleneck's conv2 runs as a CTA pair (csrc/conv_pair.cu)
+        if key == (1, 0, 0) and cout == 128 and pair and side in (16, 32, 64) and os.environ.get("SUO_HALO", "1") != "0":
+            ncu, desc = "conv3x3_halo_kernel", "3x3 convs (A-halo CTA pair: activations once per column shift, tcgen05.mma.cta_group::2, fp16x3)"
+        elif key == (1, 0, 0) and cout == 128 and pair:      # the bottleneck's conv2 runs as a CTA pair (csrc/conv_pair.cu)
             ncu, desc = "conv3x3_pair_kernel", "3x3 convs (CTA pair: tcgen05.mma.cta_group::2 of M = 256, TMA-fed, fp16x3)"
         elif key == (3, 0, 1):                               # SUO_FUSE: conv2 + conv3 + skip in one kernel
             ncu, desc, bound = "conv_fused23", "fused 3x3 + 1x1 + skip (SUO_FUSE)", "tensor"

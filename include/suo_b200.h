@@ -47,9 +47,12 @@ enum {
                                    kernel, 2 = CTA-pair kernel (tcgen05.mma.cta_group::2); 0 = two kernels. Results are identical. */
   SUO_OPT_CONV_PAIR = 8,       /* 1 (default) = 3x3 convs on FP16-plane tensors run as CTA pairs (tcgen05.mma.cta_group::2: each CTA of
                                    a 2-CTA cluster loads half of the weight rows); 0 = one CTA per tile. Results are identical. */
-  SUO_OPT_PDL = 9              /* 1 (default) = the persistent conv kernels use programmatic dependent launch (the next kernel's CTAs are
+  SUO_OPT_PDL = 9,             /* 1 (default) = the persistent conv kernels use programmatic dependent launch (the next kernel's CTAs are
                                    scheduled and run their prologue while the previous kernel drains; griddepcontrol.wait before any
                                    activation is touched); 0 = plain stream order */
+  SUO_OPT_CONV_HALO = 10       /* 1 (default) = the 3x3 convs at 64x64 / 32x32 / 16x16 fetch their activations once per column shift (A-halo
+                                   CTA-pair kernel, conv_halo.cu); its accumulation order differs from the other 3x3 kernels: equal to FP32
+                                   rounding, not bit for bit.  0 = CTA-pair kernel of SUO_OPT_CONV_PAIR */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

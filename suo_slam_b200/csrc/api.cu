@@ -57,6 +57,24 @@ int make_plane_tmap(suo_ctx* ctx, void* out128, const void* base, int C, int W, 
   memcpy(out128, &m, 128);
   return SUO_OK;
 }
+// The same planes with the box of the A-halo kernel (conv_halo.cu): {64 ch, W px, 128 / W + 2 rows, 1 image} — one column-shifted variant
+// of a 128-pixel tile including the row above and the row below it; zero fill outside the image = the 3x3 conv's padding in x and y.
+int make_plane_tmap_halo(suo_ctx* ctx, void* out128, const void* base, int C, int W, int H, int B) {
+  if (!(W == 16 || W == 32 || W == 64) || C % 64 || (H * W) % 128) return SUO_E_INVALID;
+  int rc = make_plane_tmap(ctx, nullptr, nullptr, 0, 0, 0, 0);   // resolves the driver entry point
+  if (rc) return rc;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)W, (cuuint32_t)(128 / W + 2), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ctx->set_error("cuTensorMapEncodeTiled (halo) failed: " + std::to_string((int)r), __FILE__, __LINE__); return SUO_E_CUDA; }
+  memcpy(out128, &m, 128);
+  return SUO_OK;
+}
 // CUtensorMap of a row-major 2-D view [rows, cols] (the NHWC tensor with pixels flattened) whose box is 32 rows x 128 bytes
 // (32 floats or 64 halfs), SWIZZLE_128B: what one epilogue warp stores (or fetches, for the skip tensor) per TMA operation.
 int make_rows_tmap(suo_ctx* ctx, void* out128, const void* base, bool fp16, size_t rows, int cols, int box_rows = 32) {
@@ -115,7 +133,8 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
-  std::vector<std::array<unsigned char, 896>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip / raw input / weight-image CUtensorMaps (split mode)
+  std::vector<std::array<unsigned char, 1152>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip / raw input / weight-image CUtensorMaps (split mode)
+  std::vector<int> halo_ok;                             // per op: the A-halo maps (bytes 896.. of tmaps) are valid
   std::vector<int> epi_ok, raw_ok, wmap_ok;             // per op: the output / skip maps, the FP32 input map, the weight-image map are valid
   // TMA-fed stem (RGB-only layout): a second copy of the network input with a 3-pixel zero border, rows of stem_wp pixels, stem_hp rows
   // per crop, and the 4-D tensor map of its overlapping kernel-row windows
@@ -127,8 +146,8 @@ struct NetState {
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair, o.pdl); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl, halo; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl, halo) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair, o.pdl, o.halo); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -204,6 +223,8 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   p.stem_raw = p.epi_tma && ctx->opt_stem_tma && N.stem_ok && o.mode == CONV_STEM7 && o.Cin == 4 && o.cpr == 1 && p.H == R;
   if (p.stem_raw) memcpy(p.tmap_raw, N.stem_tmap, 128);
   p.pair = p.epi_tma && ctx->opt_pair && N.wmap_ok[i];
+  p.halo = p.pair && ctx->opt_halo && N.halo_ok[i];
+  if (p.halo) { memcpy(p.tmap_hhi, tm + 896, 128); memcpy(p.tmap_hlo, tm + 1024, 128); }
   if (p.pair) memcpy(p.tmap_w, tm + 768, 128);
 }
 
@@ -347,7 +368,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair, ctx->opt_pdl};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair, ctx->opt_pdl, ctx->opt_halo};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -420,6 +441,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_PDL")) c->opt_pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_STEM_TMA")) c->opt_stem_tma = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_HALO")) c->opt_halo = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MMA_MERGE")) c->opt_mma_merge = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_RAW_TMA")) c->opt_raw_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_GRID_CAP")) c->opt_grid_cap = atoi(e);
@@ -487,6 +509,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_FUSE: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_fuse = value; return SUO_OK;
     case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_PDL: ctx->opt_pdl = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_CONV_HALO: ctx->opt_halo = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -550,6 +573,7 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   N.epi_ok.assign(N.ops.size(), 0);
   N.raw_ok.assign(N.ops.size(), 0);
   N.wmap_ok.assign(N.ops.size(), 0);
+  N.halo_ok.assign(N.ops.size(), 0);
   for (size_t i = 0; i < N.ops.size(); ++i) {
     const OpDesc& o = N.ops[i];
     if (o.type != OP_CONV) continue;
@@ -566,6 +590,10 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
       if (rc2) return rc2;
       rc2 = make_plane_tmap(ctx, N.tmaps[i].data() + 128, base + plane, C, side, side, ctx->max_crops);
       if (rc2) return rc2;
+      if (o.mode == CONV_3x3 && (side == 16 || side == 32 || side == 64) && C % 64 == 0 &&
+          !make_plane_tmap_halo(ctx, N.tmaps[i].data() + 896, base, C, side, side, ctx->max_crops) &&
+          !make_plane_tmap_halo(ctx, N.tmaps[i].data() + 1024, base + plane, C, side, side, ctx->max_crops))
+        N.halo_ok[i] = 1;
     }
     // output (and skip) maps of the TMA-store epilogue: rows = every pixel of every crop slot of the buffer
     const BufDesc& bo = N.bufs[o.out];
@@ -781,8 +809,9 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
   p.out_c = Cout; p.K = K; p.chunks_per_row = cpr; p.relu = relu; p.out_nchw = 0;
   // backend 2..5: tcgen05 FP16x3; 3/5 feed A by TMA from pre-split FP16 planes, 4/5 write the output as FP16 planes
   // backend 6 = 5 through the CTA-pair kernel (3x3, Cout = 128 only; other shapes run exactly as backend 5)
-  const bool want_pair = backend == 6;
-  if (backend == 6) backend = 5;
+  const bool want_halo = backend == 7;       // backend 7 = 6 through the A-halo kernel (W in {16, 32, 64})
+  const bool want_pair = backend == 6 || backend == 7;
+  if (backend == 6 || backend == 7) backend = 5;
   const bool tma_in = backend == 3 || backend == 5, split_out = backend == 4 || backend == 5;
   p.math = backend >= 2 ? 1 : 0; p.w_packed16 = d_wp16; p.range_flag = d_flag;
   if (backend >= 2) backend = 1;
@@ -820,6 +849,9 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin, cons
       r2 = make_weight_tmap(ctx, p.tmap_w, d_wp16, wp16.size());
       if (r2) { if (d_in16) cudaFree(d_in16); return r2; }
       p.pair = 1;
+      if (want_halo && d_in16 && !make_plane_tmap_halo(ctx, p.tmap_hhi, d_in16, Cin, W, H, B) &&
+          !make_plane_tmap_halo(ctx, p.tmap_hlo, d_in16 + n_in, Cin, W, H, B))
+        p.halo = 1;
     }
   }
   long long* d_dbg = nullptr;

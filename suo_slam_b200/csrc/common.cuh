@@ -74,6 +74,9 @@ struct ConvParams {
   alignas(64) unsigned char tmap_raw[128];     // FP32 input [rows, Cin], box 128 rows x 32 floats
   int stem_raw;           // CONV_STEM7 on the RGB-only layout: tmap_raw is a 4-D map over the zero-bordered input copy whose rows are the
                           // OVERLAPPING 32-float windows of one kernel row (stride 2 pixels): the stem runs on the raw-TMA plan (3)
+  int halo;               // tmap_hhi / tmap_hlo are valid and the A-halo kernel (conv_halo.cu) may run this 3x3 layer
+  alignas(64) unsigned char tmap_hhi[128];     // FP16 planes [B,H,W,C] with box {64 ch, W, 128 / W + 2 rows, 1}: one column-shifted variant of a tile
+  alignas(64) unsigned char tmap_hlo[128];
   int pair;               // tmap_w is valid and the CTA-pair kernel (conv_pair.cu) may run this layer
   alignas(64) unsigned char tmap_w[128];       // FP16x3 weight images as rows of 64 halfs (128 B), box 64 rows, no swizzle (the images are pre-swizzled)
 };
@@ -115,6 +118,9 @@ int launch_conv_fused23_pair(suo_ctx* ctx, const FusedParams& p, cudaStream_t s)
 // 3x3 conv as a CTA pair (tcgen05.mma.cta_group::2, conv_pair.cu): eligibility test and launch
 bool conv_pair_eligible(const ConvParams& p, int passes);
 int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
+// 3x3 conv as a CTA pair that fetches the activations once per column shift (conv_halo.cu)
+bool conv_halo_eligible(const ConvParams& p, int passes);
+int launch_conv_halo(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
 int launch_conv_simt(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
 int launch_conv_tc(suo_ctx* ctx, const ConvParams& p, int tf32_passes, cudaStream_t s);
 // host-side packing of canonical [Cout_pad][K] weights into the tcgen05 smem images
@@ -177,6 +183,7 @@ struct suo_ctx {
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
   int opt_fuse = 0;     // run conv2 + conv3 of the 128-wide bottlenecks as one kernel: 1 = single CTA (conv_fused.cu), 2 = CTA pair (conv_fused2.cu); SUO_FUSE / SUO_OPT_CONV_FUSE
   int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
+  int opt_halo = 1;     // 1 = 3x3 convs at 64x64 / 32x32 / 16x16 run on the A-halo kernel (conv_halo.cu); SUO_HALO=0 / SUO_OPT_CONV_HALO turn it off
   int opt_stem_tma = 1; // 1 = the RGB-only stem fetches its operand by TMA from a zero-bordered input copy (SUO_STEM_TMA=0: register gathers)
   int opt_pdl = 1;      // 1 = the persistent conv kernels are launched with programmatic stream serialization (SUO_PDL / SUO_OPT_PDL)
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;

@@ -1109,6 +1109,7 @@ int launch_persistent_epi(suo_ctx* ctx, const ConvParams& p, int passes, cudaStr
   if (MATH == MATH_F16 && p.in_split) {
     if (p.pre_scale || p.mode == CONV_STEM7 || p.Cin % 64) { ctx->set_error("conv_tc: TMA-fed A needs a plain 1x1/3x3 conv with Cin % 64 == 0", __FILE__, __LINE__); return SUO_E_INVALID; }
     if (p.mode == CONV_3x3) {
+      if (BN == 128 && conv_halo_eligible(p, passes)) return launch_conv_halo(ctx, p, s);
       if (BN == 128 && conv_pair_eligible(p, passes)) return launch_conv_pair(ctx, p, s);
       return launch_persistent_inst<BN, CONV_3x3, false, MATH_F16, true, (EPI >= 2 ? 1 : EPI)>(ctx, p, passes, s);
     }

@@ -107,6 +107,28 @@ def test_conv_pair_kernel_equals_single_cta_kernel(gpu_ctx, case):
     assert np.abs(pair - ref).max() / np.abs(ref).max() < 8e-6
 
 
+HALO_CASES = [(2, 16, 16, 128), (24, 32, 32, 128), (3, 64, 64, 128), (2, 16, 16, 64), (1, 64, 64, 64), (9, 16, 16, 128)]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv_halo_kernel_vs_fp64_and_single_cta_kernel(gpu_ctx, case):
+    """csrc/conv_halo.cu fetches the activations once per column shift (three x-shifted variants of rows + 2 image rows, the dy taps are
+    descriptor offsets into the same shared-memory image): same products as the other 3x3 kernels in another accumulation order."""
+    B, H, W, Cin = case
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    x = rng.normal(size=(B, H, W, Cin)).astype(np.float32)
+    w = (rng.normal(size=(128, 3, 3, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
+    b = rng.normal(size=128).astype(np.float32)
+    n0 = gpu_ctx.kernel_launches()
+    halo = pkpnet.conv2d(gpu_ctx, x, w, b, 3, 1, None, None, True, backend=7)
+    single = pkpnet.conv2d(gpu_ctx, x, w, b, 3, 1, None, None, True, backend=5)
+    assert gpu_ctx.kernel_launches() - n0 == 2
+    ref = _conv_ref(x, w, b, 3, 1, None, None, True)
+    scale = np.abs(ref).max()
+    assert np.abs(halo - ref).max() / scale < 8e-6
+    assert np.abs(halo - single).max() / scale < 2e-6
+
+
 def test_heatmap_reduce_vs_reference_golden(gpu_ctx, golden_dir):
     g = np.load(f"{golden_dir}/reduce.npz")
     out = pkpnet.heatmap_reduce(gpu_ctx, g["logits"])

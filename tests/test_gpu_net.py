@@ -211,6 +211,7 @@ def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, fuse_mode,
     img = torch.from_numpy(rng.random((1, 3, 240, 320), dtype=np.float32)).cuda()
     boxes = [torch.tensor([[10.0, 20.0, 200.0, 230.0], [100.0, 5.0, 310.0, 200.0], [50.0, 50.0, 120.0, 140.0]]).cuda()]
     m = _model(sd, 2, 3, res=256, max_crops=3)
+    m.context().set_option(_lib.SUO_OPT_CONV_HALO, 0)      # the A-halo kernel accumulates in another order: identity holds among the others
     outs = {}
     for fuse in (1, 0):
         m.context().set_option(_lib.SUO_OPT_CONV_FUSE, fuse_mode if fuse else 0)
@@ -233,6 +234,7 @@ def test_cta_pair_conv_kernel_equals_single_cta_kernels(sd):
     img = torch.from_numpy(rng.random((1, 3, 240, 320), dtype=np.float32)).cuda()
     boxes = [torch.tensor([[10.0, 20.0, 200.0, 230.0], [100.0, 5.0, 310.0, 200.0], [50.0, 50.0, 120.0, 140.0]]).cuda()]
     m = _model(sd, 2, 3, res=256, max_crops=3)
+    m.context().set_option(_lib.SUO_OPT_CONV_HALO, 0)      # (see above)
     outs = {}
     for pair in (1, 0):
         m.context().set_option(_lib.SUO_OPT_CONV_PAIR, pair)
@@ -301,3 +303,27 @@ def test_frame_pipeline_ragged_frames(sd):
     none = pipe.run(imgs_u8, np.zeros((0, 4), np.float32), np.zeros(0, np.int32), np.zeros((0, 41, 3)), np.zeros((0, 41), bool),
                     np.zeros((0, 3, 3)), np.zeros(0))
     assert none["T_pnp"].shape == (0, 4, 4) and none["kp_used"].shape == (0, 41) and none["kp_used"].dtype == bool
+
+
+@pytest.mark.parametrize("grid_cap", [0, 3])
+def test_halo_conv_kernel_network_output(sd, grid_cap, monkeypatch):
+    """The 3x3 convs on the A-halo kernel (csrc/conv_halo.cu, opt-in): the network output agrees with the default kernels to FP32
+    rounding (another accumulation order) and with the oracle within the usual tolerance; grid_cap = 3: many tiles per cluster."""
+    if grid_cap:
+        monkeypatch.setenv("SUO_GRID_CAP", str(grid_cap))
+    rng = np.random.default_rng(24)
+    img = torch.from_numpy(rng.random((1, 3, 240, 320), dtype=np.float32)).cuda()
+    boxes = [torch.tensor([[10.0, 20.0, 200.0, 230.0], [100.0, 5.0, 310.0, 200.0], [50.0, 50.0, 120.0, 140.0]]).cuda()]
+    m = _model(sd, 2, 3, res=256, max_crops=3)
+    outs = {}
+    for halo in (1, 0):
+        m.context().set_option(_lib.SUO_OPT_CONV_HALO, halo)
+        o = m(img, boxes)
+        torch.cuda.synchronize()
+        outs[halo] = {k: v.cpu().numpy() for k, v in o.items()}
+    ref = net_oracle.pkpnet_forward(sd, img.cpu(), [b.cpu() for b in boxes], None, (256, 256))
+    lr = ref["prob_logits"].numpy()
+    tol = 5e-4 * max(1.0, np.abs(lr).max() / 10)
+    assert np.abs(outs[1]["prob_logits"] - lr).max() < tol
+    assert np.abs(outs[1]["prob_logits"] - outs[0]["prob_logits"]).max() < tol
+    assert np.abs(outs[1]["uv"] - ref["uv"].numpy()).max() < 5e-5
