@@ -28,7 +28,7 @@ def run_smoke(verbose: bool = False):
     out = m(torch.from_numpy(g["img"]).cuda(), [torch.from_numpy(g["boxes"]).cuda()], None)
     torch.cuda.synchronize()
     err = float(np.abs(out["prob_logits"].cpu().numpy() - g["logits"]).max())
-    say(f"network (tcgen05, fp16x3 split math, CTA-pair 3x3 convs) vs reference golden: max |dlogit| = {err:.2e}")
+    say(f"network (tcgen05, fp16x3 split math, A-halo / CTA-pair 3x3 convs) vs reference golden: max |dlogit| = {err:.2e}")
     assert err < 3e-3, err
     np.testing.assert_allclose(out["uv"].cpu().numpy(), g["uv"], atol=5e-5)
     np.testing.assert_allclose(out["cov"].cpu().numpy(), g["cov"], atol=5e-5)
