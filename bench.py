@@ -398,23 +398,35 @@ def run_native(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": dom["name"], "launches_per_step": dom["n"], "share_of_step": dom["ms"] / (ms_dev / args.steps),
-                         "achieved": dom["gflop"] / dom["ms"], "peak": peak_tf, "unit": "TFLOP/s", "frac": dom["gflop"] / dom["ms"] / peak_tf,
-                         "mma_achieved": 3 * dom["gflop"] / dom["ms"], "mma_frac": 3 * dom["gflop"] / dom["ms"] / peak_tf,
-                         "traffic": cls_traffic(dom), "algorithmic_bytes": dom["bytes"] / dom["n"],
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
-                         "note": "achieved = algorithmic FLOPs of these launches (2*M*N*K per conv, summing to 31.495 GFLOP/crop over the net) / their summed duration "
-                                 "(CUDA events per launch); the reference computes in FP32 and tcgen05 has no FP32 MMA, so each product is 3 f16-kind MMAs (fp16x3 split): "
-                                 "mma_achieved = 3 x achieved is what the tensor pipe executes, the ceiling of frac is 1/3; traffic / algorithmic_bytes are per launch (average)"},
-            "roofline_hbm": {"bound": "hbm", "kernel": hbm_cls["name"], "launches_per_step": hbm_cls["n"], "share_of_step": hbm_cls["ms"] / (ms_dev / args.steps),
-                             "achieved": hbm_cls["bytes"] / hbm_cls["ms"] * 1e-6, "peak": peak_bw, "unit": "GB/s",
-                             "frac": hbm_cls["bytes"] / hbm_cls["ms"] * 1e-6 / peak_bw, "traffic": cls_traffic(hbm_cls), "algorithmic_bytes": hbm_cls["bytes"] / hbm_cls["n"],
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6500 (of fallback)"},
+            "roofline": None, "roofline_tensor": None, "roofline_hbm": None,      # filled below
             "conv_engine": {"achieved_all_convs": achieved_all, "unit": "TFLOP/s", "frac": achieved_all / peak_tf, "conv_ms_per_step": conv_ms.value,
                             "other_net_ms_per_step": other_ms.value, "dram_bytes_per_step": traffic,
                             "classes": {k: {"n": c["n"], "ms": round(c["ms"], 4), "TFLOP/s": round(c["gflop"] / c["ms"], 1),
                                             "GB/s": round(c["bytes"] / c["ms"] * 1e-6, 1), "bound": c["bound"]} for k, c in classes.items()}},
         }
+        step_ms = ms_dev / args.steps
+        ten_cls = max((c for c in classes.values() if c["bound"] == "tensor"), key=lambda c: c["ms"])
+
+        def roof(c):
+            """Roofline of one kernel class against the resource that bounds it.  achieved = algorithmic work of these launches / their summed duration
+            (CUDA events per launch); traffic / algorithmic_bytes are per launch (average)."""
+            base = {"bound": c["bound"], "kernel": c["name"], "launches_per_step": c["n"], "share_of_step": c["ms"] / step_ms,
+                    "traffic": cls_traffic(c), "algorithmic_bytes": c["bytes"] / c["n"]}
+            if c["bound"] == "tensor":
+                tf = c["gflop"] / c["ms"]
+                base.update({"achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "mma_achieved": 3 * tf, "mma_frac": 3 * tf / peak_tf,
+                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1400 (of fallback)",
+                             "note": "algorithmic FLOPs = 2*M*N*K per conv (31.495 GFLOP/crop over the net); the reference computes in FP32 and tcgen05 has no FP32 MMA, so "
+                                     "each product is 3 f16-kind MMAs (fp16x3 split): mma_achieved = 3 x achieved is what the tensor pipe executes, the ceiling of frac is 1/3"})
+            else:
+                gb = c["bytes"] / c["ms"] * 1e-6
+                base.update({"achieved": gb, "peak": peak_bw, "unit": "GB/s", "frac": gb / peak_bw,
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6500 (of fallback)"})
+            return base
+
+        out["roofline"] = roof(dom)                   # the kernel class with the largest share of the step, against ITS bound
+        out["roofline_tensor"] = roof(ten_cls)        # largest tensor-bound class (the 3x3 convs)
+        out["roofline_hbm"] = roof(hbm_cls)           # largest HBM-bound class (the 1x1 convs that add the skip tensor)
         if not args.no_cpu_baseline and world == 1:
             cfps, n, cores, _ = cpu_reference_frames_per_s(args.cpu_baseline_seconds)
             out["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
