@@ -15,8 +15,11 @@ w = (rng.normal(size=(128, 3, 3, Cin)) / np.sqrt(9 * Cin)).astype(np.float32)
 b = rng.normal(size=128).astype(np.float32)
 ctx = _lib.Context(device=0, max_crops=8, crop_res=64, num_kp=41)
 outs = {}
-for rep in range(2):
-    for backend in (6, 5):
+backends = tuple(int(v) for v in os.environ.get("PROBE_BACKENDS", "6,5").split(","))     # 7 = A-halo, 6 = CTA pair, 5 = single CTA
+for rep in range(int(os.environ.get("PROBE_REPS", "2"))):
+    for backend in backends:
         outs[backend] = pkpnet.conv2d(ctx, x, w, b, 3, 1, None, None, True, backend=backend)
-print("identical:", np.array_equal(outs[5], outs[6]))
+ref = outs[backends[-1]]
+for k in backends[:-1]:
+    print(f"backend {k} vs {backends[-1]}: identical {np.array_equal(outs[k], ref)}, max rel diff {np.abs(outs[k] - ref).max() / np.abs(ref).max():.2e}")
 ctx.close()
