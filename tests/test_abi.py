@@ -96,3 +96,14 @@ def test_checkpoint_converter_roundtrip(tmp_path):
         checkpoint.load_checkpoint(str(tmp_path / "bad.pth.tar"))
     with pytest.raises(RuntimeError):
         PkpNet().load_packed(b"\\0" * 128)
+
+
+def test_option_constants_match_the_header():
+    """suo_slam_b200/_lib.py mirrors the SUO_OPT_* enum of include/suo_b200.h by hand: keep them equal."""
+    import re
+    from suo_slam_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(_lib.HERE), "include", "suo_b200.h")).read()
+    enum = dict(re.findall(r"(SUO_OPT_[A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    assert len(enum) >= 10
+    for name, val in enum.items():
+        assert getattr(_lib, name) == int(val), name
