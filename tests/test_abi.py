@@ -107,3 +107,41 @@ def test_option_constants_match_the_header():
     assert len(enum) >= 10
     for name, val in enum.items():
         assert getattr(_lib, name) == int(val), name
+
+
+@pytest.mark.parametrize("cin_store", [4, 48])
+def test_stem_weight_layout_matches_the_gather_order(cin_store):
+    """The packed stem weights [Cout_pad][K] and the implicit-GEMM gather order of csrc/conv_gather.cuh (K index = kernel row ky *
+    (chunks_per_row * 32) + kx * Cin_store + ci, starting at input pixel (2 oy + ky - 3, 2 ox - 3)) reproduce the 7x7/2 pad-3 conv: emulate the
+    gather in numpy and compare with torch.  RGB-only layout: one 32-float chunk per kernel row and an eighth all-zero row (K = 256)."""
+    import torch
+    import torch.nn.functional as F
+    rng = np.random.default_rng(cin_store)
+    Cin = 3 if cin_store == 4 else 44
+    w = rng.normal(size=(64, Cin, 7, 7))
+    b = rng.normal(size=64)
+    B = weights._Builder({}, 41)
+    i0, o0 = B.buf(1, cin_store), B.buf(2, 64)
+    B.conv(i0, o0, w, b, weights.CONV_STEM7, relu=1, variant=0)
+    op = B.ops[0]
+    Cout_pad, K, cpr, w_off, b_off = op[8], op[9], op[10], op[13], op[14]
+    pool = np.concatenate(B.pool)
+    wk = pool[w_off:w_off + Cout_pad * K].reshape(Cout_pad, K).astype(np.float64)
+    assert (K, cpr) == ((256, 1) if cin_store == 4 else (7 * 12 * 32, 12))
+    H = W = 16
+    x = np.zeros((H, W, cin_store))
+    x[:, :, :Cin] = rng.normal(size=(H, W, Cin))
+    Ho, Wo = H // 2, W // 2
+    A = np.zeros((Ho * Wo, K))
+    for oy in range(Ho):
+        for ox in range(Wo):
+            for ky in range(K // (cpr * 32)):
+                iy = 2 * oy + ky - 3
+                for e in range(cpr * 32):                      # float index inside the kernel row window
+                    pix, ci = divmod(e, cin_store)
+                    ix = 2 * ox - 3 + pix
+                    if pix < 7 and 0 <= iy < H and 0 <= ix < W:
+                        A[oy * Wo + ox, ky * cpr * 32 + e] = x[iy, ix, ci]
+    got = np.maximum(A @ wk[:64].T + pool[b_off:b_off + 64], 0).reshape(Ho, Wo, 64)
+    ref = F.relu(F.conv2d(torch.from_numpy(x[:, :, :Cin]).permute(2, 0, 1)[None], torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=3))
+    np.testing.assert_allclose(got, ref[0].permute(1, 2, 0).numpy(), atol=2e-5)      # pool is float32
