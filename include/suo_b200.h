@@ -170,15 +170,32 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
  *   inliers   [n_edges] u8 in/out
  *   its[n_rounds] LM iterations per round; huber_delta; chi2_gate; init_with_outliers
  *   stats     [n_prob,3] i32 or NULL: rounds run, outer iterations, LM trials
- * Every edge must touch exactly one non-fixed vertex (single-view mode: camera fixed;
- * curr_only mode: objects folded into p_inG) — the camera+object coupled global graph
- * is SURVEY.md §8 row f3 and returns SUO_E_INVALID here. */
+ * Graphs in which every edge touches exactly one non-fixed vertex (single-view mode: camera fixed; curr_only mode:
+ * objects folded into p_inG) with at most 64 vertices run on the shared-memory kernel (csrc/ba.cu); coupled
+ * camera+object graphs (global BA, lib/object_slam.py:736-778 -> LinearSolverCholmod) and larger graphs run on the
+ * Schur-complement kernel (csrc/ba_global.cu).  The call routes by graph structure. */
 int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge,
                  double* poses, const uint8_t* fixed, int n_vert,
                  const int32_t* e_obj, const int32_t* e_cam, const double* cam_k, const double* p,
                  const double* uv, const double* info, uint8_t* inliers, int n_edges,
                  const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
                  int init_with_outliers, int32_t* stats, int on_device, void* stream);
+
+/* The 2-vector error of every edge as the most recent suo_ba_batch call left it — what g2o keeps inside each edge
+ * after SparseOptimizer::optimize and ObjectSLAM.optimize() reads back through e.chi2() without recomputing
+ * (lib/object_slam.py:881-883; after a rejected LM trial that is the REJECTED state's error,
+ * optimization_algorithm_levenberg.cpp:120-141).  err [n_edges,2] f64; n_edges must match that call. */
+int suo_ba_last_errors(suo_ctx* ctx, double* err, int n_edges, int on_device, void* stream);
+
+/* computeError + linearizeOplus of a batch of independent edges (thirdparty/g2opy/g2o/types/object_slam/
+ * types_object_slam.cpp:45-60,70-123 EdgeSE3ProjectFromObject; :156-169,177-201 EdgeSE3ProjectFromFixedObject when
+ * T_obj == NULL): the device functions the LM kernels use, exposed so that the analytic Jacobians can be checked
+ * against central differences (the recipe the reference left commented out at :108-122).
+ *   T_obj [n,12] or NULL, T_cam [n,12] row-major [R|t]; cam_k [n,4]; p [n,3]; uv [n,2]
+ *   err [n,2], J_obj [n,2,6], J_cam [n,2,6] (tangent order omega, upsilon; update T <- exp(dx) T); any may be NULL */
+int suo_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const double* T_cam, const double* cam_k,
+                       const double* p, const double* uv, double* err, double* J_obj, double* J_cam,
+                       int on_device, void* stream);
 
 /* ---- keypoints -> poses ---------------------------------------------------------- */
 /* Everything ObjectSLAM does with the network output of single-view frames, device resident:
@@ -232,6 +249,40 @@ int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int
                   uint64_t seed, int run_ba,
                   double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
                   float* uv, float* cov, int on_device, void* stream);
+
+/* Asynchronous, double-buffered form of suo_frames_u8 for a STREAM of frame batches (host pointers, priors == NULL):
+ * submit enqueues the host->device copies of the batch on the library's copy stream and the frame path on `stream`
+ * and returns at once; suo_frames_wait blocks until that slot's results are in the host output buffers (and reports
+ * the FP16-range flag like the synchronous call).  With two slots the copies of batch i+1 overlap the kernels of
+ * batch i.  Input and output buffers must stay valid (and should be pinned) until the wait returns; a slot must be
+ * waited for before it is submitted again.  slot in {0, 1}. */
+int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W,
+                         const float* boxes, const int32_t* box_img, int L,
+                         const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                         const double* diameter, double kp_var_thresh, double bbox_thresh,
+                         uint64_t seed, int run_ba,
+                         double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
+                         float* uv, float* cov, void* stream);
+int suo_frames_wait(suo_ctx* ctx, int slot);
+
+/* ---- multi-GPU exchange (BASELINE.json configs[3]) -------------- */
+/* The reference has no inference-side distribution.  Crops / frames are sharded over one process per GPU and the
+ * per-crop results are exchanged ONCE, as fixed-size records, before any step that needs all objects (camera-pose
+ * voting lib/object_slam.py:975-1072, the joint graph :736-837).  Record of one crop (suo_record_bytes(K) bytes,
+ * 1240 for K = 41, little endian):
+ *   f64 T_pnp[12] | f64 T_ba[12] | i32 crop_id, accepted, n_used, n_ba_inliers | f32 uv[K][2] | f32 cov[K][4] |
+ *   u8 flags[K] (bit 0 = keypoint passed the gate, bit 1 = BA inlier) | zero padding to a multiple of 8 bytes. */
+size_t suo_record_bytes(int num_kp);
+/* Packs the outputs of suo_frames / suo_solve_keypoints into records (one device kernel).  crop_ids [L] or NULL
+ * (then crop_id = id_base + index); T_pnp [L,16]; T_ba [L,12], kp_used, ba_inliers, uv, cov may be NULL. */
+int suo_pack_records(suo_ctx* ctx, const int32_t* crop_ids, int id_base, const double* T_pnp, const double* T_ba,
+                     const uint8_t* kp_used, const uint8_t* ba_inliers, const float* uv, const float* cov, int L,
+                     void* records, int on_device, void* stream);
+/* ncclAllGather of n_local records per rank on `stream` (device pointers; `nccl_comm` is the caller's ncclComm_t;
+ * `out` holds world_size * n_local records, rank-major).  The library calls the NCCL the process has already loaded
+ * (dlopen of libnccl.so.2): it does not link NCCL itself.  Every rank passes the same n_local (pad with crop_id -1). */
+int suo_allgather_results(suo_ctx* ctx, void* nccl_comm, const void* records, size_t rec_bytes, int n_local,
+                          void* out, void* stream);
 
 /* ---- measurement ----------------------------------------------------------------- */
 /* Per-op CUDA-event timing of the network program on the current input buffer (eager launches):

@@ -25,7 +25,9 @@ def exported_symbols():
     return ["suo_create", "suo_destroy", "suo_last_error", "suo_set_option", "suo_kernel_launches",
             "suo_load_weights", "suo_forward", "suo_heatmap_reduce", "suo_crop_concat", "suo_conv2d",
             "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range",
-            "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts", "suo_frames_u8"]
+            "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts", "suo_frames_u8",
+            "suo_ba_last_errors", "suo_edge_linearize", "suo_frames_u8_submit", "suo_frames_wait", "suo_record_bytes",
+            "suo_pack_records", "suo_allgather_results"]
 
 
 def lib():
@@ -61,6 +63,15 @@ def lib():
                                  C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [C.c_int, vp]
         L.suo_frames_u8.argtypes = L.suo_frames.argtypes
         L.suo_check_range.argtypes = [vp]
+        L.suo_ba_last_errors.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+        L.suo_edge_linearize.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+        L.suo_frames_u8_submit.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double,
+                                           C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [vp]
+        L.suo_frames_wait.argtypes = [vp, C.c_int]
+        L.suo_record_bytes.argtypes = [C.c_int]
+        L.suo_record_bytes.restype = C.c_size_t
+        L.suo_pack_records.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]
+        L.suo_allgather_results.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, vp, vp]
         L.suo_profile_network.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), vp]
         _lib = L
     return _lib

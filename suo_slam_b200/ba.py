@@ -14,7 +14,9 @@ CHI2_GATE = 5.991                     # object_slam.py:860,886
 
 
 def ba_batch(prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its,
-             huber_delta=HUBER_DELTA, chi2_gate=CHI2_GATE, init_with_outliers=False, ctx=None):
+             huber_delta=HUBER_DELTA, chi2_gate=CHI2_GATE, init_with_outliers=False, ctx=None, return_errors=False):
+    """return_errors: also return err [n_edges,2], each edge's error as g2o would hold it after optimize() (the error of
+    the last evaluated LM trial, rejected or not — what e.chi2() reads at lib/object_slam.py:881-883)."""
     ctx = ctx or runtime.get_context()
     c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
     prob_vert, prob_edge = c(prob_vert, np.int32), c(prob_edge, np.int32)
@@ -32,6 +34,11 @@ def ba_batch(prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, inf
         _lib.ptr(e_obj), _lib.ptr(e_cam), _lib.ptr(cam_k), _lib.ptr(p), _lib.ptr(uv), _lib.ptr(info), _lib.ptr(inl),
         len(e_cam), _lib.ptr(its), len(its), float(huber_delta), float(chi2_gate), int(init_with_outliers),
         _lib.ptr(stats), 0, None))
+    if return_errors:
+        err = np.zeros((len(e_cam), 2))
+        if len(e_cam):
+            ctx.check(_lib.lib().suo_ba_last_errors(ctx.handle, _lib.ptr(err), len(e_cam), 0, None))
+        return poses.reshape(-1, 3, 4), inl.astype(bool), stats, err
     return poses.reshape(-1, 3, 4), inl.astype(bool), stats
 
 

@@ -15,6 +15,7 @@
 #include <tuple>
 
 #include <cuda.h>
+#include <dlfcn.h>
 
 #include "common.cuh"
 #include "ba_math.cuh"
@@ -159,7 +160,7 @@ struct DevScratch {   // growable device + pinned staging for host-pointer calls
   void* d = nullptr; size_t dn = 0;
   int grow(suo_ctx* ctx, size_t n) {
     if (n <= dn) return SUO_OK;
-    if (d) cudaFree(d);
+    if (d) { cudaDeviceSynchronize(); cudaFree(d); }      // enqueued work (asynchronous submits included) may still use the old block
     dn = 0; d = nullptr;
     SUO_CUDA_TRY(ctx, cudaMalloc(&d, n));
     dn = n;
@@ -176,6 +177,18 @@ struct CtxExtra {
   int32_t* pnp_off = nullptr;   // row offsets c * num_kp of the gated keypoint lists (grown on demand)
   int pnp_off_n = 0;
   bool loaded = false;
+  // double-buffered asynchronous frame batches (suo_frames_u8_submit / suo_frames_wait): per slot the staged inputs and
+  // results and two events; one copy stream shared by the slots so that the host->device copy of batch i+1 overlaps batch i
+  struct FrameSlot {
+    DevScratch in, out;
+    cudaEvent_t h2d_done = nullptr, done = nullptr;
+    bool pending = false;
+  } slot[2];
+  cudaStream_t copy_stream = nullptr;
+  // NCCL entry point for suo_allgather_results, resolved at first use from the libnccl the process already loaded
+  void* nccl_allgather = nullptr;
+  const double* last_err = nullptr;   // per-edge errors left by the most recent suo_ba_batch (device, inside `ba`)
+  int last_err_n = 0;
 };
 
 CtxExtra* X(suo_ctx* c) { return reinterpret_cast<CtxExtra*>(c->net); }
@@ -484,6 +497,13 @@ void suo_destroy(suo_ctx* ctx) {
     if (N.pool) cudaFree(N.pool);
     if (N.pooled) cudaFree(N.pooled);
     if (N.d_uv) cudaFree(N.d_uv);
+    for (auto& sl : x->slot) {
+      if (sl.in.d) cudaFree(sl.in.d);
+      if (sl.out.d) cudaFree(sl.out.d);
+      if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+      if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->io.d) cudaFree(x->io.d);
     if (x->ba.d) cudaFree(x->ba.d);
     if (x->fr.d) cudaFree(x->fr.d);
@@ -1197,6 +1217,7 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   if (rc) return rc;
   Bump sb{static_cast<uint8_t*>(x->ba.d)};
   double* d_err = sb.take<double>(2 * (size_t)n_edges);
+  x->last_err = d_err; x->last_err_n = n_edges;
   uint8_t* d_level = sb.take<uint8_t>(n_edges);
   int8_t* d_fv = sb.take<int8_t>(n_edges);
   auto base_args = [&](const int32_t* pv, const int32_t* pe, double* po, const uint8_t* fx, const int32_t* eo, const int32_t* ec,
@@ -1413,11 +1434,12 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
                        int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
                        const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
                        double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
-                       int on_device, void* stream) {
+                       int on_device, void* stream, int slot = -1) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
   if (!x->loaded) { ctx->set_error("suo_frames before suo_load_weights", __FILE__, __LINE__); return SUO_E_STATE; }
+  if (slot >= 0 && (slot > 1 || on_device)) { ctx->set_error("suo_frames_u8_submit: slot must be 0 or 1", __FILE__, __LINE__); return SUO_E_INVALID; }
   if (L <= 0 || L > ctx->max_crops || n_img <= 0 || !images || !boxes || !box_img || !model_kps || !model_mask || !K_bbox || !diameter) {
     ctx->set_error("suo_frames: bad crop count / null input", __FILE__, __LINE__);
     return SUO_E_INVALID;
@@ -1427,10 +1449,29 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   const int K = ctx->num_kp, R = ctx->crop_res;
   const size_t LK = (size_t)L * K, n_im = (size_t)n_img * 3 * H * W, n_pr = priors ? LK * R * R : 0;
   size_t bytes = solve_workspace_bytes(L, K, n_img) + LK * 64;
-  if (!on_device) bytes += (n_im + n_pr) * sizeof(float) + 4096;
+  const size_t in_bytes = (n_im + n_pr) * sizeof(float) + LK * 25 + (size_t)L * 100 + 16 * 256;
+  if (!on_device && slot < 0) bytes += in_bytes;
   rc = x->fr.grow(ctx, bytes);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->fr.d)};
+  // asynchronous submit: inputs are staged in the slot's own block by the copy stream; `s` waits for them
+  CtxExtra::FrameSlot* sl = slot >= 0 ? &x->slot[slot] : nullptr;
+  Bump ip = bp;
+  cudaStream_t cs = s;
+  if (sl) {
+    if (sl->pending) { ctx->set_error("suo_frames_u8_submit: slot still pending (call suo_frames_wait first)", __FILE__, __LINE__); return SUO_E_STATE; }
+    if (!x->copy_stream) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    if (!sl->h2d_done) {
+      SUO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming));
+      SUO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
+    }
+    rc = sl->in.grow(ctx, in_bytes);
+    if (!rc) rc = sl->out.grow(ctx, (size_t)L * (16 + 12) * 8 + LK * (2 + 24) + 8 * 256);
+    if (rc) return rc;
+    ip = Bump{static_cast<uint8_t*>(sl->in.d)};
+    cs = x->copy_stream;
+    // the slot's previous batch (its compute read this staging block) has finished: suo_frames_wait synchronised on `done`
+  }
   const void* d_im = images;
   const float *d_box = boxes, *d_pr = priors;
   const int32_t* d_bi = box_img;
@@ -1438,24 +1479,33 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   const uint8_t* d_mm = model_mask;
   if (!on_device) {
     for (int c = 1; c < L; ++c) if (box_img[c] < box_img[c - 1]) { ctx->set_error("suo_frames: box_img must be sorted", __FILE__, __LINE__); return SUO_E_INVALID; }
-    float* a = bp.take<float>(n_im); float* b = bp.take<float>(4 * (size_t)L); int32_t* c = bp.take<int32_t>(L);
-    float* d = priors ? bp.take<float>(n_pr) : nullptr;
-    double* e = bp.take<double>(3 * LK); uint8_t* f = bp.take<uint8_t>(LK); double* g = bp.take<double>(9 * (size_t)L); double* h = bp.take<double>(L);
-#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+    Bump& q = sl ? ip : bp;
+    float* a = q.take<float>(n_im); float* b = q.take<float>(4 * (size_t)L); int32_t* c = q.take<int32_t>(L);
+    float* d = priors ? q.take<float>(n_pr) : nullptr;
+    double* e = q.take<double>(3 * LK); uint8_t* f = q.take<uint8_t>(LK); double* g = q.take<double>(9 * (size_t)L); double* h = q.take<double>(L);
+#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, cs))
     H2D(a, images, n_im * (images_u8 ? 1 : 4)); H2D(b, boxes, 16 * (size_t)L); H2D(c, box_img, 4 * (size_t)L);
     if (d) H2D(d, priors, n_pr * 4);
     H2D(e, model_kps, 24 * LK); H2D(f, model_mask, LK); H2D(g, K_bbox, 72 * (size_t)L); H2D(h, diameter, 8 * (size_t)L);
 #undef H2D
     d_im = a; d_box = b; d_bi = c; d_pr = d; d_mk = e; d_mm = f; d_kb = g; d_diam = h;
+    if (sl) {
+      SUO_CUDA_TRY(ctx, cudaEventRecord(sl->h2d_done, cs));
+      SUO_CUDA_TRY(ctx, cudaStreamWaitEvent(s, sl->h2d_done, 0));
+    }
   }
   // forward (device path): results land in the executor's own uv / cov / mask buffers
   rc = forward_impl(ctx, d_im, n_img, H, W, d_box, d_bi, L, d_pr, nullptr, nullptr, N.d_uv, N.d_cov, nullptr, nullptr, N.d_mask_logits,
                     N.d_mask, N.d_argmax, 1, stream, images_u8);
   if (rc) return rc;
-  double* d_Tpnp = (on_device && T_pnp) ? T_pnp : bp.take<double>(16 * (size_t)L);
-  double* d_Tba = (on_device && T_ba) ? T_ba : bp.take<double>(12 * (size_t)L);
-  uint8_t* d_used = (on_device && kp_used) ? kp_used : bp.take<uint8_t>(LK);
-  uint8_t* d_bain = (on_device && ba_inliers) ? ba_inliers : bp.take<uint8_t>(LK);
+  Bump op = sl ? Bump{static_cast<uint8_t*>(sl->out.d)} : bp;      // (a slot keeps its results in its own block until suo_frames_wait)
+  Bump& ob = sl ? op : bp;
+  double* d_Tpnp = (on_device && T_pnp) ? T_pnp : ob.take<double>(16 * (size_t)L);
+  double* d_Tba = (on_device && T_ba) ? T_ba : ob.take<double>(12 * (size_t)L);
+  uint8_t* d_used = (on_device && kp_used) ? kp_used : ob.take<uint8_t>(LK);
+  uint8_t* d_bain = (on_device && ba_inliers) ? ba_inliers : ob.take<uint8_t>(LK);
+  float* d_uvo = sl ? ob.take<float>(2 * LK) : N.d_uv;
+  float* d_covo = sl ? ob.take<float>(4 * LK) : N.d_cov;
   rc = solve_keypoints_device(ctx, bp, N.d_uv, N.d_cov, N.d_mask, d_bi, n_img, L, d_mk, d_mm, d_kb, d_diam, kp_var_thresh,
                               bbox_thresh, seed, run_ba, d_Tpnp, d_Tba, d_used, d_bain, s);
   if (rc) return rc;
@@ -1464,13 +1514,22 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
     if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(cov, N.d_cov, LK * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return SUO_OK;
   }
+  if (sl) {     // the next batch's forward overwrites the executor's uv / cov: keep this batch's copy in the slot
+    if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_uvo, N.d_uv, LK * 8, cudaMemcpyDeviceToDevice, s));
+    if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_covo, N.d_cov, LK * 16, cudaMemcpyDeviceToDevice, s));
+  }
 #define D2H(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, s))
   D2H(T_pnp, d_Tpnp, 128 * (size_t)L); D2H(kp_used, d_used, LK);
-  D2H(uv, N.d_uv, LK * 8); D2H(cov, N.d_cov, LK * 16);
+  D2H(uv, d_uvo, LK * 8); D2H(cov, d_covo, LK * 16);
   if (run_ba) { D2H(T_ba, d_Tba, 96 * (size_t)L); D2H(ba_inliers, d_bain, LK); }
 #undef D2H
+  if (sl) {
+    SUO_CUDA_TRY(ctx, cudaEventRecord(sl->done, s));
+    sl->pending = true;
+    return SUO_OK;
+  }
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
-  return SUO_OK;
+  return suo_check_range(ctx);      // fp16x3: an activation outside the FP16 range invalidates the keypoints and poses
 }
 
 int suo_frames(suo_ctx* ctx, const float* images, int n_img, int H, int W, const float* boxes, const int32_t* box_img,
@@ -1489,6 +1548,120 @@ int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int
                   int on_device, void* stream) {
   return frames_impl(ctx, images_hwc, 1, n_img, H, W, boxes, box_img, L, priors, model_kps, model_mask, K_bbox, diameter, kp_var_thresh,
                      bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, on_device, stream);
+}
+
+int suo_ba_last_errors(suo_ctx* ctx, double* err, int n_edges, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!err || n_edges <= 0 || n_edges != x->last_err_n || !x->last_err) { ctx->set_error("suo_ba_last_errors: no suo_ba_batch result with this edge count", __FILE__, __LINE__); return SUO_E_STATE; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(err, x->last_err, 16 * (size_t)n_edges, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  if (!on_device) SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const double* T_cam, const double* cam_k, const double* p,
+                       const double* uv, double* err, double* J_obj, double* J_cam, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (n_edges <= 0 || !T_cam || !cam_k || !p || !uv) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (on_device) return launch_edge_linearize(ctx, n_edges, T_obj, T_cam, cam_k, p, uv, err, J_obj, J_cam, s);
+  CtxExtra* x = X(ctx);
+  const size_t n = (size_t)n_edges;
+  rc = x->io.grow(ctx, n * 8 * (12 + 12 + 4 + 3 + 2 + 2 + 12 + 12) + 16 * 256);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  double* d_to = T_obj ? bp.take<double>(12 * n) : nullptr; double* d_tc = bp.take<double>(12 * n);
+  double* d_k = bp.take<double>(4 * n); double* d_p = bp.take<double>(3 * n); double* d_uv = bp.take<double>(2 * n);
+  double* d_e = bp.take<double>(2 * n); double* d_jo = bp.take<double>(12 * n); double* d_jc = bp.take<double>(12 * n);
+#define H2D(dst, src, k) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (k), cudaMemcpyHostToDevice, s))
+  H2D(d_to, T_obj, 96 * n); H2D(d_tc, T_cam, 96 * n); H2D(d_k, cam_k, 32 * n); H2D(d_p, p, 24 * n); H2D(d_uv, uv, 16 * n);
+#undef H2D
+  rc = launch_edge_linearize(ctx, n_edges, d_to, d_tc, d_k, d_p, d_uv, d_e, d_jo, d_jc, s);
+  if (rc) return rc;
+  if (err) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(err, d_e, 16 * n, cudaMemcpyDeviceToHost, s));
+  if (J_obj && T_obj) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(J_obj, d_jo, 96 * n, cudaMemcpyDeviceToHost, s));
+  if (J_cam) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(J_cam, d_jc, 96 * n, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W, const float* boxes,
+                         const int32_t* box_img, int L, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
+                         const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
+                         double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov, void* stream) {
+  if (slot < 0) return SUO_E_INVALID;
+  return frames_impl(ctx, images_hwc, 1, n_img, H, W, boxes, box_img, L, nullptr, model_kps, model_mask, K_bbox, diameter, kp_var_thresh,
+                     bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, 0, stream, slot);
+}
+
+int suo_frames_wait(suo_ctx* ctx, int slot) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (slot < 0 || slot > 1) return SUO_E_INVALID;
+  CtxExtra::FrameSlot& sl = X(ctx)->slot[slot];
+  if (!sl.pending) { ctx->set_error("suo_frames_wait: nothing submitted on this slot", __FILE__, __LINE__); return SUO_E_STATE; }
+  SUO_CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
+  sl.pending = false;
+  return suo_check_range(ctx);
+}
+
+// ---- result records + the single exchange of the multi-GPU path -------------------------------------------------
+size_t suo_record_bytes(int num_kp) { return num_kp > 0 ? (size_t)208 + 24 * (size_t)num_kp + (((size_t)num_kp + 7) & ~(size_t)7) : 0; }
+
+int suo_pack_records(suo_ctx* ctx, const int32_t* crop_ids, int id_base, const double* T_pnp, const double* T_ba,
+                     const uint8_t* kp_used, const uint8_t* ba_inliers, const float* uv, const float* cov, int L,
+                     void* records, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (L <= 0 || !T_pnp || !records) return SUO_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int K = ctx->num_kp;
+  const int rb = (int)suo_record_bytes(K);
+  if (on_device)
+    return launch_pack_records(ctx, crop_ids, id_base, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, L, K, rb, static_cast<uint8_t*>(records), s);
+  CtxExtra* x = X(ctx);
+  const size_t LK = (size_t)L * K;
+  rc = x->io.grow(ctx, (size_t)L * (4 + 28 * 8 + rb) + LK * 26 + 16 * 256);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->io.d)};
+  int32_t* d_id = crop_ids ? bp.take<int32_t>(L) : nullptr;
+  double* d_tp = bp.take<double>(16 * (size_t)L); double* d_tb = T_ba ? bp.take<double>(12 * (size_t)L) : nullptr;
+  uint8_t* d_u = kp_used ? bp.take<uint8_t>(LK) : nullptr; uint8_t* d_b = ba_inliers ? bp.take<uint8_t>(LK) : nullptr;
+  float* d_uv = uv ? bp.take<float>(2 * LK) : nullptr; float* d_cov = cov ? bp.take<float>(4 * LK) : nullptr;
+  uint8_t* d_rec = bp.take<uint8_t>((size_t)L * rb);
+#define H2D(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
+  H2D(d_id, crop_ids, 4 * (size_t)L); H2D(d_tp, T_pnp, 128 * (size_t)L); H2D(d_tb, T_ba, 96 * (size_t)L);
+  H2D(d_u, kp_used, LK); H2D(d_b, ba_inliers, LK); H2D(d_uv, uv, 8 * LK); H2D(d_cov, cov, 16 * LK);
+#undef H2D
+  rc = launch_pack_records(ctx, d_id, id_base, d_tp, d_tb, d_u, d_b, d_uv, d_cov, L, K, rb, d_rec, s);
+  if (rc) return rc;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(records, d_rec, (size_t)L * rb, cudaMemcpyDeviceToHost, s));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return SUO_OK;
+}
+
+int suo_allgather_results(suo_ctx* ctx, void* nccl_comm, const void* records, size_t rec_bytes, int n_local, void* out, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if (!nccl_comm || !records || !out || n_local <= 0 || rec_bytes == 0) return SUO_E_INVALID;
+  CtxExtra* x = X(ctx);
+  if (!x->nccl_allgather) {
+    // the communicator was created by the caller's NCCL: use that same library (already loaded), never a second copy
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+    x->nccl_allgather = h ? dlsym(h, "ncclAllGather") : nullptr;
+    if (!x->nccl_allgather) { ctx->set_error("suo_allgather_results: libnccl.so.2 / ncclAllGather not found", __FILE__, __LINE__); return SUO_E_STATE; }
+  }
+  // ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t, ncclComm_t, cudaStream_t); ncclChar = 0
+  typedef int (*AllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+  const int r = reinterpret_cast<AllGatherFn>(x->nccl_allgather)(records, out, rec_bytes * (size_t)n_local, 0, nccl_comm, static_cast<cudaStream_t>(stream));
+  if (r != 0) { ctx->set_error("ncclAllGather failed: ncclResult_t " + std::to_string(r), __FILE__, __LINE__); return SUO_E_CUDA; }
+  ctx->launches++;
+  return SUO_OK;
 }
 
 // Per-op device timing of the network program (eager launches, one CUDA event pair per op) on

@@ -46,6 +46,7 @@ ba_kernel(const BaArgs a) {
   __shared__ SE3q est[BA_MAXV], bak[BA_MAXV];
   __shared__ double Hs[BA_MAXV][36], bs[BA_MAXV][6], xsol[BA_MAXV][6];
   __shared__ uint8_t vact[BA_MAXV], vok[BA_MAXV];
+  __shared__ int vfirst[BA_MAXV], vlast[BA_MAXV];      // edge range that holds every edge whose free vertex is v (exact when the edges are grouped by vertex)
   __shared__ double red[BA_WARPS];
   __shared__ double s_lambda, s_ni, s_cur, s_rho;
   __shared__ int s_flag, s_bad;
@@ -64,6 +65,8 @@ ba_kernel(const BaArgs a) {
     const double t[3] = {T[3], T[7], T[11]};
     se3_from_Rt(R, t, est[v]);
   }
+  for (int v = tid; v < nv; v += BA_THREADS) { vfirst[v] = 0x7fffffff; vlast[v] = -1; }
+  __syncthreads();
   // which vertex of each edge is free
   for (int e = tid; e < ne; e += BA_THREADS) {
     const int ge = e0 + e;
@@ -74,6 +77,7 @@ ba_kernel(const BaArgs a) {
     else if (fo) k = 0;
     else if (fc) k = 1;
     a.fv_kind[ge] = k;
+    if (k >= 0) { const int fv = (k == 0 ? vo : vc) - v0; atomicMin(&vfirst[fv], e); atomicMax(&vlast[fv], e); }
   }
   __syncthreads();
   if (s_bad) { if (tid == 0 && a.stats) { a.stats[3 * prob] = -2; a.stats[3 * prob + 1] = 0; a.stats[3 * prob + 2] = 0; } return; }
@@ -144,7 +148,7 @@ ba_kernel(const BaArgs a) {
 #pragma unroll
           for (int k = 0; k < 27; ++k) acc[k] = 0;
           if (vact[v]) {
-            for (int e = lane; e < ne; e += 32) {
+            for (int e = vfirst[v] + lane; e <= vlast[v]; e += 32) {
               const int ge = e0 + e;
               if (!is_active(ge)) continue;
               const int fvert = (a.fv_kind[ge] == 0 ? a.e_obj[ge] : a.e_cam[ge]) - v0;
@@ -155,31 +159,11 @@ ba_kernel(const BaArgs a) {
               const SE3q& Tcw = est[a.e_cam[ge] - v0];
               se3_map(Tcw, pw, pc);
               const double* k = a.cam_k + 4 * ge;
-              const double iz = 1.0 / pc[2];
-              double pj[6] = {-(k[0] * iz), 0.0, k[0] * pc[0] * iz * iz, 0.0, -(k[1] * iz), k[1] * pc[1] * iz * iz};
-              double J[12];
-              const double* q = pc;
-              if (a.fv_kind[ge] == 0) {   // Jacobian wrt the object: projectJac * R_cw * [-[p_W]x | I]
-                double Rcw[9];
-                se3_R(Tcw, Rcw);
-                double pr[6];
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                  for (int c = 0; c < 3; ++c) pr[3 * r + c] = pj[3 * r] * Rcw[c] + pj[3 * r + 1] * Rcw[3 + c] + pj[3 * r + 2] * Rcw[6 + c];
-#pragma unroll
-                for (int c = 0; c < 6; ++c) pj[c] = pr[c];
-                q = pw;
-              }
-              // [ -[q]x | I ] = [[0, z, -y, 1,0,0],[-z, 0, x, 0,1,0],[y, -x, 0, 0,0,1]]
-#pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                const double p0 = pj[3 * r], p1 = pj[3 * r + 1], p2 = pj[3 * r + 2];
-                J[6 * r + 0] = -p1 * q[2] + p2 * q[1];
-                J[6 * r + 1] = p0 * q[2] - p2 * q[0];
-                J[6 * r + 2] = -p0 * q[1] + p1 * q[0];
-                J[6 * r + 3] = p0; J[6 * r + 4] = p1; J[6 * r + 5] = p2;
-              }
+              double J[12], Jx[12];
+              double Rcw[9];
+              se3_R(Tcw, Rcw);
+              const bool wrt_obj = a.fv_kind[ge] == 0;
+              edge_jacobians(Rcw, pw, pc, k, wrt_obj, !wrt_obj, wrt_obj ? J : Jx, wrt_obj ? Jx : J);
               const double* O = a.info + 4 * ge;
               const double r0 = a.err[2 * ge], r1 = a.err[2 * ge + 1];
               double w = 1.0;
@@ -303,7 +287,46 @@ ba_kernel(const BaArgs a) {
   if (tid == 0 && a.stats) { a.stats[3 * prob] = rounds; a.stats[3 * prob + 1] = outer_total; a.stats[3 * prob + 2] = trials_total; }
 }
 
+// error and both Jacobians of independent edges at given vertex poses (suo_edge_linearize): the device functions the LM
+// kernels use, exposed so that tests can compare them with central differences (the recipe left commented out in
+// types_object_slam.cpp:108-122).
+__global__ void edge_linearize_kernel(int n, const double* __restrict__ T_obj, const double* __restrict__ T_cam,
+                                      const double* __restrict__ cam_k, const double* __restrict__ p, const double* __restrict__ uv,
+                                      double* __restrict__ err, double* __restrict__ J_obj, double* __restrict__ J_cam) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  auto load = [](const double* T, SE3q& o) {
+    const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+    const double t[3] = {T[3], T[7], T[11]};
+    se3_from_Rt(R, t, o);
+  };
+  SE3q To, Tc;
+  load(T_cam + 12 * (size_t)e, Tc);
+  double pw[3] = {p[3 * e], p[3 * e + 1], p[3 * e + 2]}, pc[3];
+  if (T_obj) { load(T_obj + 12 * (size_t)e, To); double tmp[3]; se3_map(To, pw, tmp); pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; }
+  se3_map(Tc, pw, pc);
+  const double* k = cam_k + 4 * e;
+  if (err) {
+    err[2 * e] = uv[2 * e] - (k[0] * pc[0] / pc[2] + k[2]);
+    err[2 * e + 1] = uv[2 * e + 1] - (k[1] * pc[1] / pc[2] + k[3]);
+  }
+  double Rcw[9], Ji[12], Jj[12];
+  se3_R(Tc, Rcw);
+  edge_jacobians(Rcw, pw, pc, k, T_obj != nullptr && J_obj != nullptr, J_cam != nullptr, Ji, Jj);
+  if (T_obj && J_obj) for (int q = 0; q < 12; ++q) J_obj[12 * (size_t)e + q] = Ji[q];
+  if (J_cam) for (int q = 0; q < 12; ++q) J_cam[12 * (size_t)e + q] = Jj[q];
+}
+
 }  // namespace
+
+int launch_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const double* T_cam, const double* cam_k, const double* p,
+                          const double* uv, double* err, double* J_obj, double* J_cam, cudaStream_t s) {
+  if (n_edges <= 0) return SUO_OK;
+  edge_linearize_kernel<<<(n_edges + 127) / 128, 128, 0, s>>>(n_edges, T_obj, T_cam, cam_k, p, uv, err, J_obj, J_cam);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
+}
 
 int launch_ba_kernel(suo_ctx* ctx, int n_prob, const BaArgs& args, cudaStream_t s) {
   if (n_prob <= 0) return SUO_OK;

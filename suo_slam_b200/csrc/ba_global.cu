@@ -189,30 +189,7 @@ ba_global_kernel(const BgArgs a) {
               pc[1] = Rcw[3] * pw[0] + Rcw[4] * pw[1] + Rcw[5] * pw[2] + Tcw.t[1];
               pc[2] = Rcw[6] * pw[0] + Rcw[7] * pw[1] + Rcw[8] * pw[2] + Tcw.t[2];
               const double* k = g.cam_k + 4 * ge;
-              const double iz = 1.0 / pc[2];
-              const double pj[6] = {-(k[0] * iz), 0.0, k[0] * pc[0] * iz * iz, 0.0, -(k[1] * iz), k[1] * pc[1] * iz * iz};
-              if (fc) {   // wrt the camera: projectJac * [-[p_C]x | I]
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  const double q0 = pj[3 * r], q1 = pj[3 * r + 1], q2 = pj[3 * r + 2];
-                  Jj[6 * r + 0] = -q1 * pc[2] + q2 * pc[1];
-                  Jj[6 * r + 1] = q0 * pc[2] - q2 * pc[0];
-                  Jj[6 * r + 2] = -q0 * pc[1] + q1 * pc[0];
-                  Jj[6 * r + 3] = q0; Jj[6 * r + 4] = q1; Jj[6 * r + 5] = q2;
-                }
-              }
-              if (fo) {   // wrt the object: projectJac * R_cw * [-[p_W]x | I]
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  const double q0 = pj[3 * r] * Rcw[0] + pj[3 * r + 1] * Rcw[3] + pj[3 * r + 2] * Rcw[6];
-                  const double q1 = pj[3 * r] * Rcw[1] + pj[3 * r + 1] * Rcw[4] + pj[3 * r + 2] * Rcw[7];
-                  const double q2 = pj[3 * r] * Rcw[2] + pj[3 * r + 1] * Rcw[5] + pj[3 * r + 2] * Rcw[8];
-                  Ji[6 * r + 0] = -q1 * pw[2] + q2 * pw[1];
-                  Ji[6 * r + 1] = q0 * pw[2] - q2 * pw[0];
-                  Ji[6 * r + 2] = -q0 * pw[1] + q1 * pw[0];
-                  Ji[6 * r + 3] = q0; Ji[6 * r + 4] = q1; Ji[6 * r + 5] = q2;
-                }
-              }
+              edge_jacobians(Rcw, pw, pc, k, fo, fc, Ji, Jj);
               const double* O = g.info + 4 * ge;
               const double r0 = g.err[2 * ge], r1 = g.err[2 * ge + 1];
               double w = 1.0;

@@ -77,6 +77,40 @@ __device__ inline void se3_oplus(const SE3q& T, const double* u, SE3q& out) {   
   out.qx = x / n; out.qy = y / n; out.qz = z / n; out.qw = w / n;
 }
 
+// linearizeOplus of both edge types (types_object_slam.cpp:70-123: EdgeSE3ProjectFromObject, :177-201:
+// EdgeSE3ProjectFromFixedObject).  Rcw = rotation of the camera vertex, pw = the keypoint in the world / camera-fixed frame
+// (T_wo * p_O, or p_inG for the unary edge), pc = T_cw * pw, k = {fx, fy, cx, cy}.  Tangent order (omega, upsilon).
+//   Ji [2x6] wrt the object vertex: projectJac * R_cw * [-[p_W]x | I]      (want_obj)
+//   Jj [2x6] wrt the camera vertex: projectJac * [-[p_C]x | I]             (want_cam)
+// with projectJac = -[[fx/z, 0, -fx x/z^2], [0, fy/z, -fy y/z^2]] at p_C.
+__device__ __forceinline__ void edge_jacobians(const double* Rcw, const double* pw, const double* pc, const double* k,
+                                               bool want_obj, bool want_cam, double* Ji, double* Jj) {
+  const double iz = 1.0 / pc[2];
+  const double pj[6] = {-(k[0] * iz), 0.0, k[0] * pc[0] * iz * iz, 0.0, -(k[1] * iz), k[1] * pc[1] * iz * iz};
+  if (want_cam) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double q0 = pj[3 * r], q1 = pj[3 * r + 1], q2 = pj[3 * r + 2];
+      Jj[6 * r + 0] = -q1 * pc[2] + q2 * pc[1];
+      Jj[6 * r + 1] = q0 * pc[2] - q2 * pc[0];
+      Jj[6 * r + 2] = -q0 * pc[1] + q1 * pc[0];
+      Jj[6 * r + 3] = q0; Jj[6 * r + 4] = q1; Jj[6 * r + 5] = q2;
+    }
+  }
+  if (want_obj) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double q0 = pj[3 * r] * Rcw[0] + pj[3 * r + 1] * Rcw[3] + pj[3 * r + 2] * Rcw[6];
+      const double q1 = pj[3 * r] * Rcw[1] + pj[3 * r + 1] * Rcw[4] + pj[3 * r + 2] * Rcw[7];
+      const double q2 = pj[3 * r] * Rcw[2] + pj[3 * r + 1] * Rcw[5] + pj[3 * r + 2] * Rcw[8];
+      Ji[6 * r + 0] = -q1 * pw[2] + q2 * pw[1];
+      Ji[6 * r + 1] = q0 * pw[2] - q2 * pw[0];
+      Ji[6 * r + 2] = -q0 * pw[1] + q1 * pw[0];
+      Ji[6 * r + 3] = q0; Ji[6 * r + 4] = q1; Ji[6 * r + 5] = q2;
+    }
+  }
+}
+
 __device__ __forceinline__ void huber(double e, double delta, double& rho0, double& rho1) {
   const double dsqr = delta * delta;
   if (e <= dsqr) { rho0 = e; rho1 = 1.0; }
@@ -145,3 +179,6 @@ struct BgArgs {
 }  // namespace ba
 
 int launch_ba_global(suo_ctx* ctx, int n_prob, const ba::BgArgs& args, cudaStream_t s);
+// error + both Jacobians of a batch of edges at given vertex poses (test hook for the linearisation, ba.cu)
+int launch_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const double* T_cam, const double* cam_k, const double* p,
+                          const double* uv, double* err, double* J_obj, double* J_cam, cudaStream_t s);

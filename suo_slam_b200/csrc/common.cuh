@@ -171,6 +171,9 @@ int launch_ba_assemble(suo_ctx* ctx, int n_img, const int32_t* frame_start, cons
 int launch_ba_scatter(suo_ctx* ctx, int n_img, const int32_t* frame_start, const int32_t* edge_cnt, const int32_t* edge_src,
                       const uint8_t* inliers, const double* poses, const uint8_t* accepted, int K, double* T_ba,
                       uint8_t* ba_inliers, cudaStream_t s);
+int launch_pack_records(suo_ctx* ctx, const int32_t* crop_ids, int id_base, const double* T_pnp, const double* T_ba,
+                        const uint8_t* kp_used, const uint8_t* ba_inliers, const float* uv, const float* cov, int L, int K,
+                        int rec_bytes, uint8_t* out, cudaStream_t s);
 int launch_chi2_counts(suo_ctx* ctx, int n_pairs, const double* T, const int32_t* pair_det, const int32_t* det_off,
                        const double* model_kp, const double* K, const float* uv, const float* cov, const uint8_t* use,
                        double manual_kp_std, double gate, int32_t* counts, cudaStream_t s);

@@ -107,31 +107,84 @@ __global__ void ba_assemble_kernel(const int32_t* __restrict__ frame_start, cons
     fixed[c + f] = ok ? 0 : 1;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int ne = 0;
-    const size_t ebase = (size_t)c0 * K;
-    for (int c = c0; c < c1; ++c) {
-      if (!accepted[c]) continue;
-      const double* Kb = K_bbox + 9 * c;
-      for (int j = 0; j < counts[c]; ++j) {
-        const size_t src = (size_t)c * K + j;
-        const int k = kp_index[src];
-        const size_t m = (size_t)c * K + k;
-        const size_t e = ebase + ne;
-        e_obj[e] = c + f; e_cam[e] = vcam;
-        cam_k[4 * e] = Kb[0]; cam_k[4 * e + 1] = Kb[4]; cam_k[4 * e + 2] = Kb[2]; cam_k[4 * e + 3] = Kb[5];   // object_slam.py:799
-        p[3 * e] = xs[3 * src]; p[3 * e + 1] = xs[3 * src + 1]; p[3 * e + 2] = xs[3 * src + 2];
-        uvd[2 * e] = (double)uv[2 * m]; uvd[2 * e + 1] = (double)uv[2 * m + 1];
-        // information = inv(cov) (object_slam.py:825-828, no clamping), cov is the fp32 network output
-        const double s00 = cov[4 * m], s01 = cov[4 * m + 1], s10 = cov[4 * m + 2], s11 = cov[4 * m + 3];
-        const double det = s00 * s11 - s01 * s10;
-        info[4 * e] = s11 / det; info[4 * e + 1] = -s01 / det; info[4 * e + 2] = -s10 / det; info[4 * e + 3] = s00 / det;
-        inliers[e] = 1;
-        edge_src[e] = (int32_t)m;
-        ++ne;
-      }
+  // edges in (crop, gated keypoint) order: thread 0 scans the accepted crops' counts (chunks of kScan crops), then one
+  // thread per (crop, slot) writes its edge
+  constexpr int kScan = 256;
+  __shared__ int s_off[kScan + 1];
+  const size_t ebase = (size_t)c0 * K;
+  for (int cb = c0; cb < c1; cb += kScan) {
+    const int nc = min(kScan, c1 - cb);
+    if (threadIdx.x == 0) {
+      int ne = s_ne;
+      for (int q = 0; q < nc; ++q) { s_off[q] = ne; ne += accepted[cb + q] ? counts[cb + q] : 0; }
+      s_off[nc] = ne;
     }
-    edge_cnt[f] = ne;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nc * K; idx += blockDim.x) {
+      const int q = idx / K, j = idx - q * K, c = cb + q;
+      if (!accepted[c] || j >= counts[c]) continue;
+      const double* Kb = K_bbox + 9 * c;
+      const size_t src = (size_t)c * K + j;
+      const int k = kp_index[src];
+      const size_t m = (size_t)c * K + k;
+      const size_t e = ebase + s_off[q] + j;
+      e_obj[e] = c + f; e_cam[e] = vcam;
+      cam_k[4 * e] = Kb[0]; cam_k[4 * e + 1] = Kb[4]; cam_k[4 * e + 2] = Kb[2]; cam_k[4 * e + 3] = Kb[5];   // object_slam.py:799
+      p[3 * e] = xs[3 * src]; p[3 * e + 1] = xs[3 * src + 1]; p[3 * e + 2] = xs[3 * src + 2];
+      uvd[2 * e] = (double)uv[2 * m]; uvd[2 * e + 1] = (double)uv[2 * m + 1];
+      // information = inv(cov) (object_slam.py:825-828, no clamping), cov is the fp32 network output
+      const double s00 = cov[4 * m], s01 = cov[4 * m + 1], s10 = cov[4 * m + 2], s11 = cov[4 * m + 3];
+      const double det = s00 * s11 - s01 * s10;
+      info[4 * e] = s11 / det; info[4 * e + 1] = -s01 / det; info[4 * e + 2] = -s10 / det; info[4 * e + 3] = s00 / det;
+      inliers[e] = 1;
+      edge_src[e] = (int32_t)m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_ne = s_off[nc];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) edge_cnt[f] = s_ne;
+}
+
+// ---- result records for the all-gather ----
+// One fixed-size record per crop: everything a rank that did not process the crop needs before a step over ALL objects
+// (camera-pose voting lib/object_slam.py:975-1072, joint graph :736-837): both poses, the acceptance flag, the gated
+// keypoints with their covariances and the per-keypoint flags.  Layout (include/suo_b200.h, suo_record_bytes):
+//   f64 T_pnp[12], f64 T_ba[12], i32 crop_id, i32 accepted, i32 n_used, i32 n_ba_inliers, f32 uv[K][2], f32 cov[K][4],
+//   u8 flags[K] (bit 0 = gated in, bit 1 = BA inlier), zero padding to a multiple of 8 bytes.
+__global__ void pack_records_kernel(const int32_t* __restrict__ crop_ids, int id_base, const double* __restrict__ T_pnp,
+                                    const double* __restrict__ T_ba, const uint8_t* __restrict__ kp_used,
+                                    const uint8_t* __restrict__ ba_inliers, const float* __restrict__ uv,
+                                    const float* __restrict__ cov, int K, int rec_bytes, uint8_t* __restrict__ out) {
+  const int c = blockIdx.x;
+  uint8_t* r = out + (size_t)c * rec_bytes;
+  double* rd = reinterpret_cast<double*>(r);
+  int32_t* ri = reinterpret_cast<int32_t*>(r + 192);
+  float* ruv = reinterpret_cast<float*>(r + 208);
+  float* rcov = ruv + 2 * K;
+  uint8_t* rfl = reinterpret_cast<uint8_t*>(rcov + 4 * K);
+  const double* Tp = T_pnp + 16 * (size_t)c;
+  int n_used = 0, n_inl = 0;
+  for (int k = threadIdx.x; k < K; k += 32) {
+    const size_t m = (size_t)c * K + k;
+    const int u = kp_used ? (kp_used[m] != 0) : 0, b = ba_inliers ? (ba_inliers[m] != 0) : 0;
+    n_used += u; n_inl += b;
+    rfl[k] = (uint8_t)(u | (b << 1));
+    ruv[2 * k] = uv ? uv[2 * m] : 0.f; ruv[2 * k + 1] = uv ? uv[2 * m + 1] : 0.f;
+    for (int q = 0; q < 4; ++q) rcov[4 * k + q] = cov ? cov[4 * m + q] : 0.f;
+  }
+  for (int k = K + threadIdx.x; k < rec_bytes - 208 - 24 * K; k += 32) rfl[k] = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { n_used += __shfl_xor_sync(0xffffffffu, n_used, o); n_inl += __shfl_xor_sync(0xffffffffu, n_inl, o); }
+  if (threadIdx.x < 12) {
+    rd[threadIdx.x] = Tp[threadIdx.x];
+    rd[12 + threadIdx.x] = T_ba ? T_ba[12 * (size_t)c + threadIdx.x] : ((threadIdx.x % 5 == 0) ? 1.0 : 0.0);
+  }
+  if (threadIdx.x == 0) {
+    bool ident = true;   // identity == PnP failure (lambdatwist convention, lib/object_slam.py:38-39)
+    for (int q = 0; q < 12; ++q) if (fabs(Tp[q] - ((q % 5 == 0) ? 1.0 : 0.0)) > 1e-8 + ((q % 5 == 0) ? 1e-5 : 0.0)) ident = false;
+    ri[0] = crop_ids ? crop_ids[c] : id_base + c;
+    ri[1] = ident ? 0 : 1; ri[2] = n_used; ri[3] = n_inl;
   }
 }
 
@@ -227,7 +280,7 @@ int launch_ba_assemble(suo_ctx* ctx, int n_img, const int32_t* frame_start, cons
                        const double* T_pnp, int K, double* poses, uint8_t* fixed, int32_t* prob_vert, int32_t* vert_cnt,
                        int32_t* prob_edge, int32_t* edge_cnt, int32_t* e_obj, int32_t* e_cam, double* cam_k, double* p,
                        double* uvd, double* info, uint8_t* inliers, int32_t* edge_src, uint8_t* accepted, cudaStream_t s) {
-  ba_assemble_kernel<<<n_img, 32, 0, s>>>(frame_start, counts, kp_index, xs, uv, cov, K_bbox, diameter, T_pnp, K, poses, fixed,
+  ba_assemble_kernel<<<n_img, 128, 0, s>>>(frame_start, counts, kp_index, xs, uv, cov, K_bbox, diameter, T_pnp, K, poses, fixed,
                                           prob_vert, vert_cnt, prob_edge, edge_cnt, e_obj, e_cam, cam_k, p, uvd, info, inliers,
                                           edge_src, accepted);
   ctx->launches++;
@@ -250,6 +303,16 @@ int launch_chi2_counts(suo_ctx* ctx, int n_pairs, const double* T, const int32_t
   if (n_pairs <= 0) return SUO_OK;
   chi2_count_kernel<<<(n_pairs + 7) / 8, 256, 0, s>>>(T, pair_det, det_off, model_kp, K, uv, cov, use,
                                                       1.0 / (manual_kp_std * manual_kp_std), gate, n_pairs, counts);
+  ctx->launches++;
+  SUO_CUDA_TRY(ctx, cudaGetLastError());
+  return SUO_OK;
+}
+
+int launch_pack_records(suo_ctx* ctx, const int32_t* crop_ids, int id_base, const double* T_pnp, const double* T_ba,
+                        const uint8_t* kp_used, const uint8_t* ba_inliers, const float* uv, const float* cov, int L, int K,
+                        int rec_bytes, uint8_t* out, cudaStream_t s) {
+  if (L <= 0) return SUO_OK;
+  pack_records_kernel<<<L, 32, 0, s>>>(crop_ids, id_base, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, K, rec_bytes, out);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;

@@ -2,12 +2,11 @@
 // 2x2 covariance, hard argmax, channel mean and the keypoint-present classifier.
 // Replaces reference lib/models/pkpnet.py:13-63 (spatial_softmax, mesh_grid,
 // post_process_kp) and :74-78,116-118 (classifier), which materialise
-// [B,K,H,W,2] and [B,K,H,W,2,2] temporaries; here one CTA owns one (b,k) map:
-//   pass 1 (HBM -> registers/L1): max, argmax, sum x           (float4 loads)
-//   pass 2 (L1):                  S = sum e, first moments, optional prob store
-//   pass 3 (L1):                  central second moments
-// The map (16 KB at 64x64) stays in L1 between passes, so DRAM traffic is the
-// algorithmic H*W*4 bytes per map.  HBM-bound: no tensor cores on purpose.
+// [B,K,H,W,2] and [B,K,H,W,2,2] temporaries; here one CTA owns one (b,k) map.
+// 64x64 and 128x128 maps (what the network produces) run heatmap_reduce_reg_kernel: the map is read
+// ONCE into registers and reduced with three barriers.  Other sizes run the generic three-pass kernel
+// (the map stays in L1 between passes).  Either way DRAM traffic is the algorithmic H*W*4 bytes per
+// map.  HBM-bound: no tensor cores on purpose.
 //
 // Grid convention is the reference's TRANSPOSED mesh (pkpnet.py:19-26):
 //   xx[h,w] = r[h], yy[h,w] = -r[w], r[i] = (i + 0.5)/(H/2) - 1.
@@ -119,6 +118,111 @@ heatmap_reduce_kernel(const float* __restrict__ logits, int K, int H, int W, flo
   }
 }
 
+// Register-resident version for the two map sizes the network produces (64x64: NV = 4 float4 per thread, 128x128: NV = 16):
+// ONE global read of the map (all loads of a thread issued back to back), three block reductions of three values each
+// (max / first argmax / plain sum; S, sum e*x, sum e*y; the three central second moments), one barrier per reduction.
+// Same arithmetic per element as the generic kernel above (expf(x - m), moments about the mean), so the two agree to the
+// summation order.
+template <int NV>
+__global__ void __launch_bounds__(kThreads)
+heatmap_reduce_reg_kernel(const float* __restrict__ logits, int H, int W, float* __restrict__ pooled,
+                          float* __restrict__ uv, float* __restrict__ cov, float* __restrict__ prob,
+                          int32_t* __restrict__ argmax) {
+  constexpr int NW = kThreads / 32;
+  __shared__ float r1[3][NW];
+  __shared__ int r1i[NW];
+  __shared__ float r2[3][NW];
+  __shared__ float r3[3][NW];
+  const int map = blockIdx.x;  // b*K + k
+  const int HW = H * W;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(logits + (size_t)map * HW);
+  const float inv_half = 1.0f / (0.5f * (float)H);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+  float e[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 v = __ldg(x4 + threadIdx.x + j * kThreads);
+    e[j][0] = v.x; e[j][1] = v.y; e[j][2] = v.z; e[j][3] = v.w;
+  }
+  // ---- reduction 1: max / first argmax / plain sum ---------------------------------
+  float m = -INFINITY, s = 0.f;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s += e[j][q];
+      if (e[j][q] > m) { m = e[j][q]; mi = 4 * (threadIdx.x + j * kThreads) + q; }   // ascending index per thread => first occurrence
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  s = warp_sum(s);
+  if (lane == 0) { r1[0][wid] = m; r1i[wid] = mi; r1[1][wid] = s; }
+  __syncthreads();
+  m = r1[0][0]; mi = r1i[0];
+  float total = r1[1][0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) {
+    if (r1[0][w] > m || (r1[0][w] == m && r1i[w] < mi)) { m = r1[0][w]; mi = r1i[w]; }
+    total += r1[1][w];
+  }
+  // ---- reduction 2: normaliser and first moments ------------------------------------
+  float S = 0.f, sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int idx = 4 * (threadIdx.x + j * kThreads);
+    const int h = idx / W, w0 = idx - h * W;      // W % 4 == 0 => the 4 elements share a row
+    const float gx = ((float)h + 0.5f) * inv_half - 1.0f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float gy = -(((float)(w0 + q) + 0.5f) * inv_half - 1.0f);
+      e[j][q] = expf(e[j][q] - m);
+      S += e[j][q]; sx += e[j][q] * gx; sy += e[j][q] * gy;
+    }
+  }
+  S = warp_sum(S); sx = warp_sum(sx); sy = warp_sum(sy);
+  if (lane == 0) { r2[0][wid] = S; r2[1][wid] = sx; r2[2][wid] = sy; }
+  __syncthreads();
+  S = 0.f; sx = 0.f; sy = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) { S += r2[0][w]; sx += r2[1][w]; sy += r2[2][w]; }
+  const float invS = 1.0f / S;
+  const float u = sx * invS, vv = sy * invS;
+  // ---- reduction 3: central second moments (+ optional prob store) -------------------
+  float cxx = 0.f, cxy = 0.f, cyy = 0.f;
+  float4* __restrict__ p4 = prob ? reinterpret_cast<float4*>(prob + (size_t)map * HW) : nullptr;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int idx = 4 * (threadIdx.x + j * kThreads);
+    const int h = idx / W, w0 = idx - h * W;
+    const float dx = (((float)h + 0.5f) * inv_half - 1.0f) - u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float dy = -(((float)(w0 + q) + 0.5f) * inv_half - 1.0f) - vv;
+      e[j][q] *= invS;
+      cxx += e[j][q] * dx * dx; cxy += e[j][q] * dx * dy; cyy += e[j][q] * dy * dy;
+    }
+    if (p4) p4[threadIdx.x + j * kThreads] = make_float4(e[j][0], e[j][1], e[j][2], e[j][3]);
+  }
+  cxx = warp_sum(cxx); cxy = warp_sum(cxy); cyy = warp_sum(cyy);
+  if (lane == 0) { r3[0][wid] = cxx; r3[1][wid] = cxy; r3[2][wid] = cyy; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cxx = 0.f; cxy = 0.f; cyy = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { cxx += r3[0][w]; cxy += r3[1][w]; cyy += r3[2][w]; }
+    if (uv) { uv[2 * map] = u; uv[2 * map + 1] = vv; }
+    if (cov) { cov[4 * map] = cxx; cov[4 * map + 1] = cxy; cov[4 * map + 2] = cxy; cov[4 * map + 3] = cyy; }
+    if (argmax) argmax[map] = mi;
+    if (pooled) pooled[map] = total / (float)HW;
+  }
+}
+
 // kp_mask_logits = W * relu(mean_hw(raw)) + b ; kp_mask = sigmoid (pkpnet.py:74-78,116-118)
 __global__ void classifier_kernel(const float* __restrict__ pooled, const float* __restrict__ Wc,
                                   const float* __restrict__ bc, int K, float* __restrict__ mask_logits,
@@ -141,7 +245,12 @@ int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H
     ctx->set_error("heatmap_reduce: need square maps with W % 4 == 0", __FILE__, __LINE__);
     return SUO_E_INVALID;
   }
-  heatmap_reduce_kernel<<<B * K, kThreads, 0, s>>>(logits, K, H, W, pooled_scratch, uv, cov, prob, argmax);
+  if (H * W == 4 * 4 * kThreads)
+    heatmap_reduce_reg_kernel<4><<<B * K, kThreads, 0, s>>>(logits, H, W, pooled_scratch, uv, cov, prob, argmax);
+  else if (H * W == 16 * 4 * kThreads)
+    heatmap_reduce_reg_kernel<16><<<B * K, kThreads, 0, s>>>(logits, H, W, pooled_scratch, uv, cov, prob, argmax);
+  else
+    heatmap_reduce_kernel<<<B * K, kThreads, 0, s>>>(logits, K, H, W, pooled_scratch, uv, cov, prob, argmax);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   if (cls_w && cls_b && (mask_logits || mask)) {

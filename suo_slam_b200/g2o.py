@@ -10,10 +10,12 @@ optimization_algorithm_levenberg.cpp:58-150 on the GPU).  With this module on th
 (cameras and objects free, the CHOLMOD path of lib/object_slam.py:710: the library eliminates the
 cameras by a Schur complement, csrc/ba_global.cu).
 
-One documented difference: g2o leaves the error of the last *rejected* LM trial in the active
-edges (the reference then reads it through ``e.chi2()``); here ``chi2()`` after ``optimize()``
-is evaluated at the returned estimates.  The packed path (``suo_ba_batch`` with rounds) keeps
-g2o's behaviour exactly.
+g2o quirk kept: after ``optimize()`` the active edges hold the error of the last EVALUATED LM trial —
+after a rejected trial that is the rejected state's error, not the error at the returned estimate
+(optimization_algorithm_levenberg.cpp:120-141) — and the reference reads it through ``e.chi2()``
+without recomputing (lib/object_slam.py:881-883).  The kernel leaves exactly those errors behind
+(``suo_ba_last_errors``) and ``optimize()`` copies them into the edges, so the reference's 4-round flow
+through this module classifies inliers like the packed path (``suo_ba_batch`` with rounds) and like g2o.
 """
 from __future__ import annotations
 
@@ -199,13 +201,17 @@ class SparseOptimizer:
             cam_k.append(e.cam_k); p.append(e.p); uv.append(e._uv); info.append(e._info.ravel())
         kernels = [e._kernel for e in active if e._kernel is not None]
         delta = kernels[0].delta if kernels else 1e150            # no kernel == Huber with an unreachable threshold
-        P, _, stats = _ba.ba_batch([0, len(verts)], [0, len(active)], poses, fixed, e_obj, e_cam, cam_k, p, uv, info,
-                                   np.ones(len(active)), [int(iterations)], huber_delta=delta, chi2_gate=1e300,
-                                   init_with_outliers=True)
+        P, _, stats, err = _ba.ba_batch([0, len(verts)], [0, len(active)], poses, fixed, e_obj, e_cam, cam_k, p, uv, info,
+                                        np.ones(len(active)), [int(iterations)], huber_delta=delta, chi2_gate=1e300,
+                                        init_with_outliers=True, return_errors=True)
         for v, T in zip(verts, P):
             if not v.fixed():
                 v.set_estimate(SE3Quat(T[:, :3], T[:, 3]))
-        for e in active:
-            e.compute_error()
+        ran = int(stats[0, 1]) > 0
+        for e, r, o, c in zip(active, err, e_obj, e_cam):
+            if ran and ((o >= 0 and not fixed[o]) or not fixed[c]):
+                e._err = r.copy()                                  # the error g2o leaves in the edge (see module docstring)
+            else:
+                e.compute_error()                                  # edge not in the active set / no LM iteration ran
         self.last_stats = stats[0]
         return int(stats[0, 1])

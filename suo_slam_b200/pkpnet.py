@@ -22,6 +22,10 @@ class PkpNet:
         self.max_crops = max_crops
         self.training = False
         self.return_prob = True          # the reference always returns "prob"; turn off to save 2x heat-map traffic
+        # fp16x3 conv math is range-guarded (|activation| <= 6e4): forwards on CUDA tensors poll the device flag after the call
+        # (one stream synchronisation — the reference's caller synchronises right after anyway, lib/object_slam.py:1100-1109);
+        # set to True to skip the poll and call check_range() yourself at the next synchronisation point
+        self.defer_range_check = False
         self._sd = None
         self._blob = None
         self._ctx = None
@@ -150,6 +154,8 @@ class PkpNet:
         else:
             ctx.check(_lib.lib().suo_forward(ctx.handle, _lib.ptr(images), B, H, W, _lib.ptr(boxes_t), _lib.ptr(box_img), L,
                                              _lib.ptr(priors), *outs))
+        if on_dev and not self.defer_range_check:
+            self.check_range()
         if cov is not None:
             out["cov"] = cov
         if prob is not None:
@@ -157,6 +163,12 @@ class PkpNet:
         return out
 
     __call__ = forward
+
+    def check_range(self):
+        """Raises SuoError (SUO_E_RANGE) when an activation left the FP16 range of the fp16x3 conv math since the last check:
+        the outputs of those forwards are invalid; switch the context to SUO_OPT_CONV_MATH = 0 (tf32x3)."""
+        ctx = self.context()
+        ctx.check(_lib.lib().suo_check_range(ctx.handle))
 
 
 def heatmap_reduce(ctx: _lib.Context, logits, cls_w=None, cls_b=None, want_prob=True):

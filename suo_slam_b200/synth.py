@@ -279,3 +279,144 @@ def make_slam_scene(seed: int, n_views: int = 6, n_obj: int = 6, kp_range=(8, 16
             detections[100 + v][10 + o] = dict(pose=pose, model_kp=kps[o].copy(), K=Kb, uv_pred=uv, cov_pred=cov if with_cov else None,
                                                inliers=~out | (rng.random(len(uv)) < 0.3), bbox=bbox)
     return dict(obj_poses=obj_poses, cam_poses=cam_poses, detections=detections, view_ids=[100 + v for v in range(n_views)])
+
+
+# ---- fiducial ("marker") network + frames: synthetic weights that really place keypoints ----------------------------
+# No checkpoint ships with the reference (README.md:63-84), and a random-init network gates almost every keypoint out
+# (lib/object_slam.py:1100-1115), so PnP / BA would run on empty inputs.  The generator below builds a state dict with
+# the reference's exact architecture and key names in which 41 trunk channels carry a colour-marker detector through the
+# skip connections of all 59 bottlenecks (every other weight stays seeded-random, every conv runs on dense data), and
+# frames whose objects carry one coloured disc per model keypoint.  The frame path then produces gated keypoints, PnP
+# consensus sets and non-empty BA graphs on both the CUDA path and the CPU oracle.
+MARKER_T = 0.481            # detector threshold on the colour projection (own colour 0.5, closest other colour 0.462)
+MARKER_GAIN = 1600.0        # tmpOut gain: peak logit ~ 30 over a background of O(1)
+MARKER_RADIUS = 10.0        # disc radius in crop pixels (256x256 crop)
+
+
+def marker_codes(num_kp: int = arch.NUM_KP) -> np.ndarray:
+    """[num_kp, 3] unit colour directions: a golden-angle lattice on the part of the sphere at least 107 degrees away
+    from black (zero padding at the crop border must not look like a marker); colour k = 0.5 + 0.5 * d_k."""
+    i = np.arange(num_kp) + 0.5
+    z = -0.3 + 1.3 * i / num_kp
+    phi = i * np.pi * (3.0 - np.sqrt(5.0))
+    r = np.sqrt(1.0 - z * z)
+    a = np.ones(3) / np.sqrt(3.0)
+    b = np.cross(a, [0.0, 0.0, 1.0])
+    b /= np.linalg.norm(b)
+    c = np.cross(a, b)
+    return (r * np.cos(phi))[:, None] * b + (r * np.sin(phi))[:, None] * c + z[:, None] * a
+
+
+def marker_colors_u8(num_kp: int = arch.NUM_KP) -> np.ndarray:
+    return np.clip(np.rint(255.0 * (0.5 + 0.5 * marker_codes(num_kp))), 0, 255).astype(np.uint8)
+
+
+def make_marker_state_dict(seed: int = 0, num_kp: int = arch.NUM_KP, noise: float = 0.15):
+    """Reference-format state dict (arch.state_dict_spec) of the fiducial network.
+
+    Trunk channels 0..num_kp-1 ("signal") are wired by hand, everything else is make_synthetic_state_dict(seed):
+      * stem conv1_ (hg.py:67): channel k = 6x6 box filter (taps -2..+3: centred half a pixel to the right/below, which
+        makes the stride-2 stem + 2x2 max-pool sample positions agree with the NDC pixel centres of pkpnet.py:19-26) of
+        the colour projection (rgb - 0.5) . d_k, minus the threshold; bn1 = identity; ReLU keeps what exceeds it;
+      * every bottleneck (Residual.py:20-35): conv3 rows of the signal channels are zero, so the skip path carries the
+        signal unchanged (conv4 = identity on them where Cin != Cout); the branches still READ the signal channels;
+      * the first bottleneck of each outer hourglass' low path (hg.py:42-44) computes -x on the signal channels, so the
+        low-resolution pyramid carries no signal (its nearest-upsampled max-pool plateaus would swamp the sub-pixel peak);
+      * lin_ = identity (+ identity BN) on the signal channels, tmpOut = MARKER_GAIN on the diagonal plus random weights
+        on the other 215 features (an O(1) background texture), ll_ / tmpOut_ feed nothing back into the signal channels;
+      * classifier (pkpnet.py:74-78): bias +2, small random weights -> kp_mask ~ 0.88 (gating is left to the covariance
+        and bbox tests of lib/object_slam.py:1100-1115).
+    """
+    sd = make_synthetic_state_dict(seed, num_kp)
+    S = num_kp
+    d = torch.tensor(marker_codes(num_kp), dtype=torch.float32)
+
+    def bn_identity(p, n):
+        sd[p + ".weight"][:n] = 1.0
+        sd[p + ".bias"][:n] = 0.0
+        sd[p + ".running_mean"][:n] = 0.0
+        sd[p + ".running_var"][:n] = 1.0
+
+    w = sd["backbone.conv1_.weight"]
+    w[:S] = 0.0
+    w[:S, :3, 1:7, 1:7] = (d / 36.0)[:, :, None, None]
+    sd["backbone.conv1_.bias"][:S] = -0.5 * d.sum(1) - MARKER_T
+    bn_identity("backbone.bn1", S)
+    eye = torch.arange(S)
+    prefixes = [k[:-len(".conv3.weight")] for k in sd if k.endswith(".conv3.weight")]
+    for p in prefixes:
+        sd[p + ".conv3.weight"][:S] = 0.0
+        sd[p + ".conv3.bias"][:S] = 0.0
+        if p + ".conv4.weight" in sd:
+            sd[p + ".conv4.weight"][:S] = 0.0
+            sd[p + ".conv4.weight"][eye, eye, 0, 0] = 1.0
+            sd[p + ".conv4.bias"][:S] = 0.0
+    for i in range(arch.N_STACK):
+        p = f"backbone.hourglass.{i}.low1_.0"
+        bn_identity(p + ".bn", S)
+        sd[p + ".conv1.weight"][:S] = 0.0
+        sd[p + ".conv1.weight"][eye, eye, 0, 0] = 1.0
+        sd[p + ".conv1.bias"][:S] = 0.0
+        bn_identity(p + ".bn1", S)
+        sd[p + ".conv2.weight"][:S] = 0.0
+        sd[p + ".conv2.weight"][eye, eye, 1, 1] = 1.0
+        sd[p + ".conv2.bias"][:S] = 0.0
+        bn_identity(p + ".bn2", S)
+        sd[p + ".conv3.weight"][eye, eye, 0, 0] = -1.0
+        p = f"backbone.lin_.{i}"
+        sd[p + ".0.weight"][:S] = 0.0
+        sd[p + ".0.weight"][eye, eye, 0, 0] = 1.0
+        sd[p + ".0.bias"][:S] = 0.0
+        bn_identity(p + ".1", S)
+        p = f"backbone.tmpOut.{i}"
+        sd[p + ".weight"] *= noise
+        sd[p + ".weight"][:, :S] = 0.0
+        sd[p + ".weight"][eye, eye, 0, 0] = MARKER_GAIN
+        sd[p + ".bias"][:] = 0.0
+    for i in range(arch.N_STACK - 1):
+        sd[f"backbone.ll_.{i}.weight"][:S] = 0.0
+        sd[f"backbone.ll_.{i}.bias"][:S] = 0.0
+        sd[f"backbone.tmpOut_.{i}.weight"][:S] = 0.0
+        sd[f"backbone.tmpOut_.{i}.bias"][:S] = 0.0
+    sd["classifier.2.weight"] *= 0.1
+    sd["classifier.2.bias"][:] = 2.0
+    return sd
+
+
+def make_marker_frame(seed: int, n_obj: int = 8, H: int = 480, W: int = 640, num_kp: int = arch.NUM_KP,
+                      K: np.ndarray = K_YCBV, res: int = 256, bg=(96, 160), radius: float = MARKER_RADIUS):
+    """make_frame's geometry with an image the fiducial network can read: low-contrast noise background and, per object,
+    one solid disc of colour k per valid model keypoint k.  The disc of a keypoint whose bbox-NDC position is (u, v) is
+    painted where the network's soft-argmax reads (u, v): the reference's mesh grid is transposed (uv_x runs along heat-map
+    ROWS, uv_y = -r[col]; lib/models/pkpnet.py:19-26,44-49), so inside the bbox the disc sits at the transposed position
+    (column fraction (1 - v) / 2, row fraction (u + 1) / 2).  Discs are circles of `radius` crop pixels (ellipses in the frame),
+    painted in object order — later objects occlude earlier ones and same-colour discs of other objects that fall into a
+    crop act as the gross outliers PnP has to reject."""
+    fr = make_frame(seed, n_obj, H, W, num_kp, K)
+    rng = np.random.default_rng(seed ^ 0x5EED)
+    img = rng.integers(bg[0], bg[1], size=(H, W, 3)).astype(np.float32)
+    col = marker_colors_u8(num_kp).astype(np.float32)
+    ss = 4
+    sub = (np.arange(ss) + 0.5) / ss
+    for o in fr["objs"]:
+        x1, y1, x2, y2 = [float(v) for v in o["bbox"]]
+        bw, bh = x2 - x1, y2 - y1
+        rx, ry = radius * bw / res, radius * bh / res
+        for k in np.nonzero(o["model_kps_mask"])[0]:
+            u, v = o["uv_gt"][k]
+            cx, cy = x1 + 0.5 * (1.0 - v) * bw, y1 + 0.5 * (u + 1.0) * bh
+            ix0, ix1 = int(np.floor(cx - rx)), int(np.ceil(cx + rx)) + 2
+            iy0, iy1 = int(np.floor(cy - ry)), int(np.ceil(cy + ry)) + 2
+            ix0, iy0, ix1, iy1 = max(ix0, 0), max(iy0, 0), min(ix1, W), min(iy1, H)
+            if ix0 >= ix1 or iy0 >= iy1:
+                continue
+            # sample positions: pixel i is centred on the integer coordinate i (the convention of K and of roi_align's
+            # aligned=False bilinear taps, lib/models/pkpnet.py:93), i.e. covers [i - 0.5, i + 0.5)
+            xs = (np.arange(ix0, ix1)[:, None] - 0.5 + sub[None, :]).ravel()
+            ys = (np.arange(iy0, iy1)[:, None] - 0.5 + sub[None, :]).ravel()
+            inside = (((xs[None, :] - cx) / rx) ** 2 + ((ys[:, None] - cy) / ry) ** 2) <= 1.0
+            alpha = inside.reshape(iy1 - iy0, ss, ix1 - ix0, ss).mean((1, 3)).astype(np.float32)
+            patch = img[iy0:iy1, ix0:ix1]
+            patch += alpha[:, :, None] * (col[k] - patch)
+    fr["img"] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return fr
