@@ -50,9 +50,16 @@ enum {
   SUO_OPT_PDL = 9,             /* 1 (default) = the persistent conv kernels use programmatic dependent launch (the next kernel's CTAs are
                                    scheduled and run their prologue while the previous kernel drains; griddepcontrol.wait before any
                                    activation is touched); 0 = plain stream order */
-  SUO_OPT_CONV_HALO = 10       /* 1 (default) = the 3x3 convs at 64x64 / 32x32 / 16x16 fetch their activations once per column shift (A-halo
+  SUO_OPT_CONV_HALO = 10,      /* 1 (default) = the 3x3 convs at 64x64 / 32x32 / 16x16 fetch their activations once per column shift (A-halo
                                    CTA-pair kernel, conv_halo.cu); its accumulation order differs from the other 3x3 kernels: equal to FP32
                                    rounding, not bit for bit.  0 = CTA-pair kernel of SUO_OPT_CONV_PAIR */
+  SUO_OPT_PNP_MAX_POINTS = 12,  /* points per object the PnP kernel reserves shared memory for on DEVICE-pointer suo_pnp_batch calls (default 64,
+                                   4..4096).  Host-pointer calls size it from `offsets`.  An object with more points is NOT truncated: it
+                                   returns the identity (failure) with stats[.,0] = -1 */
+  SUO_OPT_BA_BLOCK_DIAGONAL = 11 /* 1 = the caller vouches that every graph passed to suo_ba_batch with DEVICE pointers has exactly one free
+                                   vertex per edge and at most 64 vertices (single-view / curr_only graphs): the call then only enqueues the
+                                   shared-memory kernel instead of copying the index arrays to the host to choose a kernel (a violation is
+                                   reported per problem through stats[.,0] = -1 / -2).  0 (default) = inspect the structure */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */
@@ -150,7 +157,9 @@ int suo_conv2d(suo_ctx* ctx, const float* in, int B, int H, int W, int Cin,
  *   offsets[n_obj+1] row ranges per object (object o owns rows offsets[o]..offsets[o+1])
  *   seed / obj_keys[n_obj] (NULL -> key = object index): counter-based RANSAC sampling
  *   T_out [n_obj,16] row-major 4x4; identity == failure, exactly like the reference
- *   stats [n_obj,5] i32 or NULL: best_inliers, best_iter, total_iters, refine1_its, refine2_its */
+ *   stats [n_obj,5] i32 or NULL: best_inliers, best_iter, total_iters, refine1_its, refine2_its
+ * Any number of points per object up to 4876 (the points of one object live in shared memory; the reference's own
+ * benchmark uses 250, thirdparty/lambdatwist/test_pnp.cpp:68-147). */
 int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj,
                   double threshold, uint64_t seed, const uint64_t* obj_keys,
                   double* T_out, int32_t* stats, int on_device, void* stream);
@@ -255,14 +264,16 @@ int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int
  * and returns at once; suo_frames_wait blocks until that slot's results are in the host output buffers (and reports
  * the FP16-range flag like the synchronous call).  With two slots the copies of batch i+1 overlap the kernels of
  * batch i.  Input and output buffers must stay valid (and should be pinned) until the wait returns; a slot must be
- * waited for before it is submitted again.  slot in {0, 1}. */
+ * waited for before it is submitted again.  slot in {0, 1}.  records_dev (DEVICE pointer, L records, or NULL): the
+ * batch's result records (suo_pack_records layout, crop_id = record_id_base + index) are also packed there on `stream`,
+ * ready for suo_allgather_results — the multi-GPU exchange then needs no host round trip. */
 int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W,
                          const float* boxes, const int32_t* box_img, int L,
                          const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
                          const double* diameter, double kp_var_thresh, double bbox_thresh,
                          uint64_t seed, int run_ba,
                          double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
-                         float* uv, float* cov, void* stream);
+                         float* uv, float* cov, void* records_dev, int record_id_base, void* stream);
 int suo_frames_wait(suo_ctx* ctx, int slot);
 
 /* ---- multi-GPU exchange (BASELINE.json configs[3]) -------------- */

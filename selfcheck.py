@@ -1,6 +1,6 @@
 """smoke(): one small invocation of every hot-path stage on cuda:0, each checked against the
-CPU oracle (oracle/ is test infrastructure; this module is only reached from
-__graft_entry__.smoke())."""
+CPU oracle (oracle/ is test infrastructure; this module sits next to __graft_entry__.py, outside the
+product package, and is only reached from __graft_entry__.smoke())."""
 from __future__ import annotations
 
 import os
@@ -8,13 +8,13 @@ import os
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 
 
 def run_smoke(verbose: bool = False):
     from oracle import frame_oracle, geom
-    from . import _lib, frames, synth
-    from .pkpnet import PkpNet
+    from suo_slam_b200 import _lib, frames, synth
+    from suo_slam_b200.pkpnet import PkpNet
 
     def say(*a):
         if verbose:
@@ -50,6 +50,25 @@ def run_smoke(verbose: bool = False):
     np.testing.assert_allclose(got["T_ba"], ref["T_ba"], rtol=1e-7, atol=1e-5)
     say(f"PnP + BA vs oracle: {int(ref['accepted'].sum())}/4 objects accepted, poses match to 1e-7; "
         f"{m.context().kernel_launches()} kernel launches")
+    # pixels -> poses: one marker frame (4 objects) through the fused frame call, against the CPU frame oracle
+    fr = synth.make_marker_frame(1000, n_obj=4)
+    sdm = synth.make_marker_state_dict(0)
+    mm2 = PkpNet(input_res=(256, 256), max_crops=4)
+    mm2.load_state_dict(sdm)
+    mm2.cuda(0).eval()
+    bb = np.stack([o["bbox"] for o in fr["objs"]]).astype(np.float32)
+    mk = np.stack([o["model_kps"] for o in fr["objs"]])
+    msk = np.stack([o["model_kps_mask"] for o in fr["objs"]])
+    kb = frames.k_bbox_for(fr["K"], bb)
+    got = frames.FramePipeline(mm2).run(fr["img"][None], bb, bi, mk, msk, kb, diam)
+    ref = frame_oracle.run_frames(sdm, fr["img"].transpose(2, 0, 1)[None].astype(np.float32) / 255, bb, bi, mk, msk, kb, diam)
+    np.testing.assert_allclose(got["uv"], ref["uv"], atol=2e-4)
+    same = np.array_equal(got["kp_used"], ref["kp_used"])
+    acc = ref["accepted"] & np.all(got["kp_used"] == ref["kp_used"], axis=1)
+    d = [np.linalg.norm(got["T_ba"][c] - ref["T_ba"][c]) / np.linalg.norm(ref["T_ba"][c]) for c in np.nonzero(acc)[0]]
+    say(f"marker frame, pixels -> poses vs CPU oracle: {int(got['kp_used'].sum())} gated keypoints (same gating: {same}), "
+        f"{int(ref['accepted'].sum())}/4 objects accepted, max rel pose diff {max(d) if d else float('nan'):.2e}")
+    assert got["kp_used"].sum() >= 16 and ref["accepted"].sum() >= 2 and d and max(d) < 1e-2
     _ = geom
     _ = _lib
     say("ok")

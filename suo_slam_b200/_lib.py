@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsuo_b200.so")
 
-SUO_OPT_CONV_BACKEND, SUO_OPT_TF32_PASSES, SUO_OPT_USE_GRAPH, SUO_OPT_CONV_PERSISTENT, SUO_OPT_MULTISTREAM, SUO_OPT_CONV_MATH, SUO_OPT_CONV_FUSE, SUO_OPT_CONV_PAIR, SUO_OPT_PDL, SUO_OPT_CONV_HALO = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+SUO_OPT_CONV_BACKEND, SUO_OPT_TF32_PASSES, SUO_OPT_USE_GRAPH, SUO_OPT_CONV_PERSISTENT, SUO_OPT_MULTISTREAM, SUO_OPT_CONV_MATH, SUO_OPT_CONV_FUSE, SUO_OPT_CONV_PAIR, SUO_OPT_PDL, SUO_OPT_CONV_HALO, SUO_OPT_BA_BLOCK_DIAGONAL, SUO_OPT_PNP_MAX_POINTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 
 _lib = None
 vp = C.c_void_p
@@ -66,7 +66,7 @@ def lib():
         L.suo_ba_last_errors.argtypes = [vp, vp, C.c_int, C.c_int, vp]
         L.suo_edge_linearize.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
         L.suo_frames_u8_submit.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double,
-                                           C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [vp]
+                                           C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [vp, C.c_int, vp]
         L.suo_frames_wait.argtypes = [vp, C.c_int]
         L.suo_record_bytes.argtypes = [C.c_int]
         L.suo_record_bytes.restype = C.c_size_t

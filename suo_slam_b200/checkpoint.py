@@ -11,7 +11,7 @@ The reference saves ``{'model': state_dict, 'epoch': int, 'args': Namespace, ...
 ``suo_load_weights`` consumes (suo_slam_b200.weights.pack_state_dict) next to a small JSON header, so a deployment
 needs neither torch pickles nor the folding step at start-up:
 
-    python -m suo_slam_b200.checkpoint results/.../model_best.pth.tar model_best.suo
+    python -m suo_slam_b200.checkpoint [--unsafe] results/.../model_best.pth.tar model_best.suo
 """
 from __future__ import annotations
 
@@ -32,9 +32,22 @@ def _strip_prefix(sd):
     return sd
 
 
-def load_checkpoint(path: str):
-    """-> (state_dict ready for PkpNet.load_state_dict, epoch, args) from a reference checkpoint file."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+def load_checkpoint(path: str, allow_pickle: bool = False):
+    """-> (state_dict ready for PkpNet.load_state_dict, epoch, args) from a reference checkpoint file.
+
+    The file is read with ``weights_only=True`` plus ``argparse.Namespace`` (the only non-tensor object ObjectSLAM needs,
+    lib/object_slam.py:94-96) on the allow-list, so a third-party checkpoint cannot run code at load time.  Reference
+    checkpoints written by train.py:349-355 also pickle the Adam optimizer OBJECT; those need ``allow_pickle=True``
+    (full unpickling: only for files you trust)."""
+    import argparse
+    try:
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            ck = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as e:
+        if not allow_pickle:
+            raise ValueError(f"{path}: cannot be read with weights_only=True ({type(e).__name__}: {str(e)[:200]}); if you trust the file, "
+                             "pass allow_pickle=True / --unsafe (reference checkpoints pickle their optimizer object)") from e
+        ck = torch.load(path, map_location="cpu", weights_only=False)
     if not isinstance(ck, dict) or "model" not in ck:
         raise ValueError(f"{path}: not a SUO-SLAM checkpoint (expected a dict with a 'model' entry, train.py:173-181)")
     sd = _strip_prefix(dict(ck["model"]))
@@ -44,9 +57,9 @@ def load_checkpoint(path: str):
     return sd, int(ck.get("epoch", -1)), ck.get("args")
 
 
-def convert(path_in: str, path_out: str) -> dict:
+def convert(path_in: str, path_out: str, allow_pickle: bool = False) -> dict:
     """Reference checkpoint -> packed blob file.  Returns the JSON header that was written."""
-    sd, epoch, args = load_checkpoint(path_in)
+    sd, epoch, args = load_checkpoint(path_in, allow_pickle)
     blob = weights.pack_state_dict(sd, arch.NUM_KP)
     meta = dict(epoch=epoch, num_kp=arch.NUM_KP, source=str(path_in), **weights.program_summary(blob),
                 train_args={k: repr(v) for k, v in vars(args).items()} if hasattr(args, "__dict__") else None)
@@ -70,6 +83,7 @@ def load_packed(path: str):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) != 3:
+    argv = [a for a in sys.argv[1:] if a != "--unsafe"]
+    if len(argv) != 2:
         sys.exit(__doc__)
-    print(json.dumps(convert(sys.argv[1], sys.argv[2]), indent=1))
+    print(json.dumps(convert(argv[0], argv[1], allow_pickle="--unsafe" in sys.argv), indent=1))

@@ -7,6 +7,7 @@
 // packs the weights for the tensor-core kernel once, and replays the op list — as a CUDA
 // graph per (crop count, variant) — on the caller's stream.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <array>
@@ -134,6 +135,7 @@ struct NetState {
   std::vector<float*> packed;                // per op: tcgen05 TF32 weight images (device) or nullptr
   std::vector<uint16_t*> packed16;           // per op: tcgen05 FP16x3 weight images (device) or nullptr
   int* range_flag = nullptr;                 // device int: FP16 operand range exceeded
+  bool w_exceeds_fp16 = false;               // some folded weight is outside the FP16 range (or not finite): fp16x3 math is refused
   std::vector<std::array<unsigned char, 1152>> tmaps;   // per op: in hi / in lo / out (FP32 or hi) / out lo / skip / raw input / weight-image CUtensorMaps (split mode)
   std::vector<int> halo_ok;                             // per op: the A-halo maps (bytes 896.. of tmaps) are valid
   std::vector<int> epi_ok, raw_ok, wmap_ok;             // per op: the output / skip maps, the FP32 input map, the weight-image map are valid
@@ -379,6 +381,10 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
 
 int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   NetState& N = X(ctx)->net;
+  if (N.w_exceeds_fp16 && ctx->opt_backend == 1 && ctx->opt_math == 1) {
+    ctx->set_error("fp16x3 conv math: a BN-folded weight exceeds the FP16 range (|w| > 6e4) or is not finite; use SUO_OPT_CONV_MATH = 0 (tf32x3)", __FILE__, __LINE__);
+    return SUO_E_RANGE;
+  }
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
   NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair, ctx->opt_pdl, ctx->opt_halo};
@@ -432,6 +438,8 @@ int check_ctx(suo_ctx* ctx) {
 }  // namespace
 
 extern "C" {
+
+size_t suo_record_bytes(int num_kp);
 
 int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** out) {
   if (!out || max_crops <= 0 || crop_res < 64 || (crop_res & (crop_res - 1)) || num_kp <= 0 || num_kp > 45) return SUO_E_INVALID;
@@ -530,6 +538,8 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_PDL: ctx->opt_pdl = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_HALO: ctx->opt_halo = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_PNP_MAX_POINTS: if (value < 4 || value > 4096) return SUO_E_INVALID; ctx->opt_pnp_max_pts = value; return SUO_OK;
+    case SUO_OPT_BA_BLOCK_DIAGONAL: ctx->opt_ba_blockdiag = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -555,6 +565,35 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   N.ops.resize(N.h.n_ops);
   memcpy(N.ops.data(), b + off, sizeof(OpDesc) * N.h.n_ops); off += sizeof(OpDesc) * N.h.n_ops;
   const float* pool_h = reinterpret_cast<const float*>(b + off);
+  {   // a corrupt or stale .suo file must be rejected here, not index out of bounds later
+    const long long nf = N.h.n_floats, nb = N.h.n_bufs, Kp = ctx->num_kp;
+    auto in_pool = [&](long long o, long long n) { return o >= 0 && n >= 0 && o + n <= nf; };
+    auto buf_ok = [&](long long i) { return i >= 0 && i < nb; };
+    bool ok = buf_ok(N.h.in_buf_noprior) && buf_ok(N.h.in_buf_prior) && buf_ok(N.h.logits_buf) && in_pool(N.h.cls_w_off, Kp * Kp) &&
+              in_pool(N.h.cls_b_off, Kp) && N.h.heat_div > 0 && ctx->crop_res % N.h.heat_div == 0;
+    for (const BufDesc& d : N.bufs) ok = ok && d.div > 0 && d.div <= ctx->crop_res && ctx->crop_res % d.div == 0 && d.C > 0 && d.C <= 4096;
+    for (const OpDesc& o : N.ops) {
+      if (!ok) break;
+      ok = buf_ok(o.in) && buf_ok(o.out) && (o.res == -1 || buf_ok(o.res)) && o.in != o.out;
+      if (!ok) break;
+      if (o.type == OP_CONV) {
+        ok = (o.mode == CONV_1x1 || o.mode == CONV_3x3 || o.mode == CONV_STEM7) && o.Cin == N.bufs[o.in].C && o.Cout > 0 && o.Cout <= o.Cout_pad &&
+             o.Cout_pad % 64 == 0 && o.Cout <= N.bufs[o.out].C + 63 && o.K > 0 && o.K % 32 == 0 && in_pool(o.w_off, (long long)o.Cout_pad * o.K) &&
+             in_pool(o.b_off, o.Cout_pad) && (o.pre_off == -1 || in_pool(o.pre_off, 2LL * o.Cin)) &&
+             (o.res == -1 || (N.bufs[o.res].C == N.bufs[o.out].C && N.bufs[o.res].div == N.bufs[o.out].div)) &&
+             (o.mode == CONV_1x1 ? o.K == o.Cin : o.mode == CONV_3x3 ? o.K == 9 * o.Cin : (o.cpr > 0 && o.K % (o.cpr * 32) == 0)) &&
+             (o.mode == CONV_STEM7 ? N.bufs[o.out].div == 2 * N.bufs[o.in].div : N.bufs[o.out].div == N.bufs[o.in].div);
+      } else if (o.type == OP_MAXPOOL) {
+        ok = N.bufs[o.out].C == N.bufs[o.in].C && N.bufs[o.out].div == 2 * N.bufs[o.in].div;
+      } else if (o.type == OP_UPADD) {
+        ok = o.res >= 0 && N.bufs[o.out].C == N.bufs[o.in].C && N.bufs[o.res].C == N.bufs[o.in].C && N.bufs[o.out].div == N.bufs[o.in].div &&
+             N.bufs[o.res].div == 2 * N.bufs[o.in].div;
+      } else {
+        ok = false;
+      }
+    }
+    if (!ok) { N.bufs.clear(); N.ops.clear(); ctx->set_error("weight blob: buffer / op table is inconsistent (corrupt or stale file)", __FILE__, __LINE__); return SUO_E_INVALID; }
+  }
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pool, sizeof(float) * (size_t)N.h.n_floats));
   SUO_CUDA_TRY(ctx, cudaMemcpy(N.pool, pool_h, sizeof(float) * (size_t)N.h.n_floats, cudaMemcpyHostToDevice));
   // tensor-core weight images
@@ -570,6 +609,12 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
     conv_tc_pack_weights(pool_h + o.w_off, o.Cout_pad, o.K, tmp.data());
     SUO_CUDA_TRY(ctx, cudaMalloc(&N.packed[i], nf * sizeof(float)));
     SUO_CUDA_TRY(ctx, cudaMemcpy(N.packed[i], tmp.data(), nf * sizeof(float), cudaMemcpyHostToDevice));
+    {   // fp16x3 splits every weight into two FP16 numbers: a BN-folded weight beyond the FP16 range cannot be represented
+      float wmax = 0.f;
+      const float* wp = pool_h + o.w_off;
+      for (size_t q = 0; q < (size_t)o.Cout_pad * o.K; ++q) wmax = std::max(wmax, std::fabs(wp[q]));
+      if (!(wmax <= 6.0e4f)) N.w_exceeds_fp16 = true;
+    }
     if (o.K % 64 == 0) {
       const size_t nh = conv_tc_packed16_halfs(o.Cout_pad, o.K);
       tmp16.resize(nh);
@@ -736,6 +781,7 @@ int suo_crop_concat(suo_ctx* ctx, const float* images, int n_img, int H, int W, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (L <= 0 || n_img <= 0 || !images || !boxes || !box_img || !out) return SUO_E_INVALID;
   if (on_device) return launch_crop_concat(ctx, images, n_img, H, W, boxes, box_img, L, priors, ctx->num_kp, R, out, out_c, s);
+  for (int c = 0; c < L; ++c) if (box_img[c] < 0 || box_img[c] >= n_img) { ctx->set_error("suo_crop_concat: box_img out of range", __FILE__, __LINE__); return SUO_E_INVALID; }
   CtxExtra* x = X(ctx);
   const size_t n_im = (size_t)n_img * 3 * H * W, n_out = (size_t)L * R * R * out_c, n_pr = priors ? (size_t)L * ctx->num_kp * R * R : 0;
   rc = x->io.grow(ctx, (n_im + n_out + n_pr + 8 * (size_t)L) * sizeof(float) + 4096);
@@ -963,6 +1009,7 @@ static int forward_impl(suo_ctx* ctx, const void* images, int n_img, int H, int 
   const int32_t* d_bi = box_img;
   float* d_prob = prob;
   if (!on_device) {
+    for (int c = 0; c < L; ++c) if (box_img[c] < 0 || box_img[c] >= n_img) { ctx->set_error("suo_forward: box_img out of range", __FILE__, __LINE__); return SUO_E_INVALID; }
     rc = x->io.grow(ctx, (n_im + n_pr + 8 * (size_t)L + (prob ? n_hm : 0) + 3 * LK) * sizeof(float) + 8192);   // (u8 images need a quarter of n_im floats)
     if (rc) return rc;
     Bump bp{static_cast<uint8_t*>(x->io.d)};
@@ -1060,13 +1107,13 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
   if (rc) return rc;
   if (n_obj <= 0 || !xs || !ys || !offsets || !T_out) return SUO_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (on_device) return launch_pnp_batch(ctx, xs, ys, offsets, n_obj, threshold, seed, obj_keys, T_out, stats, s);
+  if (on_device) return launch_pnp_batch(ctx, xs, ys, offsets, n_obj, threshold, seed, obj_keys, T_out, stats, s, ctx->opt_pnp_max_pts);
   const int N = offsets[n_obj];
-  for (int o = 0; o < n_obj; ++o)
-    if (offsets[o + 1] - offsets[o] > 64 || offsets[o + 1] < offsets[o]) {
-      ctx->set_error("suo_pnp_batch: at most 64 points per object", __FILE__, __LINE__);
-      return SUO_E_INVALID;
-    }
+  int max_pts = 0;
+  for (int o = 0; o < n_obj; ++o) {
+    if (offsets[o + 1] < offsets[o]) { ctx->set_error("suo_pnp_batch: offsets must be non-decreasing", __FILE__, __LINE__); return SUO_E_INVALID; }
+    max_pts = std::max(max_pts, offsets[o + 1] - offsets[o]);
+  }
   CtxExtra* x = X(ctx);
   rc = x->io.grow(ctx, (size_t)N * 5 * 8 + (size_t)n_obj * (16 * 8 + 5 * 4 + 8 + 4) + 8192);
   if (rc) return rc;
@@ -1081,7 +1128,7 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_ys, ys, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (n_obj + 1) * 4, cudaMemcpyHostToDevice, s));
   if (d_keys) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, obj_keys, n_obj * 8, cudaMemcpyHostToDevice, s));
-  rc = launch_pnp_batch(ctx, d_xs, d_ys, d_off, n_obj, threshold, seed, d_keys, d_T, d_st, s);
+  rc = launch_pnp_batch(ctx, d_xs, d_ys, d_off, n_obj, threshold, seed, d_keys, d_T, d_st, s, max_pts);
   if (rc) return rc;
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(T_out, d_T, 16 * (size_t)n_obj * 8, cudaMemcpyDeviceToHost, s));
   if (stats) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(stats, d_st, 5 * (size_t)n_obj * 4, cudaMemcpyDeviceToHost, s));
@@ -1228,6 +1275,9 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
     b.chi2_gate = chi2_gate; b.init_with_outliers = init_with_outliers; b.stats = st; b.err = d_err; b.level = d_level; b.fv_kind = d_fv;
     return b;
   };
+  if (on_device && ctx->opt_ba_blockdiag)    // the caller vouches for the structure: no host look at the index arrays, no synchronisation
+    return launch_ba_batch_scratch(ctx, n_prob, prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers,
+                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s);
   if (on_device) {
     // The graph structure decides the kernel: bring the index arrays to the host (this synchronises `stream`; the
     // device-resident frame path, suo_solve_keypoints / suo_frames, does not come through here).
@@ -1323,7 +1373,7 @@ static int solve_keypoints_device(suo_ctx* ctx, Bump& bp, const float* d_uv, con
     xo->pnp_off_n = n;
   }
   const int32_t* d_off = xo->pnp_off;
-  rc = launch_pnp_batch_counts(ctx, d_xs, d_ys, d_off, d_cnt, L, 0.001, seed, nullptr, d_Tpnp, d_pst, s);
+  rc = launch_pnp_batch_counts(ctx, d_xs, d_ys, d_off, d_cnt, L, 0.001, seed, nullptr, d_Tpnp, d_pst, s, K);
   if (rc) return rc;
   if (!run_ba) return SUO_OK;
   rc = launch_frame_ranges(ctx, d_bi, L, n_img, d_fs, s);
@@ -1434,7 +1484,7 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
                        int L, const float* priors, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
                        const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
                        double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
-                       int on_device, void* stream, int slot = -1) {
+                       int on_device, void* stream, int slot = -1, void* records = nullptr, int record_id_base = 0) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
@@ -1479,6 +1529,7 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   const uint8_t* d_mm = model_mask;
   if (!on_device) {
     for (int c = 1; c < L; ++c) if (box_img[c] < box_img[c - 1]) { ctx->set_error("suo_frames: box_img must be sorted", __FILE__, __LINE__); return SUO_E_INVALID; }
+    if (box_img[0] < 0 || box_img[L - 1] >= n_img) { ctx->set_error("suo_frames: box_img out of range", __FILE__, __LINE__); return SUO_E_INVALID; }
     Bump& q = sl ? ip : bp;
     float* a = q.take<float>(n_im); float* b = q.take<float>(4 * (size_t)L); int32_t* c = q.take<int32_t>(L);
     float* d = priors ? q.take<float>(n_pr) : nullptr;
@@ -1513,6 +1564,11 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
     if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(uv, N.d_uv, LK * 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (cov) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(cov, N.d_cov, LK * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return SUO_OK;
+  }
+  if (records) {   // result records for the multi-GPU exchange, packed on the device from this batch's own outputs
+    rc = launch_pack_records(ctx, nullptr, record_id_base, d_Tpnp, run_ba ? d_Tba : nullptr, d_used, run_ba ? d_bain : nullptr, N.d_uv, N.d_cov,
+                             L, K, (int)suo_record_bytes(K), static_cast<uint8_t*>(records), s);
+    if (rc) return rc;
   }
   if (sl) {     // the next batch's forward overwrites the executor's uv / cov: keep this batch's copy in the slot
     if (uv) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_uvo, N.d_uv, LK * 8, cudaMemcpyDeviceToDevice, s));
@@ -1591,10 +1647,11 @@ int suo_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const dou
 int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W, const float* boxes,
                          const int32_t* box_img, int L, const double* model_kps, const uint8_t* model_mask, const double* K_bbox,
                          const double* diameter, double kp_var_thresh, double bbox_thresh, uint64_t seed, int run_ba,
-                         double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov, void* stream) {
+                         double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers, float* uv, float* cov,
+                         void* records_dev, int record_id_base, void* stream) {
   if (slot < 0) return SUO_E_INVALID;
   return frames_impl(ctx, images_hwc, 1, n_img, H, W, boxes, box_img, L, nullptr, model_kps, model_mask, K_bbox, diameter, kp_var_thresh,
-                     bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, 0, stream, slot);
+                     bbox_thresh, seed, run_ba, T_pnp, T_ba, kp_used, ba_inliers, uv, cov, 0, stream, slot, records_dev, record_id_base);
 }
 
 int suo_frames_wait(suo_ctx* ctx, int slot) {

@@ -147,10 +147,10 @@ int launch_upsample_add(suo_ctx* ctx, const float* up1, const float* low, int B,
                         cudaStream_t s);
 int launch_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj,
                      double threshold, uint64_t seed, const uint64_t* obj_keys, double* T_out, int32_t* stats,
-                     cudaStream_t s);
+                     cudaStream_t s, int max_pts);
 int launch_pnp_batch_counts(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets,
                             const int32_t* counts, int n_obj, double threshold, uint64_t seed, const uint64_t* obj_keys,
-                            double* T_out, int32_t* stats, cudaStream_t s);
+                            double* T_out, int32_t* stats, cudaStream_t s, int max_pts);
 int launch_ba_batch_scratch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, double* poses,
                             const uint8_t* fixed, const int32_t* e_obj, const int32_t* e_cam, const double* cam_k,
                             const double* p, const double* uv, const double* info, uint8_t* inliers,
@@ -190,6 +190,8 @@ struct suo_ctx {
   int opt_stem_tma = 1; // 1 = the RGB-only stem fetches its operand by TMA from a zero-bordered input copy (SUO_STEM_TMA=0: register gathers)
   int opt_pdl = 1;      // 1 = the persistent conv kernels are launched with programmatic stream serialization (SUO_PDL / SUO_OPT_PDL)
   int opt_epi_tma = 1, opt_mma_merge = 1, opt_raw_tma = 1;
+  int opt_pnp_max_pts = 64;  // SUO_OPT_PNP_MAX_POINTS: shared-memory point capacity per object of DEVICE-pointer suo_pnp_batch calls
+  int opt_ba_blockdiag = 0;  // SUO_OPT_BA_BLOCK_DIAGONAL: device-pointer suo_ba_batch calls skip the host-side structure check
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
   int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
   void* net = nullptr;  // NetState (net_exec.cu)

@@ -15,13 +15,14 @@
 // and the number of iterations are exactly those of the serial loop.  The refine is the
 // trust-region LM Ceres runs (6 local parameters), parallelised over points by one warp.
 // Latency / FP64-issue bound: no bandwidth claim, no tensor cores.
+#include <algorithm>
 #include "common.cuh"
 
 namespace {
 
 constexpr int PNP_THREADS = 128;
 constexpr int MAX_RANSAC_ITERS = 1000;
-constexpr int MAX_PTS = 64;   // keypoints per object (41 in the reference vocabulary)
+constexpr int PNP_SMEM_BYTES_PER_POINT = 5 * 8 + 2;   // xs[3], ys[2] in FP64 + two selection bytes, all in dynamic shared memory
 
 struct D3 { double x, y, z; };
 __device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
@@ -510,15 +511,23 @@ __device__ int warp_lm(QPose& P, const double* xs, const double* ys, const uint8
 
 __global__ void __launch_bounds__(PNP_THREADS)
 pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all, const int32_t* __restrict__ offsets,
-           const int32_t* __restrict__ npts, double threshold, uint64_t seed, const uint64_t* __restrict__ keys, double* __restrict__ T_out,
-           int32_t* __restrict__ stats) {
-  __shared__ double xs[3 * MAX_PTS], ys[2 * MAX_PTS];
+           const int32_t* __restrict__ npts, int max_pts, double threshold, uint64_t seed, const uint64_t* __restrict__ keys,
+           double* __restrict__ T_out, int32_t* __restrict__ stats) {
+  extern __shared__ double pnp_dyn[];
+  double* xs = pnp_dyn;
+  double* ys = xs + 3 * max_pts;
+  uint8_t* sel = reinterpret_cast<uint8_t*>(ys + 2 * max_pts);
+  uint8_t* sel0 = sel + max_pts;
   __shared__ int counts[PNP_THREADS];
   __shared__ int sh_best_inl, sh_best_it, sh_iters, sh_done;
-  __shared__ uint8_t sel[MAX_PTS], sel0[MAX_PTS];
   const int obj = blockIdx.x;
   const int off = offsets[obj];
-  const int n = min(npts ? npts[obj] : offsets[obj + 1] - off, MAX_PTS);
+  const int n = npts ? npts[obj] : offsets[obj + 1] - off;
+  if (n > max_pts || n < 0) {     // never truncate: the object is reported as failed (identity, like the reference's failure) with best_inliers = -1
+    if (threadIdx.x < 16) T_out[16 * obj + threadIdx.x] = (threadIdx.x % 5 == 0) ? 1.0 : 0.0;
+    if (threadIdx.x == 0 && stats) { stats[5 * obj] = -1; stats[5 * obj + 1] = -1; stats[5 * obj + 2] = 0; stats[5 * obj + 3] = -1; stats[5 * obj + 4] = -1; }
+    return;
+  }
   const uint64_t key = keys ? keys[obj] : (uint64_t)obj;
   for (int i = threadIdx.x; i < 3 * n; i += PNP_THREADS) xs[i] = xs_all[3 * off + i];
   for (int i = threadIdx.x; i < 2 * n; i += PNP_THREADS) ys[i] = ys_all[2 * off + i];
@@ -600,9 +609,15 @@ pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all,
 // counts == nullptr: object o owns rows offsets[o]..offsets[o+1]; else rows offsets[o]..offsets[o]+counts[o]
 int launch_pnp_batch_counts(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets,
                             const int32_t* counts, int n_obj, double threshold, uint64_t seed, const uint64_t* obj_keys,
-                            double* T_out, int32_t* stats, cudaStream_t s) {
+                            double* T_out, int32_t* stats, cudaStream_t s, int max_pts) {
   if (n_obj <= 0) return SUO_OK;
-  pnp_kernel<<<n_obj, PNP_THREADS, 0, s>>>(xs, ys, offsets, counts, threshold, seed, obj_keys, T_out, stats);
+  max_pts = (std::max(max_pts, 4) + 7) & ~7;
+  const size_t smem = (size_t)max_pts * PNP_SMEM_BYTES_PER_POINT;
+  if (smem > 200 * 1024) { ctx->set_error("suo_pnp_batch: more than " + std::to_string(200 * 1024 / PNP_SMEM_BYTES_PER_POINT) + " points in one object", __FILE__, __LINE__); return SUO_E_INVALID; }
+  static bool configured[64] = {};
+  if (smem > 40 * 1024 && first_use_on_device(configured, nullptr))
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(pnp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  pnp_kernel<<<n_obj, PNP_THREADS, smem, s>>>(xs, ys, offsets, counts, max_pts, threshold, seed, obj_keys, T_out, stats);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
@@ -610,6 +625,6 @@ int launch_pnp_batch_counts(suo_ctx* ctx, const double* xs, const double* ys, co
 
 int launch_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_t* offsets, int n_obj,
                      double threshold, uint64_t seed, const uint64_t* obj_keys, double* T_out, int32_t* stats,
-                     cudaStream_t s) {
-  return launch_pnp_batch_counts(ctx, xs, ys, offsets, nullptr, n_obj, threshold, seed, obj_keys, T_out, stats, s);
+                     cudaStream_t s, int max_pts) {
+  return launch_pnp_batch_counts(ctx, xs, ys, offsets, nullptr, n_obj, threshold, seed, obj_keys, T_out, stats, s, max_pts);
 }

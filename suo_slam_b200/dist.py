@@ -146,6 +146,11 @@ class RecordExchange:
         p = _lib.ptr
         self.ctx.check(_lib.lib().suo_pack_records(self.ctx.handle, None, int(id_base), p(T_pnp), p(T_ba), p(kp_used), p(ba_inliers),
                                                    p(uv), p(cov), self.n_local, p(self.rec), 1, stream_ptr))
+        return self.gather(stream_ptr)
+
+    def gather(self, stream_ptr):
+        """All-gather of self.rec (already packed on the device, e.g. by suo_frames_u8_submit) into self.out."""
+        p = _lib.ptr
         if self.world == 1:
             return self.rec
         if self.comm is not None:

@@ -420,3 +420,45 @@ def make_marker_frame(seed: int, n_obj: int = 8, H: int = 480, W: int = 640, num
             patch += alpha[:, :, None] * (col[k] - patch)
     fr["img"] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     return fr
+
+
+def make_pnp_benchmark(seed: int, n: int = 250, pixel_sigma: float = 0.5, outlier_ratio: float = 0.5):
+    """One experiment of the reference's PnP Monte-Carlo benchmark (thirdparty/lambdatwist/simulator.h:46-94,
+    PointCloudWithNoisyMeasurements; points from getRandomPointsInfrontOfCamera :29-43): pose = (uniform rotation, unit
+    translation), points at uniform normalised image positions in [-1,1]^2 and depths U(0.1, 100), measurement noise =
+    a random unit 2-vector times sigma (pixel_sigma * 0.001, i.e. f = 1000), and outlier_ratio * n draws (with
+    replacement, "exact ratio is not needed") moved at least 0.002 + 3 sigma away from the true projection.
+    Returns xs [n,3], yns [n,2], Pcw [4,4]."""
+    rng = np.random.default_rng(seed)
+    unit = lambda d: (lambda v: v / np.linalg.norm(v))(rng.normal(size=d))
+    q = unit(4)
+    w, x, y, z = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    t = unit(3)
+    yn = rng.uniform(-1, 1, size=(n, 2))
+    dist = rng.uniform(0.1, 100, size=n)
+    xc = np.c_[yn, np.ones(n)] * dist[:, None]
+    xs = (xc - t) @ R                                  # Pwc * xc = R^T (xc - t)
+    gt = yn.copy()
+    sigma = pixel_sigma * 0.001
+    yns = gt + np.stack([unit(2) for _ in range(n)]) * sigma
+    for _ in range(int(n * outlier_ratio)):
+        i = int(rng.integers(0, n))
+        v = yns[i].copy()
+        if rng.uniform() > 0.5:
+            v = v + unit(2)
+        while np.linalg.norm(gt[i] - v) < 0.002 + pixel_sigma * 0.001 * 3:
+            v = v + unit(2) * 0.1 * rng.uniform(3, 10)
+        yns[i] = v
+    Pcw = np.eye(4)
+    Pcw[:3, :3], Pcw[:3, 3] = R, t
+    return xs, yns, Pcw
+
+
+def pnp_benchmark_error(T_est: np.ndarray, Pcw: np.ndarray) -> float:
+    """|angle| + |translation| of T_est * Pcw^-1 (thirdparty/lambdatwist/test_pnp.cpp:99-101); > 0.05 counts as a failure (:106)."""
+    I = T_est @ np.linalg.inv(Pcw)
+    c = np.clip((np.trace(I[:3, :3]) - 1.0) / 2.0, -1.0, 1.0)
+    return float(abs(np.arccos(c)) + np.linalg.norm(I[:3, 3]))
