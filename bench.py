@@ -311,7 +311,7 @@ def pose_parity(ctx, b, x, outs, n_frames, crops, res, dev, sp):
     F = b["images_u8"].shape[0]
     L, n = F * crops, n_frames * crops
     f32 = dict(dtype=torch.float32, device=dev)
-    img = torch.from_numpy(np.ascontiguousarray(b["images_u8"].transpose(0, 3, 1, 2))).to(dev).to(torch.float32) / 255.0     # object_slam.py:1092
+    img = torch.from_numpy(np.ascontiguousarray(b["images_u8"].transpose(0, 3, 1, 2).astype(np.float32) / 255.0)).to(dev)     # object_slam.py:1092 (host division, as there)
     boxes, bi = torch.from_numpy(b["boxes"]).to(dev), torch.from_numpy(b["box_img"]).to(dev)
     uv, cov, km = torch.empty((L, NUM_KP, 2), **f32), torch.empty((L, NUM_KP, 4), **f32), torch.empty((L, NUM_KP), **f32)
     ctx.check(lib.suo_forward(ctx.handle, p(img.contiguous()), F, H, W, p(boxes), p(bi), L, None, p(uv), p(cov), None, None, None, p(km), None, 1, sp))

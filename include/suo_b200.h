@@ -259,6 +259,42 @@ int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int
                   double* T_pnp, double* T_ba, uint8_t* kp_used, uint8_t* ba_inliers,
                   float* uv, float* cov, int on_device, void* stream);
 
+/* ---- SLAM-mode frame ------------------------------------------ */
+/* One view of ObjectSLAM.process_view with single_view_mode off (lib/object_slam.py:393-421), device resident from the camera
+ * frame to the refined camera pose:
+ *   forward on the non-symmetric crops -> gating -> per-object PnP                      (__process_objects(False), :394-397)
+ *   camera-pose vote over those PnP poses against the map                                (__estimate_camera_pose, :975-1072)
+ *   prior keypoints of the symmetric crops projected from the map, stamped on the device (:486-514, utils.make_prior_kp_input)
+ *   forward on the symmetric crops with those priors -> gating -> PnP                    (__process_objects(True), :413-418)
+ *   initialisation of unmapped objects (:577-592), re-initialisation test over the last views (__maybe_reinit_objects, :595-697)
+ *   optimize(curr_only=True): LM on the camera vertex with one unary edge per gated keypoint, its = [10] * 4 (:703-930)
+ * with no host work between the stages.  Crops [0, n_nonsym) are the non-symmetric objects, [n_nonsym, L) the symmetric ones
+ * (mesh_db[obj]["is_symmetric"], :343); L <= 128.
+ *   image_hwc [H,W,3] u8; K_cam [9] f64; boxes [L,4] xyxy f32 (already inflated, :390-391); model_kps [L,K,3] f64;
+ *   model_mask [L,K] u8; diameter [L] f64; map_valid [L] u8 and T_OtoG [L,12] f64: the map pose of each crop's object, if any
+ *   n_views: views processed so far INCLUDING this one (1 = first view: camera = identity, the PnP poses define the map)
+ *   history for the re-initialisation test: the objects' detections in up to 14 earlier views — n_hist detections, hist_crop[h] =
+ *     the crop (object) it belongs to, hist_T_GtoC [n_hist,12] the camera pose of that view, hist_K [n_hist,9] its bbox-NDC camera
+ *     matrix, hist_off [n_hist+1] its keypoint rows in hist_model_kp [N,3] f64 / hist_uv [N,2] f32 / hist_cov [N,4] f32 (or NULL)
+ *   manual_kp_std: used instead of the network covariance when a cov pointer is NULL (:1059-1061); init_with_outliers: :848-851
+ * Outputs (any may be NULL): T_GtoC [12] f64 (after the curr_only solve); status [8] i32 = {camera pose known, votes of the winning
+ * hypothesis, number of hypotheses, curr_only edges, LM trials, curr_only inlier edges, 0, 0}; T_pnp [L,16]; kp_used, ba_inliers
+ * [L,K] u8; uv [L,K,2], cov [L,K,4] f32; prior_uv [L,K,2] f32 + prior_mask [L,K] u8 (what the symmetric crops were given);
+ * K_bbox [L,9] f64; T_OtoG_out [L,12] + map_valid_out [L] (the updated map); reinit [L] u8, reinit_counts [L,2] i32 (pnp, estim).
+ * Not covered (bookkeeping the caller keeps): __backup_estimate_camera_pose (:933-973) when no non-symmetric object
+ * is in view (status[0] = 0 then), object culling (:913-930), the periodic global optimize() (suo_ba_batch). */
+int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const double* K_cam,
+                   const float* boxes, int L, int n_nonsym,
+                   const double* model_kps, const uint8_t* model_mask, const double* diameter,
+                   const uint8_t* map_valid, const double* T_OtoG, int n_views,
+                   int n_hist, const int32_t* hist_crop, const double* hist_T_GtoC, const double* hist_K,
+                   const int32_t* hist_off, const double* hist_model_kp, const float* hist_uv, const float* hist_cov,
+                   double kp_var_thresh, double bbox_thresh, double manual_kp_std, int init_with_outliers, uint64_t seed,
+                   double* T_GtoC, int32_t* status, double* T_pnp, uint8_t* kp_used, uint8_t* ba_inliers,
+                   float* uv, float* cov, float* prior_uv, uint8_t* prior_mask, double* K_bbox,
+                   double* T_OtoG_out, uint8_t* map_valid_out, uint8_t* reinit, int32_t* reinit_counts,
+                   int on_device, void* stream);
+
 /* Asynchronous, double-buffered form of suo_frames_u8 for a STREAM of frame batches (host pointers, priors == NULL):
  * submit enqueues the host->device copies of the batch on the library's copy stream and the frame path on `stream`
  * and returns at once; suo_frames_wait blocks until that slot's results are in the host output buffers (and reports

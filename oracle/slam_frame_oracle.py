@@ -1,0 +1,164 @@
+"""TEST INFRASTRUCTURE ONLY — the reference's SLAM-mode frame (ObjectSLAM.process_view with single_view_mode = False, reference
+lib/object_slam.py:327-451) restated on the CPU over the other oracles: network forward (net_oracle), prior planes
+(prior_oracle), PnP and the curr_only LM (geom), camera-pose vote and re-initialisation test (slam_oracle).  Only tests/, smoke()
+and bench.py's CPU legs may import this; the product path never does.
+
+"parity unpinned": lib/object_slam.py cannot be imported here (needs g2o / lambdatwist / glumpy) and no reference
+test covers process_view; the flow follows the cited lines.  Not restated (bookkeeping outside the hot path):
+__backup_estimate_camera_pose (:933-973, bbox-centroid PnP when no non-symmetric object is in view), the removal of objects with
+too few inliers (:913-930) and the periodic global optimisation (:443-451; csrc/ba_global.cu has its own parity tests)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import geom, net_oracle, prior_oracle, slam_oracle
+
+
+def fix_K_for_bbox_ndc(K, bbox, f32=True):
+    """utils.fix_K_for_bbox_ndc (lib/utils/utils.py:416-429).  f32: rounded through float32 as __run_kp_model stores it
+    (K_bbox_np float32, :1082,1086) and widened again (:1140); the prior projection (:500) uses the FP64 product as it is."""
+    x1, y1, x2, y2 = [float(v) for v in bbox]
+    w, h = x2 - x1, y2 - y1
+    T = np.eye(3); T[0, 2], T[1, 2] = -x1, -y1
+    S = np.eye(3); S[0, :] *= 2.0 / w; S[1, :] *= -2.0 / h; S[0, 2] -= 1.0; S[1, 2] += 1.0
+    Kb = S @ T @ np.asarray(K, np.float64)
+    return Kb.astype(np.float32).astype(np.float64) if f32 else Kb
+
+
+class State:
+    """ObjectSLAM's map (lib/object_slam.py:100-123): obj_poses {obj: T_OtoG [4,4]}, cam_poses {view: T_GtoC [3,4]},
+    detections {view: {obj: det}}, view_ids."""
+
+    def __init__(self):
+        self.obj_poses, self.cam_poses, self.detections, self.view_ids = {}, {}, {}, []
+
+
+def _to44(T):
+    T = np.asarray(T, np.float64)
+    return T if T.shape[0] == 4 else np.vstack([T, [0, 0, 0, 1.0]])
+
+
+@torch.no_grad()
+def _run_kp_model(sd, img_u8, K, obj_keys, bboxes, model_kps, model_masks, diameters, priors, res, kvt, bt, seed):
+    """__run_kp_model (:1077-1167): forward on this group's crops, gating, per-object pnp()."""
+    img = torch.from_numpy(img_u8.transpose(2, 0, 1).astype(np.float32) / 255)[None]
+    out = net_oracle.pkpnet_forward(sd, img, [torch.as_tensor(np.asarray(bboxes, np.float32))],
+                                    None if priors is None else [torch.from_numpy(priors)], (res, res))
+    uv, cov, km = out["uv"].numpy(), out["cov"].numpy(), out["kp_mask"].numpy()
+    masks = net_oracle.gate_keypoints(uv, cov, km, np.asarray(model_masks, bool), bt, kvt)
+    dets = []
+    for k in range(len(bboxes)):
+        m = masks[k]
+        Kb = fix_K_for_bbox_ndc(K, bboxes[k])
+        kp_model, uv_pred, cov_pred = model_kps[k][m].astype(np.float64), uv[k][m].astype(np.float64), cov[k][m]
+        pose = None
+        r = geom.pnp(kp_model, uv_pred, Kb, seed=seed, obj_key=int(obj_keys[k]))
+        if r is not None and r[0][2, 3] > 0.5 * diameters[k] and m.sum() >= 4:
+            pose = _to44(r[0])
+        dets.append(dict(pose=pose, inliers=np.ones(int(m.sum()), bool), kp_mask=m, model_kp=kp_model, uv_pred=uv_pred, cov_pred=cov_pred,
+                         K=Kb, uv_full=uv[k], cov_full=cov[k], bbox=np.asarray(bboxes[k])))
+    return dets
+
+
+def _process_objects(st, sd, is_sym, view_id, img, K, idx, keys, obj_ids, bboxes, model_kps, model_masks, diameters, res, kvt, bt, seed, first):
+    """__process_objects (:470-593) for the crops `idx` of the frame; keys[c] = RANSAC object key of crop c (its position in the
+    non-symmetric-first order, the order the crops are processed in)."""
+    if len(idx) == 0:
+        return {}
+    priors, prior_uv = None, {}
+    if is_sym and view_id in st.cam_poses:                      # :486-520
+        priors = np.zeros((len(idx), model_masks.shape[1], res, res), np.float32)
+        T_GtoC = _to44(st.cam_poses[view_id])
+        for q, c in enumerate(idx):
+            o = obj_ids[c]
+            if o not in st.obj_poses:
+                continue
+            m = model_masks[c].astype(bool)
+            T_OtoC = T_GtoC @ _to44(st.obj_poses[o])
+            pc = model_kps[c][m] @ T_OtoC[:3, :3].T + T_OtoC[:3, 3]
+            uvd = pc @ fix_K_for_bbox_ndc(K, bboxes[c], f32=False).T
+            if np.all(uvd[:, 2] > 0):
+                full = np.zeros((len(m), 2), np.float32)
+                full[m] = uvd[:, :2] / uvd[:, 2:3]
+                prior_uv[o] = full
+                priors[q] = prior_oracle.make_prior_kp_input(full, m, (res, res), ndc=True)
+    dets = _run_kp_model(sd, img, K, keys[idx], bboxes[idx], model_kps[idx], model_masks[idx], diameters[idx], priors, res, kvt, bt, seed)
+    detection = {}
+    for q, c in enumerate(idx):
+        o = obj_ids[c]
+        detection[o] = dict(dets[q], prior_uv=prior_uv.get(o), crop=int(c))
+        if first and dets[q]["pose"] is not None:               # :541-556: the first view defines the world frame
+            st.obj_poses[o] = dets[q]["pose"] if view_id not in st.cam_poses else slam_oracle._inv_se3(_to44(st.cam_poses[view_id])) @ dets[q]["pose"]
+    st.detections.setdefault(view_id, {}).update(detection)
+    if view_id not in st.cam_poses:                              # :566-575
+        if first:
+            st.cam_poses[view_id] = np.eye(4)[:3]
+        else:
+            cam, counts, _ = slam_oracle.estimate_camera_pose(st.obj_poses, st.detections[view_id])
+            if cam is None:
+                return detection
+            st.cam_poses[view_id] = cam[:3]
+        st.view_ids.append(view_id)
+    for c in idx:                                                # :577-592: objects that could not be initialised before
+        o = obj_ids[c]
+        if o not in st.obj_poses and detection[o]["pose"] is not None:
+            st.obj_poses[o] = slam_oracle._inv_se3(_to44(st.cam_poses[view_id])) @ detection[o]["pose"]
+    return detection
+
+
+def _optimize_curr_only(st, view_id, init_with_outliers):
+    """optimize(curr_only=True) (:703-930): one free camera vertex, one EdgeSE3ProjectFromFixedObject per gated keypoint of every
+    mapped object of the current view, its = [10] * 4."""
+    if view_id not in st.cam_poses:
+        return None
+    dets = [(o, d) for o, d in st.detections[view_id].items() if o in st.obj_poses]
+    if sum(int(np.count_nonzero(d["inliers"])) for _, d in dets) < 3:      # :726-728
+        return None
+    p, cam_k, uv, info, owner = [], [], [], [], []
+    for o, d in dets:
+        T = _to44(st.obj_poses[o])
+        for k in range(len(d["uv_pred"])):
+            p.append(T[:3, :3] @ d["model_kp"][k] + T[:3, 3])
+            cam_k.append([d["K"][0, 0], d["K"][1, 1], d["K"][0, 2], d["K"][1, 2]])
+            uv.append(d["uv_pred"][k])
+            S = d["cov_pred"][k].astype(np.float64)
+            det = S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]
+            info.append([S[1, 1] / det, -S[0, 1] / det, -S[1, 0] / det, S[0, 0] / det])
+            owner.append((o, k))
+    n = len(p)
+    if n == 0:
+        return None
+    P, inl, stats = geom.ba_optimize(np.asarray(st.cam_poses[view_id])[None, :3], np.zeros(1, np.uint8), np.full(n, -1, np.int32), np.zeros(n, np.int32),
+                                     np.asarray(cam_k), np.asarray(p), np.asarray(uv), np.asarray(info), np.ones(n), [10, 10, 10, 10],
+                                     init_with_outliers=init_with_outliers)
+    st.cam_poses[view_id] = P[0]
+    for (o, k), v in zip(owner, inl):
+        st.detections[view_id][o]["inliers"][k] = v
+    return stats
+
+
+def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, model_masks, is_sym, diameters, res=256,
+                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0):
+    """process_view (:327-451), SLAM mode, no external camera pose, bbox_inflate = 0.  Symmetric crops get the prior heat maps."""
+    obj_ids, bboxes = list(obj_ids), np.asarray(bboxes, np.float32)
+    model_kps, model_masks, is_sym, diameters = np.asarray(model_kps), np.asarray(model_masks).astype(bool), np.asarray(is_sym, bool), np.asarray(diameters, float)
+    first = len(st.view_ids) == 0
+    non, sym = np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]
+    keys = np.zeros(len(obj_ids), int)
+    keys[np.concatenate([non, sym]).astype(int)] = np.arange(len(obj_ids))
+    args = (keys, obj_ids, bboxes, model_kps, model_masks, diameters, res, kp_var_thresh, bbox_thresh, seed, first)
+    _process_objects(st, sd, False, view_id, img_u8, K, non, *args)
+    if view_id not in st.cam_poses:                              # :404-411
+        if first:
+            st.view_ids.append(view_id)
+            st.cam_poses[view_id] = np.eye(4)[:3]
+        else:
+            return dict(cam_ok=False)                            # (the reference would try __backup_estimate_camera_pose here)
+    if len(sym):
+        _process_objects(st, sd, True, view_id, img_u8, K, sym, *args)
+    reinit, counts, _ = slam_oracle.maybe_reinit_objects(st.obj_poses, st.cam_poses, st.detections, st.view_ids, view_id, 15, manual_kp_std)
+    for o, T in reinit.items():                                  # :683-690
+        st.obj_poses[o] = T
+    stats = _optimize_curr_only(st, view_id, init_with_outliers)
+    return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats)

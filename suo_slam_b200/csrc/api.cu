@@ -178,6 +178,7 @@ struct CtxExtra {
   DevScratch bg;        // coupled-graph BA structure + workspace (ba_global.cu)
   int32_t* pnp_off = nullptr;   // row offsets c * num_kp of the gated keypoint lists (grown on demand)
   int pnp_off_n = 0;
+  uint64_t* pnp_keys = nullptr; // RANSAC object keys 0, 1, 2, ... (a frame's crop index, also for the second crop group of a SLAM-mode frame)
   bool loaded = false;
   // double-buffered asynchronous frame batches (suo_frames_u8_submit / suo_frames_wait): per slot the staged inputs and
   // results and two events; one copy stream shared by the slots so that the host->device copy of batch i+1 overlaps batch i
@@ -517,6 +518,7 @@ void suo_destroy(suo_ctx* ctx) {
     if (x->fr.d) cudaFree(x->fr.d);
     if (x->bg.d) cudaFree(x->bg.d);
     if (x->pnp_off) cudaFree(x->pnp_off);
+    if (x->pnp_keys) cudaFree(x->pnp_keys);
     delete x;
   }
   delete ctx;
@@ -1342,6 +1344,27 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   return SUO_OK;
 }
 
+// offsets c * K and keys c of the per-crop keypoint lists: they never change, so they are built once per context and the device path stays
+// free of host synchronisation
+static int ensure_pnp_tables(suo_ctx* ctx, int L, cudaStream_t s) {
+  CtxExtra* xo = X(ctx);
+  if (xo->pnp_off_n >= L) return SUO_OK;
+  const int n = std::max(L, ctx->max_crops), K = ctx->num_kp;
+  std::vector<int32_t> off(n);
+  std::vector<uint64_t> keys(n);
+  for (int c = 0; c < n; ++c) { off[c] = c * K; keys[c] = (uint64_t)c; }
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));        // (re)allocation only: earlier work may still read the old arrays
+  if (xo->pnp_off) cudaFree(xo->pnp_off);
+  if (xo->pnp_keys) cudaFree(xo->pnp_keys);
+  xo->pnp_off = nullptr; xo->pnp_keys = nullptr; xo->pnp_off_n = 0;
+  SUO_CUDA_TRY(ctx, cudaMalloc(&xo->pnp_off, off.size() * sizeof(int32_t)));
+  SUO_CUDA_TRY(ctx, cudaMalloc(&xo->pnp_keys, keys.size() * sizeof(uint64_t)));
+  SUO_CUDA_TRY(ctx, cudaMemcpy(xo->pnp_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  SUO_CUDA_TRY(ctx, cudaMemcpy(xo->pnp_keys, keys.data(), keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  xo->pnp_off_n = n;
+  return SUO_OK;
+}
+
 // Device-resident part after the network: gating -> PnP -> single-view BA.  All pointers are device
 // pointers; d_uv/d_cov/d_mask are the network outputs (or caller-provided keypoints).
 static int solve_keypoints_device(suo_ctx* ctx, Bump& bp, const float* d_uv, const float* d_cov, const float* d_mask,
@@ -1359,19 +1382,9 @@ static int solve_keypoints_device(suo_ctx* ctx, Bump& bp, const float* d_uv, con
                                d_ys, d_cnt, d_kpi, d_used, s);
   if (rc) return rc;
   // PnP: object c owns rows [c*K, c*K + count[c])
-  // (the offsets c*K never change: built once per context, so the device path stays free of host synchronisation)
+  rc = ensure_pnp_tables(ctx, L, s);
+  if (rc) return rc;
   CtxExtra* xo = X(ctx);
-  if (xo->pnp_off_n < L) {
-    const int n = std::max(L, ctx->max_crops);
-    std::vector<int32_t> off(n);
-    for (int c = 0; c < n; ++c) off[c] = c * K;
-    SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));        // (re)allocation only: earlier work may still read the old array
-    if (xo->pnp_off) cudaFree(xo->pnp_off);
-    xo->pnp_off = nullptr; xo->pnp_off_n = 0;
-    SUO_CUDA_TRY(ctx, cudaMalloc(&xo->pnp_off, off.size() * sizeof(int32_t)));
-    SUO_CUDA_TRY(ctx, cudaMemcpy(xo->pnp_off, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    xo->pnp_off_n = n;
-  }
   const int32_t* d_off = xo->pnp_off;
   rc = launch_pnp_batch_counts(ctx, d_xs, d_ys, d_off, d_cnt, L, 0.001, seed, nullptr, d_Tpnp, d_pst, s, K);
   if (rc) return rc;
@@ -1642,6 +1655,128 @@ int suo_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const dou
   if (J_cam) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(J_cam, d_jc, 96 * n, cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
   return SUO_OK;
+}
+
+int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const double* K_cam, const float* boxes, int L, int n_nonsym,
+                   const double* model_kps, const uint8_t* model_mask, const double* diameter, const uint8_t* map_valid, const double* T_OtoG,
+                   int n_views, int n_hist, const int32_t* hist_crop, const double* hist_T_GtoC, const double* hist_K, const int32_t* hist_off,
+                   const double* hist_model_kp, const float* hist_uv, const float* hist_cov, double kp_var_thresh, double bbox_thresh,
+                   double manual_kp_std, int init_with_outliers, uint64_t seed, double* T_GtoC, int32_t* status, double* T_pnp, uint8_t* kp_used,
+                   uint8_t* ba_inliers, float* uv, float* cov, float* prior_uv, uint8_t* prior_mask, double* K_bbox, double* T_OtoG_out,
+                   uint8_t* map_valid_out, uint8_t* reinit, int32_t* reinit_counts, int on_device, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  CtxExtra* x = X(ctx);
+  if (!x->loaded) { ctx->set_error("suo_slam_frame before suo_load_weights", __FILE__, __LINE__); return SUO_E_STATE; }
+  if (L <= 0 || L > ctx->max_crops || L > 128 || n_nonsym < 0 || n_nonsym > L || n_views < 1 || n_hist < 0 || !image_hwc || !K_cam || !boxes || !model_kps ||
+      !model_mask || !diameter || !map_valid || !T_OtoG || (n_hist > 0 && (!hist_crop || !hist_T_GtoC || !hist_K || !hist_off || !hist_model_kp || !hist_uv)) ||
+      !(manual_kp_std > 0)) {
+    ctx->set_error("suo_slam_frame: bad crop count / null input", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  NetState& N = x->net;
+  const int K = ctx->num_kp, n1 = n_nonsym, n2 = L - n_nonsym;
+  const size_t LK = (size_t)L * K, n_im = (size_t)3 * H * W;
+  size_t NH = 0;
+  if (n_hist > 0 && !on_device) {
+    for (int h = 0; h < n_hist; ++h) if (hist_off[h + 1] < hist_off[h] || hist_crop[h] < 0 || hist_crop[h] >= L) { ctx->set_error("suo_slam_frame: bad history arrays", __FILE__, __LINE__); return SUO_E_INVALID; }
+    NH = (size_t)hist_off[n_hist];
+  }
+  const size_t in_bytes = n_im + (size_t)L * (16 + 8 + 1 + 96) + LK * 25 + 72 + (size_t)n_hist * (4 + 96 + 72 + 4) + 4 + NH * (24 + 8 + 16) + 32 * 256;
+  const size_t out_bytes = (size_t)L * (128 + 72 + 96 + 1 + 1 + 8 + 4) + LK * (1 + 1 + 8 + 16 + 8 + 1) + 96 + 32 + 32 * 256;
+  const size_t work_bytes = (size_t)L * (72 + 4 + 20) + LK * (24 + 16 + 4 + 4 + 4 + 4 + 32 + 24 + 16 + 32 + 1 + 4 + 16 + 1 + 1) + 4096 + 48 * 256;
+  rc = x->fr.grow(ctx, in_bytes + out_bytes + work_bytes);
+  if (rc) return rc;
+  rc = ensure_pnp_tables(ctx, L, s);
+  if (rc) return rc;
+  Bump bp{static_cast<uint8_t*>(x->fr.d)};
+  // ---- inputs ----
+  const uint8_t* d_im = image_hwc; const double* d_Kc = K_cam; const float* d_box = boxes; const double* d_mk = model_kps; const uint8_t* d_mm = model_mask;
+  const double* d_diam = diameter; const uint8_t* d_mv = map_valid; const double* d_To = T_OtoG;
+  const int32_t* d_hc = hist_crop; const double* d_hT = hist_T_GtoC; const double* d_hK = hist_K; const int32_t* d_ho = hist_off;
+  const double* d_hm = hist_model_kp; const float* d_hu = hist_uv; const float* d_hcv = hist_cov;
+  if (!on_device) {
+#define STAGE(T, dst, src, n) T* dst##_ = bp.take<T>(n); SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst##_, src, (n) * sizeof(T), cudaMemcpyHostToDevice, s)); dst = dst##_;
+    STAGE(uint8_t, d_im, image_hwc, n_im) STAGE(double, d_Kc, K_cam, 9) STAGE(float, d_box, boxes, 4 * (size_t)L) STAGE(double, d_mk, model_kps, 3 * LK)
+    STAGE(uint8_t, d_mm, model_mask, LK) STAGE(double, d_diam, diameter, (size_t)L) STAGE(uint8_t, d_mv, map_valid, (size_t)L) STAGE(double, d_To, T_OtoG, 12 * (size_t)L)
+    if (n_hist > 0) {
+      STAGE(int32_t, d_hc, hist_crop, (size_t)n_hist) STAGE(double, d_hT, hist_T_GtoC, 12 * (size_t)n_hist) STAGE(double, d_hK, hist_K, 9 * (size_t)n_hist)
+      STAGE(int32_t, d_ho, hist_off, (size_t)n_hist + 1) STAGE(double, d_hm, hist_model_kp, 3 * NH) STAGE(float, d_hu, hist_uv, 2 * NH)
+      if (hist_cov) { STAGE(float, d_hcv, hist_cov, 4 * NH) }
+    }
+#undef STAGE
+  }
+  // ---- outputs (device side) ----
+#define OUT(T, name, user, n) T* name = (on_device && user) ? user : bp.take<T>(n);
+  OUT(double, o_cam, T_GtoC, 12) OUT(int32_t, o_st, status, 8) OUT(double, o_Tpnp, T_pnp, 16 * (size_t)L) OUT(uint8_t, o_used, kp_used, LK)
+  OUT(uint8_t, o_bain, ba_inliers, LK) OUT(float, o_uv, uv, 2 * LK) OUT(float, o_cov, cov, 4 * LK) OUT(float, o_puv, prior_uv, 2 * LK)
+  OUT(uint8_t, o_pm, prior_mask, LK) OUT(double, o_kb, K_bbox, 9 * (size_t)L) OUT(double, o_To, T_OtoG_out, 12 * (size_t)L)
+  OUT(uint8_t, o_mv, map_valid_out, (size_t)L) OUT(uint8_t, o_ri, reinit, (size_t)L) OUT(int32_t, o_rc, reinit_counts, 2 * (size_t)L)
+#undef OUT
+  // ---- workspace ----
+  double* w_kraw = bp.take<double>(9 * (size_t)L); float* w_mask = bp.take<float>(LK); int32_t* w_bi = bp.take<int32_t>(L);
+  double* w_xs = bp.take<double>(3 * LK); double* w_ys = bp.take<double>(2 * LK); int32_t* w_cnt = bp.take<int32_t>(L); int32_t* w_kpi = bp.take<int32_t>(LK);
+  int32_t* w_pst = bp.take<int32_t>(5 * (size_t)L);
+  double* b_poses = bp.take<double>(12); uint8_t* b_fixed = bp.take<uint8_t>(1); int32_t* b_pv = bp.take<int32_t>(2); int32_t* b_vc = bp.take<int32_t>(1);
+  int32_t* b_pe = bp.take<int32_t>(2); int32_t* b_ec = bp.take<int32_t>(1); int32_t* b_eo = bp.take<int32_t>(LK); int32_t* b_ecam = bp.take<int32_t>(LK);
+  double* b_ck = bp.take<double>(4 * LK); double* b_p = bp.take<double>(3 * LK); double* b_uv = bp.take<double>(2 * LK); double* b_info = bp.take<double>(4 * LK);
+  uint8_t* b_inl = bp.take<uint8_t>(LK); int32_t* b_src = bp.take<int32_t>(LK); double* b_err = bp.take<double>(2 * LK); uint8_t* b_lvl = bp.take<uint8_t>(LK);
+  int8_t* b_fv = bp.take<int8_t>(LK); int32_t* b_its = bp.take<int32_t>(4); int32_t* b_st = bp.take<int32_t>(3);
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(w_bi, 0, L * sizeof(int32_t), s));            // one image: every crop comes from frame 0
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(o_st, 0, 8 * sizeof(int32_t), s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(o_puv, 0, 2 * LK * sizeof(float), s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(o_pm, 0, LK, s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(w_cnt, 0, L * sizeof(int32_t), s));
+  rc = launch_slam_kbbox(ctx, d_Kc, d_box, L, w_kraw, o_kb, s);
+  if (rc) return rc;
+  auto group = [&](int c0, int n, bool with_priors) -> int {      // forward + gate + PnP of crops [c0, c0 + n)
+    const size_t o = (size_t)c0 * K;
+    int r = forward_impl(ctx, d_im, 1, H, W, d_box + 4 * (size_t)c0, w_bi, n, nullptr, with_priors ? o_puv + 2 * o : nullptr, with_priors ? o_pm + o : nullptr,
+                         o_uv + 2 * o, o_cov + 4 * o, nullptr, nullptr, nullptr, w_mask + o, nullptr, 1, stream, 1);
+    if (r) return r;
+    r = launch_gate_compact(ctx, o_uv + 2 * o, o_cov + 4 * o, w_mask + o, d_mm + o, d_mk + 3 * o, o_kb + 9 * (size_t)c0, n, K, (float)kp_var_thresh,
+                            (float)bbox_thresh, w_xs + 3 * o, w_ys + 2 * o, w_cnt + c0, w_kpi + o, o_used + o, s);
+    if (r) return r;
+    // rows are addressed from the start of each crop's own slot, so the shifted base pointers keep offsets c * K valid
+    return launch_pnp_batch_counts(ctx, w_xs + 3 * o, w_ys + 2 * o, x->pnp_off, w_cnt + c0, n, 0.001, seed, x->pnp_keys + c0, o_Tpnp + 16 * (size_t)c0,
+                                   w_pst + 5 * (size_t)c0, s, K);
+  };
+  if (n1 > 0) { rc = group(0, n1, false); if (rc) return rc; }
+  else {
+    SUO_CUDA_TRY(ctx, cudaMemsetAsync(o_used, 0, LK, s));
+  }
+  rc = launch_slam_vote(ctx, n1, K, n_views == 1, o_Tpnp, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, d_diam, d_mv, d_To, manual_kp_std, 5.991, o_cam, o_st, s);
+  if (rc) return rc;
+  if (n2 > 0) {
+    rc = launch_slam_prior_uv(ctx, n1, L, K, o_st, o_cam, d_mv, d_To, d_mk, d_mm, w_kraw, o_puv, o_pm, s);
+    if (rc) return rc;
+    rc = group(n1, n2, true);
+    if (rc) return rc;
+    rc = launch_slam_drop_group(ctx, n1, L, K, o_st, w_cnt, o_used, o_Tpnp, s);
+    if (rc) return rc;
+  }
+  rc = launch_slam_map_update(ctx, L, K, n_views, n_hist, o_st, o_cam, o_Tpnp, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, d_diam, d_mv, d_To, o_mv, o_To,
+                              d_hc, d_hT, d_hK, d_ho, d_hm, d_hu, d_hcv, manual_kp_std, 5.991, o_rc, o_ri, s);
+  if (rc) return rc;
+  rc = launch_slam_ba_assemble(ctx, L, K, o_st, o_cam, o_mv, o_To, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, b_poses, b_fixed, b_pv, b_vc, b_pe, b_ec, b_eo, b_ecam,
+                               b_ck, b_p, b_uv, b_info, b_inl, b_src, s);
+  if (rc) return rc;
+  static const int32_t its_host[4] = {10, 10, 10, 10};   // curr_only (object_slam.py:845-846)
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b_its, its_host, sizeof(its_host), cudaMemcpyHostToDevice, s));
+  SUO_CUDA_TRY(ctx, cudaMemsetAsync(b_st, 0, 3 * sizeof(int32_t), s));
+  rc = launch_ba_batch_scratch(ctx, 1, b_pv, b_pe, b_poses, b_fixed, b_eo, b_ecam, b_ck, b_p, b_uv, b_info, b_inl, b_its, 4, 2.4476519768340177 /* sqrt(5.991) */,
+                               5.991, init_with_outliers, b_st, b_err, b_lvl, b_fv, s, b_vc, b_ec);
+  if (rc) return rc;
+  rc = launch_slam_ba_scatter(ctx, L, K, b_ec, b_src, b_inl, b_poses, b_st, o_cam, o_bain, o_st, s);
+  if (rc || on_device) return rc;
+#define D2H(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, s))
+  D2H(T_GtoC, o_cam, 96); D2H(status, o_st, 32); D2H(T_pnp, o_Tpnp, 128 * (size_t)L); D2H(kp_used, o_used, LK); D2H(ba_inliers, o_bain, LK);
+  D2H(uv, o_uv, 8 * LK); D2H(cov, o_cov, 16 * LK); D2H(prior_uv, o_puv, 8 * LK); D2H(prior_mask, o_pm, LK); D2H(K_bbox, o_kb, 72 * (size_t)L);
+  D2H(T_OtoG_out, o_To, 96 * (size_t)L); D2H(map_valid_out, o_mv, (size_t)L); D2H(reinit, o_ri, (size_t)L); D2H(reinit_counts, o_rc, 8 * (size_t)L);
+#undef D2H
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return suo_check_range(ctx);
 }
 
 int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W, const float* boxes,

@@ -178,6 +178,27 @@ int launch_chi2_counts(suo_ctx* ctx, int n_pairs, const double* T, const int32_t
                        const double* model_kp, const double* K, const float* uv, const float* cov, const uint8_t* use,
                        double manual_kp_std, double gate, int32_t* counts, cudaStream_t s);
 
+// SLAM-mode frame glue (slam.cu)
+int launch_slam_kbbox(suo_ctx* ctx, const double* Kc, const float* boxes, int L, double* raw, double* f32, cudaStream_t s);
+int launch_slam_vote(suo_ctx* ctx, int n1, int K, int first_view, const double* T_pnp, const int32_t* counts, const int32_t* kp_index,
+                     const double* xs, const float* uv, const float* cov, const double* Kb, const double* diameter, const uint8_t* map_valid,
+                     const double* T_OtoG, double manual_kp_std, double gate, double* T_GtoC, int32_t* status, cudaStream_t s);
+int launch_slam_prior_uv(suo_ctx* ctx, int n1, int L, int K, const int32_t* status, const double* T_GtoC, const uint8_t* map_valid, const double* T_OtoG,
+                         const double* model_kps, const uint8_t* model_mask, const double* Kb_raw, float* prior_uv, uint8_t* prior_mask, cudaStream_t s);
+int launch_slam_drop_group(suo_ctx* ctx, int n1, int L, int K, const int32_t* status, int32_t* counts, uint8_t* kp_used, double* T_pnp, cudaStream_t s);
+int launch_slam_map_update(suo_ctx* ctx, int L, int K, int n_views, int n_hist, const int32_t* status, const double* T_GtoC, const double* T_pnp,
+                           const int32_t* counts, const int32_t* kp_index, const double* xs, const float* uv, const float* cov, const double* Kb,
+                           const double* diameter, const uint8_t* map_valid_in, const double* T_OtoG_in, uint8_t* map_valid, double* T_OtoG,
+                           const int32_t* hist_crop, const double* hist_T_GtoC, const double* hist_K, const int32_t* hist_off,
+                           const double* hist_model_kp, const float* hist_uv, const float* hist_cov, double manual_kp_std, double gate,
+                           int32_t* rcounts, uint8_t* reinit, cudaStream_t s);
+int launch_slam_ba_assemble(suo_ctx* ctx, int L, int K, const int32_t* status, const double* T_GtoC, const uint8_t* map_valid, const double* T_OtoG,
+                            const int32_t* counts, const int32_t* kp_index, const double* xs, const float* uv, const float* cov, const double* Kb,
+                            double* poses, uint8_t* fixed, int32_t* prob_vert, int32_t* vert_cnt, int32_t* prob_edge, int32_t* edge_cnt, int32_t* e_obj,
+                            int32_t* e_cam, double* cam_k, double* p, double* uvd, double* info, uint8_t* inliers, int32_t* edge_src, cudaStream_t s);
+int launch_slam_ba_scatter(suo_ctx* ctx, int L, int K, const int32_t* edge_cnt, const int32_t* edge_src, const uint8_t* inliers, const double* poses,
+                           const int32_t* ba_stats, double* T_GtoC, uint8_t* ba_inliers, int32_t* status, cudaStream_t s);
+
 struct suo_ctx {
   int device = 0;
   int max_crops = 0, crop_res = 0, num_kp = 0;

@@ -5,6 +5,7 @@
 // lib/object_slam.py:1100-1115 (.cpu().numpy()), :1123-1165 (per-object pnp) and :745-837
 // (per-edge pybind graph construction).
 #include "common.cuh"
+#include "chi2.cuh"
 
 namespace {
 
@@ -233,23 +234,7 @@ __global__ void chi2_count_kernel(const double* __restrict__ T, const int32_t* _
   int cnt = 0;
   for (int r = det_off[d] + lane; r < det_off[d + 1]; r += 32) {
     if (use && !use[r]) continue;
-    const double x = model_kp[3 * r], y = model_kp[3 * r + 1], z = model_kp[3 * r + 2];
-    const double pc0 = P[0] * x + P[1] * y + P[2] * z + P[3];
-    const double pc1 = P[4] * x + P[5] * y + P[6] * z + P[7];
-    const double pc2 = P[8] * x + P[9] * y + P[10] * z + P[11];
-    const double w = Kd[6] * pc0 + Kd[7] * pc1 + Kd[8] * pc2;
-    if (!(w > 0)) continue;
-    const double r0 = (double)uv[2 * r] - (Kd[0] * pc0 + Kd[1] * pc1 + Kd[2] * pc2) / w;
-    const double r1 = (double)uv[2 * r + 1] - (Kd[3] * pc0 + Kd[4] * pc1 + Kd[5] * pc2) / w;
-    double chi2;
-    if (cov) {
-      const double a = fmax((double)cov[4 * r], 1e-4), b = (double)cov[4 * r + 1], c = (double)cov[4 * r + 2], e = fmax((double)cov[4 * r + 3], 1e-4);
-      const double det = a * e - b * c;
-      chi2 = (r0 * (e * r0 - b * r1) + r1 * (-c * r0 + a * r1)) / det;
-    } else {
-      chi2 = (r0 * r0 + r1 * r1) * inv_manual_var;
-    }
-    cnt += (chi2 <= gate) ? 1 : 0;
+    cnt += chi2_inlier(P, Kd, model_kp + 3 * (size_t)r, uv[2 * r], uv[2 * r + 1], cov ? cov + 4 * (size_t)r : nullptr, inv_manual_var, gate) ? 1 : 0;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);

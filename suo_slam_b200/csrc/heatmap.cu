@@ -3,8 +3,9 @@
 // Replaces reference lib/models/pkpnet.py:13-63 (spatial_softmax, mesh_grid,
 // post_process_kp) and :74-78,116-118 (classifier), which materialise
 // [B,K,H,W,2] and [B,K,H,W,2,2] temporaries; here one CTA owns one (b,k) map.
-// 64x64 and 128x128 maps (what the network produces) run heatmap_reduce_reg_kernel: the map is read
-// ONCE into registers and reduced with three barriers.  Other sizes run the generic three-pass kernel
+// 64x64 maps run heatmap_reduce_warp_kernel (one warp per map, the map in registers, shuffles only); 128x128
+// maps run heatmap_reduce_reg_kernel (one CTA per map, the map read ONCE into registers, three barriers).
+// Other sizes run the generic three-pass kernel
 // (the map stays in L1 between passes).  Either way DRAM traffic is the algorithmic H*W*4 bytes per
 // map.  HBM-bound: no tensor cores on purpose.
 //
@@ -223,6 +224,87 @@ heatmap_reduce_reg_kernel(const float* __restrict__ logits, int H, int W, float*
   }
 }
 
+// 64x64 maps, one WARP per map: each lane holds 32 float4 (all 32 loads of a lane are issued back to back: 16 KB in flight
+// per warp), the reductions are warp shuffles only — no shared memory, no block barrier — so the warps of an SM sit in
+// different phases and the memory pipe never drains while a CTA computes.  The kernel is issue-bound once the loads
+// overlap (4096 expf per map), so the element loop is kept to two passes: (1) max / first argmax / plain sum; (2) e =
+// expf(x - m) with S and the first AND second moments about the ARGMAX pixel: the shifted coordinates (h - h0) / 32 are exact
+// in FP32 and, on a peaky map, small where e is large, so cov = E[dd^T] - E[d] E[d]^T loses nothing to cancellation
+// (4e-7 worst case against FP64 over flat, noisy, single- and double-peak maps); uv = grid(argmax) + E[d].
+constexpr int kWarpMapThreads = 128;
+__global__ void __launch_bounds__(kWarpMapThreads, 3)
+heatmap_reduce_warp_kernel(const float* __restrict__ logits, int n_maps, float* __restrict__ pooled, float* __restrict__ uv,
+                           float* __restrict__ cov, float* __restrict__ prob, int32_t* __restrict__ argmax) {
+  constexpr int H = 64, W = 64, HW = H * W, NV = HW / (4 * 32);
+  const int lane = threadIdx.x & 31;
+  const int map = blockIdx.x * (kWarpMapThreads / 32) + (threadIdx.x >> 5);
+  if (map >= n_maps) return;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(logits + (size_t)map * HW);
+  constexpr float inv_half = 1.0f / (0.5f * (float)H);
+  float e[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float4 v = __ldg(x4 + lane + 32 * j);
+    e[j][0] = v.x; e[j][1] = v.y; e[j][2] = v.z; e[j][3] = v.w;
+  }
+  float m = -INFINITY, s = 0.f;
+  int mi = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      s += e[j][q];
+      if (e[j][q] > m) { m = e[j][q]; mi = 4 * (lane + 32 * j) + q; }   // ascending index per lane => first occurrence
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+  }
+  const float total = warp_sum(s);
+  // float4 i = lane + 32 j lies in row 2 j + (lane >> 4), columns 4 (lane & 15) .. + 3
+  const int h0 = mi >> 6, w0 = mi & 63;
+  const int hl = (lane >> 4) - h0, wl = 4 * (lane & 15) - w0;
+  float gy[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) gy[q] = -(float)(wl + q) * inv_half;           // yy[h,w] = -r[w], shifted by the argmax column
+  float S = 0.f, sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float gx = (float)(2 * j + hl) * inv_half;                         // xx[h,w] = r[h], shifted by the argmax row
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float ev = expf(e[j][q] - m);
+      e[j][q] = ev;
+      S += ev;
+      const float ax = ev * gx, ay = ev * gy[q];
+      sx += ax; sy += ay;
+      sxx = fmaf(ax, gx, sxx); sxy = fmaf(ax, gy[q], sxy); syy = fmaf(ay, gy[q], syy);
+    }
+  }
+  S = warp_sum(S); sx = warp_sum(sx); sy = warp_sum(sy); sxx = warp_sum(sxx); sxy = warp_sum(sxy); syy = warp_sum(syy);
+  const float invS = 1.0f / S;
+  if (prob) {
+    float4* __restrict__ p4 = reinterpret_cast<float4*>(prob + (size_t)map * HW);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) p4[lane + 32 * j] = make_float4(e[j][0] * invS, e[j][1] * invS, e[j][2] * invS, e[j][3] * invS);
+  }
+  if (lane == 0) {
+    const float mx = sx * invS, my = sy * invS;
+    if (uv) {
+      uv[2 * map] = (((float)h0 + 0.5f) * inv_half - 1.0f) + mx;
+      uv[2 * map + 1] = -(((float)w0 + 0.5f) * inv_half - 1.0f) + my;
+    }
+    if (cov) {
+      const float cxy = sxy * invS - mx * my;
+      cov[4 * map] = sxx * invS - mx * mx; cov[4 * map + 1] = cxy; cov[4 * map + 2] = cxy; cov[4 * map + 3] = syy * invS - my * my;
+    }
+    if (argmax) argmax[map] = mi;
+    if (pooled) pooled[map] = total / (float)HW;
+  }
+}
+
 // kp_mask_logits = W * relu(mean_hw(raw)) + b ; kp_mask = sigmoid (pkpnet.py:74-78,116-118)
 __global__ void classifier_kernel(const float* __restrict__ pooled, const float* __restrict__ Wc,
                                   const float* __restrict__ bc, int K, float* __restrict__ mask_logits,
@@ -245,7 +327,9 @@ int launch_heatmap_reduce(suo_ctx* ctx, const float* logits, int B, int K, int H
     ctx->set_error("heatmap_reduce: need square maps with W % 4 == 0", __FILE__, __LINE__);
     return SUO_E_INVALID;
   }
-  if (H * W == 4 * 4 * kThreads)
+  if (H == 64 && W == 64)
+    heatmap_reduce_warp_kernel<<<(B * K + kWarpMapThreads / 32 - 1) / (kWarpMapThreads / 32), kWarpMapThreads, 0, s>>>(logits, B * K, pooled_scratch, uv, cov, prob, argmax);
+  else if (H * W == 4 * 4 * kThreads)
     heatmap_reduce_reg_kernel<4><<<B * K, kThreads, 0, s>>>(logits, H, W, pooled_scratch, uv, cov, prob, argmax);
   else if (H * W == 16 * 4 * kThreads)
     heatmap_reduce_reg_kernel<16><<<B * K, kThreads, 0, s>>>(logits, H, W, pooled_scratch, uv, cov, prob, argmax);

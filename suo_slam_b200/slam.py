@@ -110,3 +110,89 @@ def maybe_reinit_objects(obj_poses, cam_poses, detections, view_ids, view_id, ch
             num[obj_ids[j]][key] += int(v)
     new = {o: Ts_pnp_G[j] for j, o in enumerate(obj_ids) if num[o]["pnp"] >= 3 and num[o]["pnp"] > 3 * num[o]["estim"]}   # :683-687
     return (new, num) if return_counts else new
+
+
+# ---- a whole SLAM-mode view on the device ---------------------------------------------------------------------------
+class SlamTracker:
+    """Host mirror of ObjectSLAM's per-view tracking state around ONE ``suo_slam_frame`` call per view (lib/object_slam.py:327-421):
+    the map ``obj_poses`` {obj: T_OtoG [3,4]}, ``cam_poses`` {view: T_GtoC [3,4]}, ``detections`` {view: {obj: det}} and
+    ``view_ids`` — the same containers, with the same detection keys (pose, inliers, kp_mask, model_kp, uv_pred, cov_pred, K, bbox,
+    prior_uv), so the reference's own bookkeeping (object culling, global optimize(), collect_results) can run on top of it."""
+
+    def __init__(self, model, kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, check_n_views=15):
+        self.model = model
+        self.kp_var_thresh, self.bbox_thresh, self.manual_kp_std = kp_var_thresh, bbox_thresh, manual_kp_std
+        self.init_with_outliers, self.seed, self.check_n_views = init_with_outliers, seed, check_n_views
+        self.obj_poses, self.cam_poses, self.detections, self.view_ids = {}, {}, {}, []
+
+    def process_view(self, view_id, img, K, obj_ids, bboxes, model_kps, model_kps_masks, is_sym, diameters):
+        """img [H,W,3] u8; K [3,3]; per detected object: id, bbox xyxy, model keypoints [41,3], their mask [41], symmetric flag
+        (mesh_db[obj]["is_symmetric"]), diameter.  Returns the call's raw outputs (per crop, in the ORIGINAL object order)."""
+        assert view_id not in self.cam_poses, f"Repeat view_id {view_id}"                      # :329-330
+        ctx = self.model.context()
+        obj_ids = list(obj_ids)
+        is_sym = np.asarray(is_sym, bool)
+        order = np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]]).astype(int)    # non-symmetric crops first (:394-418)
+        L, Kk = len(order), self.model.num_kp
+        c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+        img = c(img, np.uint8)
+        H, W = img.shape[:2]
+        boxes = c(np.asarray(bboxes)[order], np.float32)
+        mk, mm = c(np.asarray(model_kps)[order], np.float64), c(np.asarray(model_kps_masks)[order], np.uint8)
+        diam = c(np.asarray(diameters)[order], np.float64)
+        ids = [obj_ids[i] for i in order]
+        map_valid = c([o in self.obj_poses for o in ids], np.uint8)
+        T_map = np.tile(np.eye(4)[:3], (L, 1, 1))
+        for q, o in enumerate(ids):
+            if o in self.obj_poses:
+                T_map[q] = np.asarray(self.obj_poses[o])[:3]
+        # the objects' detections in the last check_n_views - 1 earlier views (__maybe_reinit_objects, :627-650)
+        hc, hT, hK, hoff, hmk, huv, hcov = [], [], [], [0], [], [], []
+        for v in [self.view_ids[-(i + 1)] for i in range(min(len(self.view_ids), self.check_n_views - 1))]:
+            for q, o in enumerate(ids):
+                d = self.detections[v].get(o)
+                if d is None:
+                    continue
+                hc.append(q); hT.append(np.asarray(self.cam_poses[v])[:3]); hK.append(d["K"])
+                hmk.append(d["model_kp"]); huv.append(d["uv_pred"]); hcov.append(d["cov_pred"])
+                hoff.append(hoff[-1] + len(d["uv_pred"]))
+        nh = len(hc)
+        cat = lambda xs, dt, shape: c(np.concatenate(xs), dt) if xs and sum(len(x) for x in xs) else np.zeros(shape, dt)
+        h = dict(crop=c(hc, np.int32), T=c(hT, np.float64).reshape(-1, 12), K=c(hK, np.float64).reshape(-1, 9), off=c(hoff, np.int32),
+                 mk=cat(hmk, np.float64, (1, 3)), uv=cat(huv, np.float32, (1, 2)), cov=cat([x.reshape(-1, 4) for x in hcov], np.float32, (1, 4))) if nh else None
+        out = dict(T_GtoC=np.zeros((3, 4)), status=np.zeros(8, np.int32), T_pnp=np.zeros((L, 4, 4)), kp_used=np.zeros((L, Kk), np.uint8),
+                   ba_inliers=np.zeros((L, Kk), np.uint8), uv=np.zeros((L, Kk, 2), np.float32), cov=np.zeros((L, Kk, 2, 2), np.float32),
+                   prior_uv=np.zeros((L, Kk, 2), np.float32), prior_mask=np.zeros((L, Kk), np.uint8), K_bbox=np.zeros((L, 3, 3)),
+                   T_OtoG=np.zeros((L, 3, 4)), map_valid=np.zeros(L, np.uint8), reinit=np.zeros(L, np.uint8), reinit_counts=np.zeros((L, 2), np.int32))
+        p = _lib.ptr
+        n_views = len(self.view_ids) + 1
+        ctx.check(_lib.lib().suo_slam_frame(
+            ctx.handle, p(img), H, W, p(c(K, np.float64)), p(boxes), L, int((~is_sym).sum()), p(mk), p(mm), p(diam), p(map_valid), p(c(T_map, np.float64)),
+            n_views, nh, *((p(h["crop"]), p(h["T"]), p(h["K"]), p(h["off"]), p(h["mk"]), p(h["uv"]), p(h["cov"])) if nh else (None,) * 7),
+            float(self.kp_var_thresh), float(self.bbox_thresh), float(self.manual_kp_std), int(self.init_with_outliers), int(self.seed),
+            p(out["T_GtoC"]), p(out["status"]), p(out["T_pnp"]), p(out["kp_used"]), p(out["ba_inliers"]), p(out["uv"]), p(out["cov"]), p(out["prior_uv"]),
+            p(out["prior_mask"]), p(out["K_bbox"]), p(out["T_OtoG"]), p(out["map_valid"]), p(out["reinit"]), p(out["reinit_counts"]), 0, None))
+        cam_ok = bool(out["status"][0])
+        n1 = int((~is_sym).sum())
+        det = {}
+        for q, o in enumerate(ids):
+            if q >= n1 and not cam_ok:                    # symmetric objects leave no detection without a camera pose (:413-418)
+                continue
+            m = out["kp_used"][q].astype(bool)
+            T = out["T_pnp"][q]
+            ok = (not np.allclose(T, np.eye(4))) and m.sum() >= 4 and T[2, 3] > 0.5 * diam[q]
+            det[o] = dict(pose=T.copy() if ok else None, inliers=out["ba_inliers"][q][m].astype(bool) if out["status"][3] > 0 and out["map_valid"][q] else np.ones(int(m.sum()), bool),
+                          kp_mask=m, model_kp=mk[q][m], uv_pred=out["uv"][q][m].astype(np.float64), cov_pred=out["cov"][q][m], K=out["K_bbox"][q].copy(),
+                          bbox=boxes[q], prior_uv=out["prior_uv"][q] if out["prior_mask"][q].any() else None, crop=int(order[q]))
+        self.detections[view_id] = det
+        if cam_ok:
+            self.cam_poses[view_id] = out["T_GtoC"].copy()
+            self.view_ids.append(view_id)
+            for q, o in enumerate(ids):
+                if out["map_valid"][q]:
+                    self.obj_poses[o] = np.vstack([out["T_OtoG"][q], [0, 0, 0, 1.0]])
+        inv = np.argsort(order)
+        res = {k: (v[inv] if isinstance(v, np.ndarray) and v.shape[:1] == (L,) and k not in ("status",) else v) for k, v in out.items()}
+        res["cam_ok"] = cam_ok
+        res["reinit_ids"] = sorted(ids[q] for q in range(L) if out["reinit"][q])
+        return res

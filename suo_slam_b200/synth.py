@@ -393,12 +393,18 @@ def make_marker_frame(seed: int, n_obj: int = 8, H: int = 480, W: int = 640, num
     painted in object order — later objects occlude earlier ones and same-colour discs of other objects that fall into a
     crop act as the gross outliers PnP has to reject."""
     fr = make_frame(seed, n_obj, H, W, num_kp, K)
+    fr["img"] = paint_markers(seed, fr["objs"], H, W, num_kp, res, bg, radius)
+    return fr
+
+
+def paint_markers(seed, objs, H, W, num_kp=arch.NUM_KP, res=256, bg=(96, 160), radius=MARKER_RADIUS):
+    """The u8 image of make_marker_frame for a list of objects (dicts with bbox, model_kps_mask, uv_gt)."""
     rng = np.random.default_rng(seed ^ 0x5EED)
     img = rng.integers(bg[0], bg[1], size=(H, W, 3)).astype(np.float32)
     col = marker_colors_u8(num_kp).astype(np.float32)
     ss = 4
     sub = (np.arange(ss) + 0.5) / ss
-    for o in fr["objs"]:
+    for o in objs:
         x1, y1, x2, y2 = [float(v) for v in o["bbox"]]
         bw, bh = x2 - x1, y2 - y1
         rx, ry = radius * bw / res, radius * bh / res
@@ -418,8 +424,60 @@ def make_marker_frame(seed: int, n_obj: int = 8, H: int = 480, W: int = 640, num
             alpha = inside.reshape(iy1 - iy0, ss, ix1 - ix0, ss).mean((1, 3)).astype(np.float32)
             patch = img[iy0:iy1, ix0:ix1]
             patch += alpha[:, :, None] * (col[k] - patch)
-    fr["img"] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
-    return fr
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_slam_sequence(seed: int, n_views: int = 4, n_obj: int = 6, H: int = 480, W: int = 640, num_kp: int = arch.NUM_KP,
+                       K: np.ndarray = K_YCBV, res: int = 256, n_sym=None, radius: float = MARKER_RADIUS):
+    """A SLAM-mode sequence with IMAGES (BASELINE configs[4] / SURVEY.md §8d "C5"): n_obj objects on a table (world poses T_OtoG,
+    per-object keypoint subsets as in make_frame), the camera circling them (scene modelled on
+    thirdparty/g2opy/python/examples/object_slam_demo.py:54-150); the first n_sym objects (default half) are flagged symmetric
+    (mesh_db[obj]["is_symmetric"], lib/object_slam.py:343).  Every view is a marker frame (paint_markers) with tight bboxes inflated
+    10 % (bop.py:551).  The world frame is the FIRST camera frame, as ObjectSLAM defines it (first cam pose = identity, :410-411)."""
+    rng = np.random.default_rng(seed)
+    n_sym = n_obj // 2 if n_sym is None else n_sym
+    objs = []
+    for o in range(n_obj):
+        mask = np.zeros(num_kp, dtype=bool)
+        mask[rng.choice(num_kp, size=int(rng.integers(8, 23)), replace=False)] = True
+        T = np.eye(4)
+        T[:3, :3] = random_rotation(rng)
+        T[:3, 3] = [rng.uniform(-170, 170), rng.uniform(-170, 170), rng.uniform(-30, 30)]
+        objs.append(dict(obj_id=10 + o, T_wo=T, model_kps=rng.uniform(-60, 60, size=(num_kp, 3)), model_kps_mask=mask, diameter=150.0,
+                         is_symmetric=o < n_sym))
+    cams = []
+    for v in range(n_views):
+        ang = 0.25 * v + rng.normal(scale=0.02)
+        c = np.array([1000 * np.cos(ang), 1000 * np.sin(ang), rng.uniform(450, 550)])      # camera centre in the table frame
+        z = -c / np.linalg.norm(c)
+        x = np.cross([0, 0, 1.0], z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        T = np.eye(4)
+        T[:3, :3] = np.stack([x, y, z]); T[:3, 3] = -T[:3, :3] @ c
+        cams.append(T)
+    W0_inv = np.linalg.inv(cams[0])                       # table -> first camera = world
+    for o in objs:
+        o["T_OtoG"] = cams[0] @ o["T_wo"]
+    views = []
+    for v in range(n_views):
+        T_GtoC = cams[v] @ W0_inv
+        dets = []
+        for o in objs:
+            T_oc = T_GtoC @ o["T_OtoG"]
+            pc = o["model_kps"] @ T_oc[:3, :3].T + T_oc[:3, 3]
+            px = pc @ K.T
+            px = px[:, :2] / px[:, 2:3]
+            m = o["model_kps_mask"]
+            lo, hi = px[m].min(0), px[m].max(0)
+            ctr, half = (lo + hi) / 2, (hi - lo) / 2 * 1.1
+            box = np.array([ctr[0] - half[0], ctr[1] - half[1], ctr[0] + half[0], ctr[1] + half[1]])
+            box[[0, 2]] = np.clip(box[[0, 2]], 0, W - 1)
+            box[[1, 3]] = np.clip(box[[1, 3]], 0, H - 1)
+            Kb = fix_K_for_bbox_ndc(K, box)
+            uv = pc @ Kb.T
+            dets.append(dict(obj_id=o["obj_id"], bbox=box.astype(np.float32), model_kps_mask=m, uv_gt=uv[:, :2] / uv[:, 2:3], T_OtoC=T_oc))
+        views.append(dict(view_id=100 + v, T_GtoC=T_GtoC, dets=dets, img=paint_markers(seed * 131 + v, dets, H, W, num_kp, res, radius=radius)))
+    return dict(K=K.copy(), objs=objs, views=views)
 
 
 def make_pnp_benchmark(seed: int, n: int = 250, pixel_sigma: float = 0.5, outlier_ratio: float = 0.5):
