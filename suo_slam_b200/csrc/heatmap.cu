@@ -227,11 +227,19 @@ heatmap_reduce_reg_kernel(const float* __restrict__ logits, int H, int W, float*
 // 64x64 maps, one WARP per map: each lane holds 32 float4 (all 32 loads of a lane are issued back to back: 16 KB in flight
 // per warp), the reductions are warp shuffles only — no shared memory, no block barrier — so the warps of an SM sit in
 // different phases and the memory pipe never drains while a CTA computes.  The kernel is issue-bound once the loads
-// overlap (4096 expf per map), so the element loop is kept to two passes: (1) max / first argmax / plain sum; (2) e =
-// expf(x - m) with S and the first AND second moments about the ARGMAX pixel: the shifted coordinates (h - h0) / 32 are exact
+// overlap, so the element loop is kept to two lean passes: (1) max and plain sum (the argmax is located afterwards, by the
+// lanes that hold the maximum); (2) e = exp(x - m) = ex2(x log2e - m log2e) with S and the first AND second moments about the ARGMAX pixel: the shifted coordinates (h - h0) / 32 are exact
 // in FP32 and, on a peaky map, small where e is large, so cov = E[dd^T] - E[d] E[d]^T loses nothing to cancellation
 // (4e-7 worst case against FP64 over flat, noisy, single- and double-peak maps); uv = grid(argmax) + E[d].
 constexpr int kWarpMapThreads = 128;
+// 2^x by the SFU (ex2.approx.ftz: relative error 2^-22.5).  With the argument formed by ONE fused multiply-add the weights e^(x - m) are
+// good to ~2e-7 relative where they matter (x - m > -16) — the same order as expf's own rounding — and to 3e-6 in the far tail
+// (x - m ~ -88), where they are below 1e-38 of the sum anyway.
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __global__ void __launch_bounds__(kWarpMapThreads, 3)
 heatmap_reduce_warp_kernel(const float* __restrict__ logits, int n_maps, float* __restrict__ pooled, float* __restrict__ uv,
                            float* __restrict__ cov, float* __restrict__ prob, int32_t* __restrict__ argmax) {
@@ -247,21 +255,24 @@ heatmap_reduce_warp_kernel(const float* __restrict__ logits, int n_maps, float* 
     const float4 v = __ldg(x4 + lane + 32 * j);
     e[j][0] = v.x; e[j][1] = v.y; e[j][2] = v.z; e[j][3] = v.w;
   }
+  // pass 1: max and plain sum (2 instructions per element); the argmax is located afterwards by the lanes that hold the maximum
   float m = -INFINITY, s = 0.f;
-  int mi = 0x7fffffff;
 #pragma unroll
   for (int j = 0; j < NV; ++j)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      s += e[j][q];
-      if (e[j][q] > m) { m = e[j][q]; mi = 4 * (lane + 32 * j) + q; }   // ascending index per lane => first occurrence
-    }
+    for (int q = 0; q < 4; ++q) { s += e[j][q]; m = fmaxf(m, e[j][q]); }
+  const float lane_max = m;
+  m = warp_max(m);
+  int mi = 0x7fffffff;
+  if (lane_max == m) {                     // first occurrence inside this lane (its indices ascend with j, q)
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float om = __shfl_xor_sync(0xffffffffu, m, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
-    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+    for (int j = NV - 1; j >= 0; --j)
+#pragma unroll
+      for (int q = 3; q >= 0; --q)
+        if (e[j][q] == m) mi = 4 * (lane + 32 * j) + q;
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mi = min(mi, __shfl_xor_sync(0xffffffffu, mi, o));   // first occurrence over the map
   const float total = warp_sum(s);
   // float4 i = lane + 32 j lies in row 2 j + (lane >> 4), columns 4 (lane & 15) .. + 3
   const int h0 = mi >> 6, w0 = mi & 63;
@@ -269,13 +280,15 @@ heatmap_reduce_warp_kernel(const float* __restrict__ logits, int n_maps, float* 
   float gy[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) gy[q] = -(float)(wl + q) * inv_half;           // yy[h,w] = -r[w], shifted by the argmax column
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float neg_m_log2e = -m * kLog2e;
   float S = 0.f, sx = 0.f, sy = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const float gx = (float)(2 * j + hl) * inv_half;                         // xx[h,w] = r[h], shifted by the argmax row
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float ev = expf(e[j][q] - m);
+      const float ev = fast_exp2(fmaf(e[j][q], kLog2e, neg_m_log2e));   // exp(x - m): one FFMA + one MUFU.EX2
       e[j][q] = ev;
       S += ev;
       const float ax = ev * gx, ay = ev * gy[q];

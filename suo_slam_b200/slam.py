@@ -124,6 +124,7 @@ class SlamTracker:
         self.kp_var_thresh, self.bbox_thresh, self.manual_kp_std = kp_var_thresh, bbox_thresh, manual_kp_std
         self.init_with_outliers, self.seed, self.check_n_views = init_with_outliers, seed, check_n_views
         self.obj_poses, self.cam_poses, self.detections, self.view_ids = {}, {}, {}, []
+        self.record = None        # set to a list to keep the packed input arrays of every suo_slam_frame call (bench.py replays them from HBM)
 
     def process_view(self, view_id, img, K, obj_ids, bboxes, model_kps, model_kps_masks, is_sym, diameters):
         """img [H,W,3] u8; K [3,3]; per detected object: id, bbox xyxy, model keypoints [41,3], their mask [41], symmetric flag
@@ -166,6 +167,9 @@ class SlamTracker:
                    T_OtoG=np.zeros((L, 3, 4)), map_valid=np.zeros(L, np.uint8), reinit=np.zeros(L, np.uint8), reinit_counts=np.zeros((L, 2), np.int32))
         p = _lib.ptr
         n_views = len(self.view_ids) + 1
+        if self.record is not None:
+            self.record.append(dict(img=img, K=c(K, np.float64), boxes=boxes, L=L, n1=int((~is_sym).sum()), mk=mk, mm=mm, diam=diam, map_valid=map_valid,
+                                    T_map=c(T_map, np.float64), n_views=n_views, hist=h))
         ctx.check(_lib.lib().suo_slam_frame(
             ctx.handle, p(img), H, W, p(c(K, np.float64)), p(boxes), L, int((~is_sym).sum()), p(mk), p(mm), p(diam), p(map_valid), p(c(T_map, np.float64)),
             n_views, nh, *((p(h["crop"]), p(h["T"]), p(h["K"]), p(h["off"]), p(h["mk"]), p(h["uv"]), p(h["cov"])) if nh else (None,) * 7),

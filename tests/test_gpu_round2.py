@@ -252,9 +252,9 @@ def test_result_records_device_packing_equals_the_host_layout(marker_model):
     rec = np.zeros((L, rb), np.uint8)
     ids = np.arange(100, 100 + L, dtype=np.int32)
     c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
-    ctx.check(_lib.lib().suo_pack_records(ctx.handle, _lib.ptr(ids), 0, _lib.ptr(c(got["T_pnp"], np.float64)), _lib.ptr(c(got["T_ba"], np.float64)),
-                                          _lib.ptr(c(got["kp_used"], np.uint8)), _lib.ptr(c(got["ba_inliers"], np.uint8)), _lib.ptr(c(got["uv"], np.float32)),
-                                          _lib.ptr(c(got["cov"], np.float32)), L, _lib.ptr(rec), 0, None))
+    a = [c(got["T_pnp"], np.float64), c(got["T_ba"], np.float64), c(got["kp_used"], np.uint8), c(got["ba_inliers"], np.uint8), c(got["uv"], np.float32),
+         c(got["cov"], np.float32)]                        # (kept alive across the call: the library reads them through raw pointers)
+    ctx.check(_lib.lib().suo_pack_records(ctx.handle, _lib.ptr(ids), 0, *[_lib.ptr(v) for v in a], L, _lib.ptr(rec), 0, None))
     want = sdist.pack_records_host(ids, got["T_pnp"], got["T_ba"], got["kp_used"], got["ba_inliers"], got["uv"], got["cov"])
     have = np.frombuffer(rec.tobytes(), dtype=sdist.record_dtype(41))
     for name in want.dtype.names:
