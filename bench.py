@@ -596,7 +596,8 @@ def run_native_frames(args):
                        "allgather": xch[0].how,
                        "l2": f"{n_sets} input sets rotated; per-step activation working set ({L} crops) >> 126 MB L2" if args.workload != "c4" else
                              "fixed sequence (the same frames every step); per-step activation working set >> 126 MB L2",
-                       "conv_backend": "tcgen05", "conv_math": args.conv_math, "tf32_passes": args.tf32_passes},
+                       "conv_backend": "tcgen05", "conv_math": args.conv_math, "tf32_passes": args.tf32_passes,
+                       "activation_bytes": dict(zip(("allocated", "one_allocation_per_tensor"), ctx.activation_bytes()))},
             "timed_work": work,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps, "how": "suo_frames_u8_submit / suo_frames_wait, two slots: the copies of batch i+1 overlap the kernels of batch i",

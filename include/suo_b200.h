@@ -40,7 +40,8 @@ enum {
   SUO_OPT_TF32_PASSES = 2,  /* 3 = 3xTF32 split (FP32-equivalent, default), 1 = single-pass TF32 */
   SUO_OPT_USE_GRAPH = 3,    /* 1 = replay the forward as a CUDA graph (default), 0 = eager launches */
   SUO_OPT_CONV_PERSISTENT = 4, /* 1 = persistent tcgen05 conv kernel with overlapped epilogue (default), 0 = one tile per CTA */
-  SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches) */
+  SUO_OPT_MULTISTREAM = 5,     /* 1 = run the hourglass resolution levels on concurrent streams (graph branches); only with SUO_ACT_REUSE=0 in the
+                                  environment at suo_create (shared activation allocations assume one stream) */
   SUO_OPT_CONV_MATH = 6,       /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
                                   0 = TF32 split (SUO_OPT_TF32_PASSES) */
   SUO_OPT_CONV_FUSE = 7,       /* conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel: 1 = single-CTA
@@ -75,6 +76,9 @@ const char* suo_last_error(const suo_ctx* ctx);
 int suo_set_option(suo_ctx* ctx, int option, int value);
 /* Number of this library's kernels launched since ctx creation (bench.py gpu_launches). */
 long long suo_kernel_launches(const suo_ctx* ctx);
+/* Bytes of HBM held by the network's activation tensors (after suo_load_weights): tensors whose live ranges in the layer program do not
+ * overlap share one allocation.  *unshared (may be NULL) = what one allocation per tensor would take. */
+size_t suo_activation_bytes(const suo_ctx* ctx, size_t* unshared);
 
 /* ---- weights ------------------------------------------------------------------- */
 /* Replaces PkpNet.load_state_dict(checkpoint['model']) (lib/object_slam.py:92-97).

@@ -27,7 +27,7 @@ def exported_symbols():
             "suo_pnp_batch", "suo_ba_batch", "suo_solve_keypoints", "suo_frames", "suo_profile_network", "suo_check_range",
             "suo_forward_kp_priors", "suo_render_priors", "suo_chi2_inlier_counts", "suo_frames_u8",
             "suo_ba_last_errors", "suo_edge_linearize", "suo_frames_u8_submit", "suo_frames_wait", "suo_record_bytes",
-            "suo_pack_records", "suo_allgather_results", "suo_slam_frame"]
+            "suo_pack_records", "suo_allgather_results", "suo_slam_frame", "suo_activation_bytes"]
 
 
 def lib():
@@ -68,6 +68,8 @@ def lib():
         L.suo_frames_u8_submit.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, C.c_double,
                                            C.c_double, C.c_uint64, C.c_int] + [vp] * 6 + [vp, C.c_int, vp]
         L.suo_frames_wait.argtypes = [vp, C.c_int]
+        L.suo_activation_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.suo_activation_bytes.restype = C.c_size_t
         L.suo_slam_frame.argtypes = ([vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int] + [vp] * 7 +
                                      [C.c_double, C.c_double, C.c_double, C.c_int, C.c_uint64] + [vp] * 14 + [C.c_int, vp])
         L.suo_record_bytes.argtypes = [C.c_int]
@@ -127,6 +129,11 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(lib().suo_kernel_launches(self._h))
+
+    def activation_bytes(self):
+        """(allocated, one-allocation-per-tensor) bytes of the network's activation tensors."""
+        u = C.c_size_t(0)
+        return int(lib().suo_activation_bytes(self._h, C.byref(u))), int(u.value)
 
     def load_weights(self, blob: bytes):
         buf = np.frombuffer(blob, dtype=np.uint8)

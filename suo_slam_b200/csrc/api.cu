@@ -7,6 +7,7 @@
 // packs the weights for the tensor-core kernel once, and replays the op list — as a CUDA
 // graph per (crop count, variant) — on the caller's stream.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -145,7 +146,9 @@ struct NetState {
   int stem_wp = 0, stem_hp = 0, stem_ok = 0;
   alignas(64) unsigned char stem_tmap[128];
   std::vector<int> fuse_next;                           // per op: 1 = this 3x3 conv and the next op (1x1 + skip) can run as one fused kernel
-  std::vector<float*> act;                   // per buffer: device activation tensor
+  std::vector<float*> act;                   // per buffer: device activation tensor (buffers with disjoint live ranges share an allocation)
+  std::vector<float*> act_slots;             // the allocations behind `act`
+  size_t act_bytes = 0, act_unshared_bytes = 0;   // allocated / what one allocation per buffer would take
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
@@ -314,7 +317,7 @@ int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t s
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int R = ctx->crop_res;
-  const bool multi = ctx->opt_multistream != 0;
+  const bool multi = ctx->opt_multistream != 0 && !ctx->opt_act_reuse;      // shared activation slots assume program order on ONE stream
   auto level_of = [&](const OpDesc& o) { const int d = N.bufs[o.out].div; return !multi ? 0 : (d <= 4 ? 0 : (d == 8 ? 1 : 2)); };
   cudaStream_t streams[3] = {s, s, s};
   if (multi) {
@@ -457,6 +460,7 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_CONV_PERSISTENT")) c->opt_persistent = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_USE_GRAPH")) c->opt_graph = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_MULTISTREAM")) c->opt_multistream = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SUO_ACT_REUSE")) c->opt_act_reuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = std::max(0, std::min(2, atoi(e)));
@@ -502,7 +506,7 @@ void suo_destroy(suo_ctx* ctx) {
     for (uint16_t* p : N.packed16) if (p) cudaFree(p);
     if (N.range_flag) cudaFree(N.range_flag);
     if (N.stem_pad) cudaFree(N.stem_pad);
-    for (float* p : N.act) if (p) cudaFree(p);
+    for (float* p : N.act_slots) if (p) cudaFree(p);
     if (N.pool) cudaFree(N.pool);
     if (N.pooled) cudaFree(N.pooled);
     if (N.d_uv) cudaFree(N.d_uv);
@@ -526,6 +530,12 @@ void suo_destroy(suo_ctx* ctx) {
 
 const char* suo_last_error(const suo_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 long long suo_kernel_launches(const suo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+size_t suo_activation_bytes(const suo_ctx* ctx, size_t* unshared) {
+  if (!ctx || !ctx->net) return 0;
+  const NetState& N = reinterpret_cast<const CtxExtra*>(ctx->net)->net;
+  if (unshared) *unshared = N.act_unshared_bytes;
+  return N.act_bytes;
+}
 
 int suo_set_option(suo_ctx* ctx, int option, int value) {
   if (!ctx) return SUO_E_INVALID;
@@ -630,11 +640,63 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
   // activation buffers
   N.act.assign(N.bufs.size(), nullptr);
   const int R = ctx->crop_res;
-  for (size_t i = 0; i < N.bufs.size(); ++i) {
-    const size_t side = R / N.bufs[i].div;
-    const size_t n = (size_t)ctx->max_crops * side * side * N.bufs[i].C;
-    SUO_CUDA_TRY(ctx, cudaMalloc(&N.act[i], n * sizeof(float)));
-    SUO_CUDA_TRY(ctx, cudaMemset(N.act[i], 0, n * sizeof(float)));
+  {
+    // Liveness-based reuse: a buffer lives from its first writer to its last reader in program order (the op list runs in that order on one
+    // stream; kernels launched with programmatic dependent launch touch no activation before griddepcontrol.wait, i.e. before every earlier
+    // kernel has completed).  Buffers whose live ranges do not overlap share one allocation ("slot"): ~10 slots instead of ~200 buffers.
+    // The two network-input buffers (written before the program, partly by stamping) and the logits (read after it) keep their own.
+    const int nb = (int)N.bufs.size();
+    std::vector<int> first(nb, INT32_MAX), last(nb, -1);
+    std::vector<size_t> bytes(nb);
+    for (int i = 0; i < nb; ++i) { const size_t side = R / N.bufs[i].div; bytes[i] = (size_t)ctx->max_crops * side * side * N.bufs[i].C * sizeof(float); }
+    for (int i = 0; i < (int)N.ops.size(); ++i) {
+      const OpDesc& o = N.ops[i];
+      last[o.in] = std::max(last[o.in], i);
+      if (o.res >= 0) last[o.res] = std::max(last[o.res], i);
+      first[o.out] = std::min(first[o.out], i); last[o.out] = std::max(last[o.out], i);
+    }
+    std::vector<char> own(nb, 0);
+    own[N.h.in_buf_noprior] = own[N.h.in_buf_prior] = own[N.h.logits_buf] = 1;
+    for (int i = 0; i < nb; ++i) if (first[i] == INT32_MAX || last[i] < 0 || !ctx->opt_act_reuse) own[i] = 1;     // never written / never read by the program
+    std::vector<int> order;
+    for (int i = 0; i < nb; ++i) if (!own[i]) order.push_back(i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return first[a] < first[b]; });
+    struct Slot { size_t cap; int busy_until; };
+    std::vector<Slot> slots;
+    std::vector<int> slot_of(nb, -1);
+    for (int b : order) {
+      int best = -1;
+      for (int q = 0; q < (int)slots.size(); ++q) {
+        if (slots[q].busy_until >= first[b]) continue;                       // closed intervals: an op's output never aliases its inputs
+        if (best < 0) { best = q; continue; }
+        const bool fits_q = slots[q].cap >= bytes[b], fits_b = slots[best].cap >= bytes[b];
+        if ((fits_q && (!fits_b || slots[q].cap < slots[best].cap)) || (!fits_q && !fits_b && slots[q].cap > slots[best].cap)) best = q;
+      }
+      if (best < 0) { slots.push_back({bytes[b], last[b]}); best = (int)slots.size() - 1; }
+      else { slots[best].cap = std::max(slots[best].cap, bytes[b]); slots[best].busy_until = last[b]; }
+      slot_of[b] = best;
+    }
+    N.act_slots.assign(slots.size(), nullptr);
+    N.act_bytes = 0;
+    for (size_t q = 0; q < slots.size(); ++q) {
+      SUO_CUDA_TRY(ctx, cudaMalloc(&N.act_slots[q], slots[q].cap));
+      SUO_CUDA_TRY(ctx, cudaMemset(N.act_slots[q], 0, slots[q].cap));
+      N.act_bytes += slots[q].cap;
+    }
+    for (int i = 0; i < nb; ++i) {
+      if (own[i]) {
+        float* p = nullptr;
+        SUO_CUDA_TRY(ctx, cudaMalloc(&p, bytes[i]));
+        SUO_CUDA_TRY(ctx, cudaMemset(p, 0, bytes[i]));
+        N.act_slots.push_back(p);
+        N.act[i] = p;
+        N.act_bytes += bytes[i];
+      } else {
+        N.act[i] = N.act_slots[slot_of[i]];
+      }
+    }
+    N.act_unshared_bytes = 0;
+    for (int i = 0; i < nb; ++i) N.act_unshared_bytes += bytes[i];
   }
   N.tmaps.resize(N.ops.size());
   N.epi_ok.assign(N.ops.size(), 0);
