@@ -283,8 +283,6 @@ def conv_classes(dump_path, L, pair=True):
             ncu, desc = "conv3x3_halo_kernel", "3x3 convs (A-halo CTA pair: activations once per column shift, tcgen05.mma.cta_group::2, fp16x3)"
         elif key == (1, 0, 0) and cout == 128 and pair:      # the bottleneck's conv2 runs as a CTA pair (csrc/conv_pair.cu)
             ncu, desc = "conv3x3_pair_kernel", "3x3 convs (CTA pair: tcgen05.mma.cta_group::2 of M = 256, TMA-fed, fp16x3)"
-        elif key == (3, 0, 1):                               # SUO_FUSE: conv2 + conv3 + skip in one kernel
-            ncu, desc, bound = "conv_fused23", "fused 3x3 + 1x1 + skip (SUO_FUSE)", "tensor"
         px = L * side * side
         px_in = px * 4 if key[0] == 2 else px
         b = 4.0 * (px_in * cin + px * cout * (2 if key[2] else 1)) + 4.0 * K * cout

@@ -44,8 +44,7 @@ enum {
                                   environment at suo_create (shared activation allocations assume one stream) */
   SUO_OPT_CONV_MATH = 6,       /* 1 = FP16x3 split (default): x = hi + 2^-11 lo in two FP16 numbers, range-guarded;
                                   0 = TF32 split (SUO_OPT_TF32_PASSES) */
-  SUO_OPT_CONV_FUSE = 7,       /* conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck run as one kernel: 1 = single-CTA
-                                   kernel, 2 = CTA-pair kernel (tcgen05.mma.cta_group::2); 0 = two kernels. Results are identical. */
+  SUO_OPT_CONV_FUSE = 7,       /* retired (round 1's fused conv2 + conv3 kernels measured slower than the two kernels and were removed): only 0 is accepted */
   SUO_OPT_CONV_PAIR = 8,       /* 1 (default) = 3x3 convs on FP16-plane tensors run as CTA pairs (tcgen05.mma.cta_group::2: each CTA of
                                    a 2-CTA cluster loads half of the weight rows); 0 = one CTA per tile. Results are identical. */
   SUO_OPT_PDL = 9,             /* 1 (default) = the persistent conv kernels use programmatic dependent launch (the next kernel's CTAs are

@@ -145,15 +145,14 @@ struct NetState {
   float* stem_pad = nullptr;
   int stem_wp = 0, stem_hp = 0, stem_ok = 0;
   alignas(64) unsigned char stem_tmap[128];
-  std::vector<int> fuse_next;                           // per op: 1 = this 3x3 conv and the next op (1x1 + skip) can run as one fused kernel
   std::vector<float*> act;                   // per buffer: device activation tensor (buffers with disjoint live ranges share an allocation)
   std::vector<float*> act_slots;             // the allocations behind `act`
   size_t act_bytes = 0, act_unshared_bytes = 0;   // allocated / what one allocation per buffer would take
   float* pooled = nullptr;                   // [max_crops, K] channel means
   float *d_uv = nullptr, *d_cov = nullptr, *d_mask = nullptr, *d_mask_logits = nullptr;
   int32_t* d_argmax = nullptr;
-  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl, halo; bool operator<(const GraphKey& o) const {
-    return std::tie(L, variant, backend, passes, persistent, multi, math, fuse, pair, pdl, halo) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.fuse, o.pair, o.pdl, o.halo); } };
+  struct GraphKey { int L, variant, backend, passes, persistent, multi, math, pair, pdl, halo; bool operator<(const GraphKey& o) const {
+    return std::tie(L, variant, backend, passes, persistent, multi, math, pair, pdl, halo) < std::tie(o.L, o.variant, o.backend, o.passes, o.persistent, o.multi, o.math, o.pair, o.pdl, o.halo); } };
   std::map<GraphKey, cudaGraphExec_t> graphs;
   // resolution-level streams: independent branches of the hourglass (up1 at full resolution vs the low-resolution
   // sub-hourglass, hg.py:37-58) run concurrently; cross-stream edges are CUDA events (also inside graph capture)
@@ -247,73 +246,6 @@ void fill_conv_params(suo_ctx* ctx, NetState& N, size_t i, int L, int backend, i
   if (p.pair) memcpy(p.tmap_w, tm + 768, 128);
 }
 
-// true when op i (3x3, 128 -> 128) and op i+1 (1x1, 128 -> 256, + skip) run as ONE kernel under the current options
-bool op_fused(suo_ctx* ctx, const NetState& N, size_t i, int backend, int passes) {
-  return backend == 1 && ctx->opt_math == 1 && ctx->opt_persistent && passes == 3 && ctx->opt_epi_tma && ctx->opt_fuse &&
-         i < N.fuse_next.size() && N.fuse_next[i];
-}
-
-int launch_fused_pair(suo_ctx* ctx, NetState& N, size_t i, int L, cudaStream_t st) {
-  const OpDesc& o2 = N.ops[i];
-  const OpDesc& o3 = N.ops[i + 1];
-  FusedParams f{};
-  memcpy(f.tmap_hi, N.tmaps[i].data(), 128);
-  memcpy(f.tmap_lo, N.tmaps[i].data() + 128, 128);
-  memcpy(f.tmap_out, N.tmaps[i + 1].data() + 256, 128);
-  f.w2 = N.packed16[i]; f.w3 = N.packed16[i + 1];
-  const bool as_pair = ctx->opt_fuse == 2 && N.wmap_ok[i] && N.wmap_ok[i + 1];
-  if (as_pair) { memcpy(f.tmap_w2, N.tmaps[i].data() + 768, 128); memcpy(f.tmap_w3, N.tmaps[i + 1].data() + 768, 128); }
-  {
-    const int side = ctx->crop_res / N.bufs[o2.in].div;
-    f.in_hi = reinterpret_cast<const uint16_t*>(N.act[o2.in]);
-    f.in_lo = f.in_hi + (size_t)ctx->max_crops * side * side * N.bufs[o2.in].C;
-    static const int pf = getenv("SUO_FUSE_PREFETCH") ? atoi(getenv("SUO_FUSE_PREFETCH")) : 1;
-    f.prefetch = pf;
-  }
-  auto launch = [&](const FusedParams& fp) { return as_pair ? launch_conv_fused23_pair(ctx, fp, st) : launch_conv_fused23(ctx, fp, st); };
-  f.bias2 = N.pool + o2.b_off; f.bias3 = N.pool + o3.b_off;
-  f.skip = N.act[o3.res];
-  f.B = L; f.H = ctx->crop_res / N.bufs[o2.in].div; f.W = f.H;
-  f.range_flag = N.range_flag;
-  f.dbg = nullptr;
-  // developer tool: SUO_FUSED_TIMELINE=<csv> dumps the clock64 timeline of CTA 0 for the first fused launch of the process
-  static bool dumped = false;
-  const char* tl = getenv("SUO_FUSED_TIMELINE");
-  if (tl && !dumped) {
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    if (cap == cudaStreamCaptureStatusNone) {
-      dumped = true;
-      long long* d = nullptr;
-      SUO_CUDA_TRY(ctx, cudaMalloc(&d, 16 * 64 * sizeof(long long)));
-      SUO_CUDA_TRY(ctx, cudaMemsetAsync(d, 0, 16 * 64 * sizeof(long long), st));
-      f.dbg = d;
-      int rc = launch(f);
-      if (rc) return rc;
-      std::vector<long long> h(16 * 64);
-      SUO_CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
-      SUO_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-      cudaFree(d);
-      if (FILE* fp = fopen(tl, "w")) {
-        fprintf(fp, "tile,mma_start,mma_conv2_issued,mma_a3_ready,mma_h0_issued,mma_early_issued,mma_h1_start,mma_h1_issued,epi_acc2_full,epi_a3_done,epi_h0_full,epi_h0_done,epi_h1_full,epi_h1_done\n");
-        for (int i = 0; i < 64 && h[i]; ++i) {
-          fprintf(fp, "%d", i);
-          for (int r = 0; r < 13; ++r) fprintf(fp, ",%lld", h[r * 64 + i] - h[0]);
-          fprintf(fp, "\n");
-        }
-        // rows 13 / 14 (CTA-pair version): per conv2 chunk of tiles 3 and 4, clock when its operands had landed / when its MMAs were issued
-        if (h[13 * 64]) {
-          fprintf(fp, "# chunk,operands_landed,mmas_issued (tiles 3 and 4, relative to tile 3's first entry)\n");
-          for (int c = 0; c < 64 && h[13 * 64 + c]; ++c) fprintf(fp, "# %d,%lld,%lld\n", c, h[13 * 64 + c] - h[13 * 64], h[14 * 64 + c] - h[13 * 64]);
-        }
-        fclose(fp);
-      }
-      return SUO_OK;
-    }
-  }
-  return launch(f);
-}
-
 int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaStream_t s) {
   NetState& N = X(ctx)->net;
   const int R = ctx->crop_res;
@@ -345,14 +277,7 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
       }
     }
     int rc = SUO_OK;
-    const bool fused = o.type == OP_CONV && op_fused(ctx, N, i, backend, passes);
-    if (fused) {
-      if (multi) {      // the pair's skip tensor may come from another level stream
-        const int b = N.ops[i + 1].res;
-        if (b >= 0 && writer[b] >= 0 && level_of(N.ops[writer[b]]) != lvl) SUO_CUDA_TRY(ctx, cudaStreamWaitEvent(st, N.op_done[writer[b]], 0));
-      }
-      rc = launch_fused_pair(ctx, N, i, L, st);
-    } else if (o.type == OP_CONV) {
+    if (o.type == OP_CONV) {
       ConvParams p{};
       fill_conv_params(ctx, N, i, L, backend, passes, p);
       rc = backend == 1 ? launch_conv_tc(ctx, p, passes, st) : launch_conv_simt(ctx, p, st);
@@ -366,7 +291,6 @@ int run_program(suo_ctx* ctx, int L, int variant, int backend, int passes, cudaS
     }
     if (rc != SUO_OK) return rc;
     writer[o.out] = (int)i;
-    if (fused) { ++i; writer[N.ops[i].out] = (int)i; }      // the 1x1 of the pair ran inside the same kernel
     if (multi) {
       // record completion if a later op on another level stream consumes this output
       const int produced = N.ops[i].out;
@@ -391,7 +315,7 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
   }
   const int backend = ctx->opt_backend, passes = ctx->opt_passes;
   if (!ctx->opt_graph) return run_program(ctx, L, variant, backend, passes, s);
-  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_fuse, ctx->opt_pair, ctx->opt_pdl, ctx->opt_halo};
+  NetState::GraphKey key{L, variant, backend, passes, ctx->opt_persistent, ctx->opt_multistream, ctx->opt_math, ctx->opt_pair, ctx->opt_pdl, ctx->opt_halo};
   auto it = N.graphs.find(key);
   if (it == N.graphs.end()) {
     // warm the kernels once outside capture (cudaFuncSetAttribute etc.), then capture
@@ -426,7 +350,6 @@ int run_network(suo_ctx* ctx, int L, int variant, cudaStream_t s) {
     const OpDesc& o = N.ops[i];
     if (o.variant != 2 && o.variant != variant) continue;
     ++n;
-    if (o.type == OP_CONV && op_fused(ctx, N, i, backend, passes)) ++i;    // the pair is one launch
   }
   ctx->launches += n;
   return SUO_OK;
@@ -463,7 +386,6 @@ int suo_create(int device, int max_crops, int crop_res, int num_kp, suo_ctx** ou
   if (const char* e = getenv("SUO_ACT_REUSE")) c->opt_act_reuse = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_CONV_MATH")) c->opt_math = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_EPI_TMA")) c->opt_epi_tma = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("SUO_FUSE")) c->opt_fuse = std::max(0, std::min(2, atoi(e)));
   if (const char* e = getenv("SUO_PAIR")) c->opt_pair = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_PDL")) c->opt_pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SUO_STEM_TMA")) c->opt_stem_tma = atoi(e) ? 1 : 0;
@@ -546,7 +468,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_PERSISTENT: ctx->opt_persistent = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_MULTISTREAM: ctx->opt_multistream = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_MATH: if (value != 0 && value != 1) return SUO_E_INVALID; ctx->opt_math = value; return SUO_OK;
-    case SUO_OPT_CONV_FUSE: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_fuse = value; return SUO_OK;
+    case SUO_OPT_CONV_FUSE: return value == 0 ? SUO_OK : SUO_E_INVALID;      // the fused conv2 + conv3 kernels of round 1 were slower and are gone
     case SUO_OPT_CONV_PAIR: ctx->opt_pair = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_PDL: ctx->opt_pdl = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_HALO: ctx->opt_halo = value ? 1 : 0; return SUO_OK;
@@ -766,22 +688,6 @@ int suo_load_weights(suo_ctx* ctx, const void* blob, size_t nbytes) {
                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) { memcpy(N.stem_tmap, &m, 128); N.stem_ok = 1; }     // a driver that rejects overlapping strides: register-gather stem
     }
-  }
-  // bottleneck tails that can run as one kernel (conv_fused.cu): op i = 3x3 128 -> 128 with ReLU on FP16-plane tensors,
-  // op i+1 = the 1x1 128 -> 256 that adds the skip tensor, and nothing else reads op i's output
-  N.fuse_next.assign(N.ops.size(), 0);
-  for (size_t i = 0; i + 1 < N.ops.size(); ++i) {
-    const OpDesc& a = N.ops[i];
-    const OpDesc& c = N.ops[i + 1];
-    if (a.type != OP_CONV || c.type != OP_CONV || a.variant != 2 || c.variant != 2) continue;
-    if (a.mode != CONV_3x3 || a.Cin != 128 || a.Cout != 128 || a.Cout_pad != 128 || !a.relu || a.res >= 0 || a.pre_off >= 0 || a.out_nchw) continue;
-    if (N.bufs[a.in].kind != 1 || N.bufs[a.in].C != 128 || N.bufs[a.out].kind != 1 || N.bufs[a.out].C != 128) continue;
-    if (c.mode != CONV_1x1 || c.in != a.out || c.Cin != 128 || c.Cout != 256 || c.Cout_pad != 256 || c.K != 128 || c.relu || c.res < 0 ||
-        c.pre_off >= 0 || c.out_nchw || N.bufs[c.out].kind != 0 || N.bufs[c.out].C != 256 || N.bufs[c.res].C != 256 || N.bufs[c.res].kind != 0) continue;
-    if (N.bufs[c.out].div != N.bufs[a.in].div || N.bufs[c.res].div != N.bufs[a.in].div || !N.epi_ok[i + 1] || !N.packed16[i] || !N.packed16[i + 1]) continue;
-    bool other_reader = false;
-    for (size_t k = 0; k < N.ops.size(); ++k) if (k != i + 1 && (N.ops[k].in == a.out || N.ops[k].res == a.out)) other_reader = true;
-    if (!other_reader) N.fuse_next[i] = 1;
   }
   const size_t LK = (size_t)ctx->max_crops * ctx->num_kp;
   SUO_CUDA_TRY(ctx, cudaMalloc(&N.pooled, LK * sizeof(float)));
@@ -1942,11 +1848,7 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       const OpDesc& o = N.ops[idx[q]];
       const BufDesc& bi = N.bufs[o.in];
       const BufDesc& bo = N.bufs[o.out];
-      if (q > 0 && N.ops[idx[q - 1]].type == OP_CONV && idx[q] == idx[q - 1] + 1 && op_fused(ctx, N, idx[q - 1], ctx->opt_backend, ctx->opt_passes)) {
-        rc = SUO_OK;                                      // ran inside the previous op's fused kernel
-      } else if (o.type == OP_CONV && op_fused(ctx, N, idx[q], ctx->opt_backend, ctx->opt_passes)) {
-        rc = launch_fused_pair(ctx, N, idx[q], L, s);
-      } else if (o.type == OP_CONV) {
+      if (o.type == OP_CONV) {
         ConvParams p{};
         fill_conv_params(ctx, N, idx[q], L, ctx->opt_backend, ctx->opt_passes, p);
         rc = ctx->opt_backend == 1 ? launch_conv_tc(ctx, p, ctx->opt_passes, s) : launch_conv_simt(ctx, p, s);
@@ -1970,13 +1872,7 @@ int suo_profile_network(suo_ctx* ctx, int L, int with_priors, int iters, float* 
       if (dump) {
         const int side = R / N.bufs[o.out].div;
         double gf = o.type == OP_CONV ? 2.0 * L * side * side * (double)o.Cout_pad * o.K * 1e-9 : 0.0;
-        const bool fused_head = o.type == OP_CONV && op_fused(ctx, N, idx[q], ctx->opt_backend, ctx->opt_passes);
-        const bool fused_tail = q > 0 && N.ops[idx[q - 1]].type == OP_CONV && idx[q] == idx[q - 1] + 1 && op_fused(ctx, N, idx[q - 1], ctx->opt_backend, ctx->opt_passes);
-        if (fused_tail) continue;                         // accounted for in the head's row
-        if (fused_head) { const OpDesc& c = N.ops[idx[q] + 1]; gf += 2.0 * L * side * side * (double)c.Cout_pad * c.K * 1e-9; }
-        // mode 3 = fused 3x3 + 1x1 + skip (Cout = the pair's output channels)
-        fprintf(dump, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", idx[q], o.type, fused_head ? 3 : o.mode, side, o.Cin,
-                fused_head ? N.ops[idx[q] + 1].Cout : o.Cout, o.K, o.relu, fused_head ? 1 : (o.res >= 0), o.pre_off >= 0, ms, gf);
+        fprintf(dump, "%zu,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.4f,%.3f\n", idx[q], o.type, o.mode, side, o.Cin, o.Cout, o.K, o.relu, o.res >= 0, o.pre_off >= 0, ms, gf);
       }
     }
     if (dump) fclose(dump);

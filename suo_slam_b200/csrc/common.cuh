@@ -81,26 +81,6 @@ struct ConvParams {
   alignas(64) unsigned char tmap_w[128];       // FP16x3 weight images as rows of 64 halfs (128 B), box 64 rows, no swizzle (the images are pre-swizzled)
 };
 
-// conv2 (3x3, 128 -> 128, ReLU) + conv3 (1x1, 128 -> 256, + skip) of one bottleneck as a single kernel (conv_fused.cu)
-struct FusedParams {
-  alignas(64) unsigned char tmap_hi[128];   // conv2 input, FP16 hi plane [B,H,W,128], box = one 128-pixel tile x 64 channels
-  alignas(64) unsigned char tmap_lo[128];   // lo' plane
-  alignas(64) unsigned char tmap_out[128];  // FP32 output [rows, 256], box 32 rows x 32 floats
-  const uint16_t* w2;                       // conv2 FP16x3 weight images (18 chunks x [hi | lo'])
-  const uint16_t* w3;                       // conv3 FP16x3 weight images ((half, chunk) x [hi | lo'])
-  const float* bias2;                       // [128]
-  const float* bias3;                       // [256]
-  const float* skip;                        // FP32 [rows, 256]
-  int B, H, W;
-  int* range_flag;
-  long long* dbg;                           // developer tool (SUO_FUSED_TIMELINE): [13][64] clock64 stamps of CTA 0, else nullptr
-  alignas(64) unsigned char tmap_w2[128];   // CTA-pair version (conv_fused2.cu): conv2 / conv3 weight images as rows of 64 halfs, box 64 rows
-  alignas(64) unsigned char tmap_w3[128];
-  const uint16_t* in_hi;                    // conv2 input planes (what tmap_hi / tmap_lo describe): L2 prefetch of the next tile
-  const uint16_t* in_lo;
-  int prefetch;                             // pace L2 prefetches of the next tile's HBM reads with the main loop (developer switch SUO_FUSE_PREFETCH)
-};
-
 struct suo_ctx;
 // cudaFuncSetAttribute is per device: one flag per (kernel instance, device) so that several contexts on different GPUs of one
 // process configure each kernel on each of them.  `flags` is the launcher's own static array.
@@ -113,8 +93,6 @@ inline bool first_use_on_device(bool (&flags)[64], int* num_sms) {
   flags[dev] = true;
   return true;
 }
-int launch_conv_fused23(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);
-int launch_conv_fused23_pair(suo_ctx* ctx, const FusedParams& p, cudaStream_t s);     // the same as a CTA pair (conv_fused2.cu)
 // 3x3 conv as a CTA pair (tcgen05.mma.cta_group::2, conv_pair.cu): eligibility test and launch
 bool conv_pair_eligible(const ConvParams& p, int passes);
 int launch_conv_pair(suo_ctx* ctx, const ConvParams& p, cudaStream_t s);
@@ -205,7 +183,6 @@ struct suo_ctx {
   std::string err;
   long long launches = 0;
   int opt_backend = 1, opt_passes = 3, opt_graph = 1, opt_persistent = 1, opt_multistream = 0, opt_math = 1;
-  int opt_fuse = 0;     // run conv2 + conv3 of the 128-wide bottlenecks as one kernel: 1 = single CTA (conv_fused.cu), 2 = CTA pair (conv_fused2.cu); SUO_FUSE / SUO_OPT_CONV_FUSE
   int opt_pair = 1;     // 1 = 3x3 convs on FP16-plane tensors run as CTA pairs (conv_pair.cu); SUO_PAIR=0 / SUO_OPT_CONV_PAIR turns it off
   int opt_halo = 1;     // 1 = 3x3 convs at 64x64 / 32x32 / 16x16 run on the A-halo kernel (conv_halo.cu); SUO_HALO=0 / SUO_OPT_CONV_HALO turn it off
   int opt_stem_tma = 1; // 1 = the RGB-only stem fetches its operand by TMA from a zero-bordered input copy (SUO_STEM_TMA=0: register gathers)

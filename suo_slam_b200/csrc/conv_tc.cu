@@ -838,6 +838,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_base = (t / num_n_tiles) * BLOCK_M;
       for (int j = 0; j < nchunks; ++j, ++g) {
         const uint32_t x0 = 2 * g, slot0 = x0 % RAW_BOXES;           // RAW_BOXES is even: the pair never wraps
         mbar_wait(raw_full(slot0), (x0 / RAW_BOXES) & 1);
@@ -883,7 +884,7 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
             const float4 x = cur[2 * i + u];
             const float h0 = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
             const float h2 = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+            if (m_base + r < M) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
             __half2 a = __floats2half2_rn(h0, h1), b = __floats2half2_rn(h2, h3);
             __half2 c = __floats2half2_rn((x.x - h0) * 2048.f, (x.y - h1) * 2048.f), d = __floats2half2_rn((x.z - h2) * 2048.f, (x.w - h3) * 2048.f);
             hw[2 * u] = *reinterpret_cast<uint32_t*>(&a); hw[2 * u + 1] = *reinterpret_cast<uint32_t*>(&b);
@@ -892,7 +893,9 @@ conv_tc_persistent_kernel(const __grid_constant__ ConvParams p, const int passes
           *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
           if (passes == 3) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        // rows past the end of the tensor are zero-filled by TMA (finite after the prologue): no row mask needed here
+        // rows past the last pixel of the batch (M) may hold another tensor's data (activation allocations are shared between tensors with
+        // disjoint live ranges) or TMA's zero fill past the end of the buffer: they are kept out of the range check; their products land in
+        // accumulator rows that are never stored inside the batch
         if (amax > 60000.f && p.range_flag) *p.range_flag = 1;
         fence_proxy_async();
         __syncwarp();

@@ -1,4 +1,4 @@
-// PTX wrappers shared by the tcgen05 kernels (conv_tc.cu, conv_fused.cu): mbarriers, TMA (bulk / tensor) copies,
+// PTX wrappers shared by the tcgen05 kernels (conv_tc.cu, conv_pair.cu, conv_halo.cu): mbarriers, TMA (bulk / tensor) copies,
 // TMEM allocation and loads, tcgen05.mma with shared-memory / instruction descriptors.  sm_100a only.
 #pragma once
 #include <cstdint>

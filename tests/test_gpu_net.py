@@ -198,36 +198,6 @@ def test_frame_pipeline_fused_call_vs_oracle_and_u8_frames(sd):
     assert np.array_equal(a["kp_used"][~near], ref["kp_used"][~near])
 
 
-@pytest.mark.parametrize("fuse_mode", [1, 2])
-@pytest.mark.parametrize("grid_cap", [0, 3])
-def test_fused_bottleneck_kernel_equals_unfused_kernels(sd, grid_cap, fuse_mode, monkeypatch):
-    """conv2 (3x3) + conv3 (1x1 + skip) of every 128-wide bottleneck as one kernel (csrc/conv_fused.cu) performs the same
-    floating-point operations in the same order as the two separate kernels: the whole network output must be IDENTICAL.
-    grid_cap = 3 forces ~43+ tiles per CTA at 64x64 (software pipeline across tiles, both TMEM accumulators recycled).
-    fuse_mode 1 = single-CTA kernel (conv_fused.cu), 2 = CTA-pair kernel (conv_fused2.cu, tcgen05.mma.cta_group::2)."""
-    if grid_cap:
-        monkeypatch.setenv("SUO_GRID_CAP", str(grid_cap))
-    rng = np.random.default_rng(21)
-    img = torch.from_numpy(rng.random((1, 3, 240, 320), dtype=np.float32)).cuda()
-    boxes = [torch.tensor([[10.0, 20.0, 200.0, 230.0], [100.0, 5.0, 310.0, 200.0], [50.0, 50.0, 120.0, 140.0]]).cuda()]
-    m = _model(sd, 2, 3, res=256, max_crops=3)
-    m.context().set_option(_lib.SUO_OPT_CONV_HALO, 0)      # the A-halo kernel accumulates in another order: identity holds among the others
-    outs = {}
-    for fuse in (1, 0):
-        m.context().set_option(_lib.SUO_OPT_CONV_FUSE, fuse_mode if fuse else 0)
-        n0 = m.context().kernel_launches()
-        o = m(img, boxes)
-        torch.cuda.synchronize()
-        outs[fuse] = (o, m.context().kernel_launches() - n0)
-    assert outs[1][1] < outs[0][1] - 50                      # 57 bottlenecks lost one launch each
-    for k in ("prob_logits", "uv", "cov", "kp_mask", "argmax"):
-        assert torch.equal(outs[1][0][k], outs[0][0][k]), k
-    ref = net_oracle.pkpnet_forward(sd, img.cpu(), [b.cpu() for b in boxes], None, (256, 256))
-    lr = ref["prob_logits"].numpy()
-    err = np.abs(outs[1][0]["prob_logits"].cpu().numpy() - lr).max()
-    assert err < 5e-4 * max(1.0, np.abs(lr).max() / 10), err
-
-
 def test_cta_pair_conv_kernel_equals_single_cta_kernels(sd):
     """The 3x3 convs as CTA pairs (csrc/conv_pair.cu, the default) vs one CTA per tile: identical network output."""
     rng = np.random.default_rng(22)
