@@ -145,3 +145,41 @@ def test_stem_weight_layout_matches_the_gather_order(cin_store):
     got = np.maximum(A @ wk[:64].T + pool[b_off:b_off + 64], 0).reshape(Ho, Wo, 64)
     ref = F.relu(F.conv2d(torch.from_numpy(x[:, :, :Cin]).permute(2, 0, 1)[None], torch.from_numpy(w), torch.from_numpy(b), stride=2, padding=3))
     np.testing.assert_allclose(got, ref[0].permute(1, 2, 0).numpy(), atol=2e-5)      # pool is float32
+
+
+def test_dropin_puts_the_library_under_the_reference_module_names():
+    """suo_slam_b200.dropin.install(): the three imports through which the reference reaches its hot path (lib/object_slam.py:9-10,14)
+    resolve to this package — with the reference's own lib/ package untouched when it is mounted."""
+    import importlib
+    import sys
+    from suo_slam_b200 import dropin, g2o as our_g2o, lambdatwist as our_lt
+    from suo_slam_b200.pkpnet import PkpNet
+    saved = {k: sys.modules.get(k) for k in ("g2o", "lambdatwist", "lib.models.pkpnet")}
+    try:
+        dropin.install()
+        assert importlib.import_module("g2o") is our_g2o and importlib.import_module("lambdatwist") is our_lt
+        for name in ("SparseOptimizer", "BlockSolverSE3", "LinearSolverDenseSE3", "LinearSolverCholmodSE3", "OptimizationAlgorithmLevenberg", "SE3Quat",
+                     "VertexSE3Expmap", "EdgeSE3ProjectFromObject", "EdgeSE3ProjectFromFixedObject", "RobustKernelHuber"):   # lib/object_slam.py:706-831
+            assert hasattr(our_g2o, name), name
+        assert callable(our_lt.pnp)
+        ref = "/root/reference"
+        if os.path.isdir(os.path.join(ref, "lib", "models")):
+            sys.path.insert(0, ref)
+            try:
+                for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+                    if k != "lib.models.pkpnet":
+                        sys.modules.pop(k)
+                mod = importlib.import_module("lib.models.pkpnet")          # what `from .models.pkpnet import PkpNet` resolves to
+                assert mod.PkpNet is PkpNet
+                hg = importlib.import_module("lib.models.hg")               # the rest of the reference package still imports from its own tree
+                assert hg.__file__.startswith(ref)
+            finally:
+                sys.path.remove(ref)
+                for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+                    sys.modules.pop(k)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
