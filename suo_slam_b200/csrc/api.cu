@@ -187,9 +187,10 @@ struct CtxExtra {
   struct FrameSlot {
     DevScratch in, out;
     cudaEvent_t h2d_done = nullptr, done = nullptr;
+    int* flag = nullptr;          // this batch's FP16-range flag: snapshot of the executor's flag taken (and the flag cleared) in stream order after the batch
     bool pending = false;
   } slot[2];
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr, aux_stream = nullptr;
   // NCCL entry point for suo_allgather_results, resolved at first use from the libnccl the process already loaded
   void* nccl_allgather = nullptr;
   const double* last_err = nullptr;   // per-edge errors left by the most recent suo_ba_batch (device, inside `ba`)
@@ -437,8 +438,10 @@ void suo_destroy(suo_ctx* ctx) {
       if (sl.out.d) cudaFree(sl.out.d);
       if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
       if (sl.done) cudaEventDestroy(sl.done);
+      if (sl.flag) cudaFree(sl.flag);
     }
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
+    if (x->aux_stream) cudaStreamDestroy(x->aux_stream);
     if (x->io.d) cudaFree(x->io.d);
     if (x->ba.d) cudaFree(x->ba.d);
     if (x->fr.d) cudaFree(x->fr.d);
@@ -1492,6 +1495,8 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   if (sl) {
     if (sl->pending) { ctx->set_error("suo_frames_u8_submit: slot still pending (call suo_frames_wait first)", __FILE__, __LINE__); return SUO_E_STATE; }
     if (!x->copy_stream) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    if (!x->aux_stream) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&x->aux_stream, cudaStreamNonBlocking));
+    if (!sl->flag) SUO_CUDA_TRY(ctx, cudaMalloc(&sl->flag, sizeof(int)));
     if (!sl->h2d_done) {
       SUO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming));
       SUO_CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl->done, cudaEventDisableTiming));
@@ -1561,6 +1566,9 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   if (run_ba) { D2H(T_ba, d_Tba, 96 * (size_t)L); D2H(ba_inliers, d_bain, LK); }
 #undef D2H
   if (sl) {
+    // this batch's range flag, in stream order: later batches raise (and clear) the executor's flag again, so suo_frames_wait reads the snapshot
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(sl->flag, N.range_flag, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemsetAsync(N.range_flag, 0, sizeof(int), s));
     SUO_CUDA_TRY(ctx, cudaEventRecord(sl->done, s));
     sl->pending = true;
     return SUO_OK;
@@ -1765,7 +1773,16 @@ int suo_frames_wait(suo_ctx* ctx, int slot) {
   if (!sl.pending) { ctx->set_error("suo_frames_wait: nothing submitted on this slot", __FILE__, __LINE__); return SUO_E_STATE; }
   SUO_CUDA_TRY(ctx, cudaEventSynchronize(sl.done));
   sl.pending = false;
-  return suo_check_range(ctx);
+  // (not suo_check_range: its blocking copy on the legacy stream would also wait for the NEXT batch, already queued behind this one, and the
+  // copies of the batch after that could no longer overlap it)
+  int flag = 0;
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(&flag, sl.flag, sizeof(int), cudaMemcpyDeviceToHost, X(ctx)->aux_stream));
+  SUO_CUDA_TRY(ctx, cudaStreamSynchronize(X(ctx)->aux_stream));
+  if (flag) {
+    ctx->set_error("fp16x3 conv math: an activation exceeded the FP16 range (|x| > 6e4) in this batch; results are invalid, use SUO_OPT_CONV_MATH = 0 (tf32x3)", __FILE__, __LINE__);
+    return SUO_E_RANGE;
+  }
+  return SUO_OK;
 }
 
 // ---- result records + the single exchange of the multi-GPU path -------------------------------------------------
