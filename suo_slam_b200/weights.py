@@ -185,11 +185,15 @@ def pack_state_dict(sd, num_kp: int = arch.NUM_KP) -> bytes:
         ll = B.conv(ll, B.buf(4, F, 1), wl, bl, CONV_1x1, relu=1)
         wt, bt = B.conv_wb(f"{p}.tmpOut.{i}")
         if i < arch.N_STACK - 1:
-            tmp = B.conv(ll, B.buf(4, 64, 1), wt, bt, CONV_1x1, cout_store=64)    # NHWC, 41 real + 23 zero channels
+            # x = x + ll_(ll) + tmpOut_(tmpOut(ll)) (hg.py:113-117).  The intermediate heat-maps of this stack are not returned (hg.py:119 keeps
+            # out[-1] only) and nothing non-linear sits between tmpOut and tmpOut_, so the two 1x1 convs and ll_ are ONE 1x1 conv on ll:
+            #   W = W_ll + W_tmpOut_ W_tmpOut,  b = b_ll + W_tmpOut_ b_tmpOut + b_tmpOut_      (folded in float64, rounded once like BN)
+            # — one launch and one pass over the 64x64x256 tensor instead of three (the reference's association differs by FP32 rounding only).
             wll, bll = B.conv_wb(f"{p}.ll_.{i}")
-            t = B.conv(ll, B.buf(4, F), wll, bll, CONV_1x1, res=x)                 # x + ll_
             wto, bto = B.conv_wb(f"{p}.tmpOut_.{i}")
-            x = B.conv(tmp, B.buf(4, F), wto, bto, CONV_1x1, res=t, cin_store=64)   # ... + tmpOut_
+            w_eff = wll[:, :, 0, 0] + wto[:, :, 0, 0] @ wt[:, :, 0, 0]
+            b_eff = bll + wto[:, :, 0, 0] @ bt + bto
+            x = B.conv(ll, B.buf(4, F), w_eff[:, :, None, None], b_eff, CONV_1x1, res=x)
         else:
             logits = B.conv(ll, B.buf(4, num_kp), wt, bt, CONV_1x1, out_nchw=1)   # NCHW heat-map logits
     cls_w = B.put(_np(sd["classifier.2.weight"]))

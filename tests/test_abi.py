@@ -36,10 +36,10 @@ def test_pack_state_dict_program():
     sd = synth.make_synthetic_state_dict(0)
     blob = weights.pack_state_dict(sd)
     info = weights.program_summary(blob)
-    # 186 reference convs + the second (RGB-only) stem variant
-    assert info["n_convs"] == 187
+    # 186 reference convs + the second (RGB-only) stem variant - 2: ll_, tmpOut_ and the first stack's tmpOut are folded into one 1x1 conv
+    assert info["n_convs"] == 185
     # 9 max-pools (hg.py:16,71) and 8 up-sample+adds (hg.py:56-58) in two depth-4 hourglasses
-    assert info["n_ops"] == 187 + 9 + 8
+    assert info["n_ops"] == 185 + 9 + 8
     h = np.frombuffer(blob[:64], np.int32)
     assert h[0] == weights.MAGIC and h[2] == arch.NUM_KP
 
@@ -87,7 +87,7 @@ def test_checkpoint_converter_roundtrip(tmp_path):
     assert epoch == 7 and args.dataset == "ycbv" and set(sd2) == set(sd)
     meta = checkpoint.convert(str(ck), str(tmp_path / "m.suo"))
     blob, meta2 = checkpoint.load_packed(str(tmp_path / "m.suo"))
-    assert meta2 == meta and meta["epoch"] == 7 and meta["n_convs"] == 187
+    assert meta2 == meta and meta["epoch"] == 7 and meta["n_convs"] == 185
     assert blob == weights.pack_state_dict(sd)
     m = PkpNet().load_packed(blob)
     assert m._blob == blob

@@ -31,7 +31,7 @@ def test_marker_state_dict_is_a_reference_format_state_dict():
     for k, shp in spec.items():
         assert tuple(sd[k].shape) == tuple(shp), k
     info = weights.program_summary(weights.pack_state_dict(sd))
-    assert info["n_convs"] == 187
+    assert info["n_convs"] == 185
     # dense: outside the hand-wired signal rows every conv keeps its seeded random weights
     w = sd["backbone.hourglass.1.up1_.0.conv2.weight"]
     assert float((w != 0).float().mean()) > 0.99
