@@ -80,3 +80,34 @@ def test_slam_sequence_vs_the_cpu_oracle(marker_model, corrupt):
                 m[bad][:3, 3] += [70.0, -50.0, 40.0]
         if corrupt and i == 1:
             assert bad in out["reinit_ids"]
+
+
+def test_slam_views_at_512_with_symmetric_priors():
+    """BASELINE configs[4] shape: 512x512 crops -> 128x128 heat-maps (the CTA-per-map reduction kernel, the 48-channel stem fed by device-rendered
+    priors), 4 objects of which 2 symmetric, 2 views — the same comparison as above at the T-LESS resolution and thresholds (evaluate.py:68-76)."""
+    sd = synth.make_marker_state_dict(0)
+    m = PkpNet(input_res=(512, 512), max_crops=4)
+    m.load_state_dict(sd)
+    m.cuda().eval()
+    seq = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
+    tl = dict(kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, init_with_outliers=True)
+    trk = slam.SlamTracker(m, **tl)
+    st = sfo.State()
+    for v in seq["views"]:
+        a = _view_args(seq, v)
+        out = trk.process_view(*a)
+        ref = sfo.process_view(st, sd, *a, res=512, **tl)
+        vid = v["view_id"]
+        assert out["cam_ok"] and ref["cam_ok"]
+        for o, d in st.detections[vid].items():
+            g = trk.detections[vid][o]
+            if np.array_equal(g["kp_mask"], d["kp_mask"]):
+                np.testing.assert_allclose(g["uv_pred"], d["uv_pred"], atol=2e-4)
+                if d["prior_uv"] is not None:
+                    np.testing.assert_allclose(g["prior_uv"], d["prior_uv"], atol=1e-4)
+        print(f"[slam 512 view {vid}] cam rel diff {_rel(trk.cam_poses[vid], st.cam_poses[vid]):.2e}, vs ground truth "
+              f"{np.linalg.norm(trk.cam_poses[vid][:, 3] - v['T_GtoC'][:3, 3]):.2f} mm, status {out['status'][:6].tolist()}")
+        assert _rel(trk.cam_poses[vid], st.cam_poses[vid]) < 1e-3
+        assert np.linalg.norm(trk.cam_poses[vid][:, 3] - v["T_GtoC"][:3, 3]) < 15.0
+    sym_ids = [o["obj_id"] for o in seq["objs"] if o["is_symmetric"]]
+    assert all(trk.detections[seq["views"][1]["view_id"]][o]["prior_uv"] is not None for o in sym_ids)      # the second view's symmetric crops saw priors
