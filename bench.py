@@ -653,7 +653,7 @@ def run_native_ba512(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = _lib.Context(device=local, max_crops=1, crop_res=256, num_kp=NUM_KP)
-    ctx.set_option(_lib.SUO_OPT_BA_BLOCK_DIAGONAL, 1)
+    ctx.set_option(_lib.SUO_OPT_BA_BLOCK_DIAGONAL, 2)      # 512 single-object problems: one warp each, no host look at the graph structure
     lib, hdl, p = _lib.lib(), ctx.handle, _lib.ptr
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -727,7 +727,7 @@ def run_native_ba512(args):
                        "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for k, v in pinned.items()) + h_inl.numel()),
                        "d2h_bytes_per_step": int(h_poses.numel() * 8 + h_inl.numel() + h_stats.numel() * 4), "ms_per_step": ms_e2e / args.steps},
                "gpu_launches": int(launches), "clocks": clocks,
-               "roofline": {"bound": "latency / FP64 issue", "kernel": "ba_kernel (one CTA per object graph, FP64, state in shared memory)",
+               "roofline": {"bound": "latency / FP64 issue", "kernel": "ba_warp_kernel (one warp per object graph, FP64, LM state in registers, shuffle reductions, no barrier)",
                             "achieved": flop / (step_ms * 1e-3) * 1e-12, "peak": 40.0, "unit": "TFLOP/s (FP64)", "frac": flop / (step_ms * 1e-3) * 1e-12 / 40.0,
                             "peak_source": "nominal B200 FP64 (SURVEY.md §8d); the kernel is bound by the serial LM dependency chain of 512 tiny problems, not by FP64 issue",
                             "algorithmic_flop_per_step": flop, "traffic": None}}

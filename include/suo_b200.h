@@ -59,7 +59,9 @@ enum {
   SUO_OPT_BA_BLOCK_DIAGONAL = 11 /* 1 = the caller vouches that every graph passed to suo_ba_batch with DEVICE pointers has exactly one free
                                    vertex per edge and at most 64 vertices (single-view / curr_only graphs): the call then only enqueues the
                                    shared-memory kernel instead of copying the index arrays to the host to choose a kernel (a violation is
-                                   reported per problem through stats[.,0] = -1 / -2).  0 (default) = inspect the structure */
+                                   reported per problem through stats[.,0] = -1 / -2 / -3).  2 = additionally every problem has ONE free vertex and at
+                                   most one fixed one (BASELINE config 3, the curr_only camera solve): one warp per problem, state in registers.
+                                   0 (default) = inspect the structure (host-pointer calls always do, and pick the same kernels) */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

@@ -476,7 +476,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_PDL: ctx->opt_pdl = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_CONV_HALO: ctx->opt_halo = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_PNP_MAX_POINTS: if (value < 4 || value > 4096) return SUO_E_INVALID; ctx->opt_pnp_max_pts = value; return SUO_OK;
-    case SUO_OPT_BA_BLOCK_DIAGONAL: ctx->opt_ba_blockdiag = value ? 1 : 0; return SUO_OK;
+    case SUO_OPT_BA_BLOCK_DIAGONAL: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_ba_blockdiag = value; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -1122,6 +1122,18 @@ static bool ba_needs_global(int n_prob, const int32_t* prob_vert, const int32_t*
   return false;
 }
 
+// True when every problem has one free vertex and at most one fixed one (BASELINE config 3, single-object frames, the curr_only camera solve):
+// those run one warp per problem (ba_warp_kernel) instead of one CTA per problem.
+static bool ba_single_vertex(int n_prob, const int32_t* prob_vert, const uint8_t* fixed) {
+  for (int pr = 0; pr < n_prob; ++pr) {
+    const int v0 = prob_vert[pr], nv = prob_vert[pr + 1] - v0;
+    if (nv < 1 || nv > 2) return false;
+    const int n_free = (fixed[v0] ? 0 : 1) + ((nv == 2 && !fixed[v0 + 1]) ? 1 : 0);
+    if (n_free != 1) return false;
+  }
+  return true;
+}
+
 // Host arrays describe the graph structure (indices only); every d_* pointer is the device copy of the packed graph.
 static int run_ba_global(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32_t* prob_edge, const uint8_t* fixed,
                          int n_vert, const int32_t* e_obj, const int32_t* e_cam, int n_edges, ba::BaArgs base, cudaStream_t s) {
@@ -1250,7 +1262,8 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   };
   if (on_device && ctx->opt_ba_blockdiag)    // the caller vouches for the structure: no host look at the index arrays, no synchronisation
     return launch_ba_batch_scratch(ctx, n_prob, prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers,
-                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s);
+                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s, nullptr, nullptr,
+                                   ctx->opt_ba_blockdiag == 2);
   if (on_device) {
     // The graph structure decides the kernel: bring the index arrays to the host (this synchronises `stream`; the
     // device-resident frame path, suo_solve_keypoints / suo_frames, does not come through here).
@@ -1267,7 +1280,8 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
       return run_ba_global(ctx, n_prob, h_pv.data(), h_pe.data(), h_fx.data(), n_vert, h_eo.data(), h_ec.data(), n_edges,
                            base_args(prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, stats), s);
     return launch_ba_batch_scratch(ctx, n_prob, prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers,
-                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s);
+                                   its, n_rounds, huber_delta, chi2_gate, init_with_outliers, stats, d_err, d_level, d_fv, s, nullptr, nullptr,
+                                   ba_single_vertex(n_prob, h_pv.data(), h_fx.data()));
   }
   // host-side validation (the kernels report the same conditions through stats)
   if (prob_vert[n_prob] > n_vert || prob_edge[n_prob] > n_edges) { ctx->set_error("suo_ba_batch: offsets exceed n_vert / n_edges", __FILE__, __LINE__); return SUO_E_INVALID; }
@@ -1306,7 +1320,8 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
                        base_args(d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its, d_st), s);
   else
     rc = launch_ba_batch_scratch(ctx, n_prob, d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its,
-                                 n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s);
+                                 n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s, nullptr, nullptr,
+                                 ba_single_vertex(n_prob, prob_vert, fixed));
   if (rc) return rc;
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(poses, d_poses, 12 * (size_t)n_vert * 8, cudaMemcpyDeviceToHost, s));
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(inliers, d_inl, n_edges, cudaMemcpyDeviceToHost, s));
@@ -1742,7 +1757,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b_its, its_host, sizeof(its_host), cudaMemcpyHostToDevice, s));
   SUO_CUDA_TRY(ctx, cudaMemsetAsync(b_st, 0, 3 * sizeof(int32_t), s));
   rc = launch_ba_batch_scratch(ctx, 1, b_pv, b_pe, b_poses, b_fixed, b_eo, b_ecam, b_ck, b_p, b_uv, b_info, b_inl, b_its, 4, 2.4476519768340177 /* sqrt(5.991) */,
-                               5.991, init_with_outliers, b_st, b_err, b_lvl, b_fv, s, b_vc, b_ec);
+                               5.991, init_with_outliers, b_st, b_err, b_lvl, b_fv, s, b_vc, b_ec, 1 /* one camera vertex: warp kernel */);
   if (rc) return rc;
   rc = launch_slam_ba_scatter(ctx, L, K, b_ec, b_src, b_inl, b_poses, b_st, o_cam, o_bain, o_st, s);
   if (rc || on_device) return rc;

@@ -287,6 +287,223 @@ ba_kernel(const BaArgs a) {
   if (tid == 0 && a.stats) { a.stats[3 * prob] = rounds; a.stats[3 * prob + 1] = outer_total; a.stats[3 * prob + 2] = trials_total; }
 }
 
+// ---- one WARP per problem: graphs with a single free vertex and at most one fixed one -----------------------------------------
+// BASELINE config 3 (512 objects, each its own LM problem against a fixed camera), single-object frames and the curr_only camera solve of
+// SLAM mode (one camera vertex, unary edges) have ONE 6x6 block: a CTA per graph leaves 3 of 4 warps idle and pays ~12 block barriers per
+// LM iteration.  Here the whole LM state of a problem (vertex estimate, backup, H, b, lambda) lives in the registers of one warp, edges are
+// strided over the lanes, sums are shuffle trees (every lane ends up with the same value, so every lane takes the same branch), the 6x6
+// solve runs on lane 0 and is broadcast: no shared memory, no barrier.  Same LM driver, same g2o semantics as ba_kernel (accept / reject rule,
+// rejected-trial error left in the edges, rounds with chi2 re-classification, Huber strip); the summation order differs, i.e. results agree with
+// ba_kernel and the oracle to FP64 rounding.
+constexpr int BAW_THREADS = 128;
+
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(BAW_THREADS)
+ba_warp_kernel(const BaArgs a, int n_prob) {
+  const int lane = threadIdx.x & 31;
+  const int prob = blockIdx.x * (BAW_THREADS / 32) + (threadIdx.x >> 5);
+  if (prob >= n_prob) return;
+  const int v0 = a.prob_vert[prob], nv = a.vert_cnt ? a.vert_cnt[prob] : a.prob_vert[prob + 1] - v0;
+  const int e0 = a.prob_edge[prob], ne = a.edge_cnt ? a.edge_cnt[prob] : a.prob_edge[prob + 1] - e0;
+  auto fail = [&](int code) { if (lane == 0 && a.stats) { a.stats[3 * prob] = code; a.stats[3 * prob + 1] = 0; a.stats[3 * prob + 2] = 0; } };
+  if (nv < 1 || nv > 2) { fail(-1); return; }
+  const bool f0 = !a.fixed[v0], f1 = nv == 2 && !a.fixed[v0 + 1];
+  if (f0 == f1) { fail(f0 ? -2 : -3); return; }          // two free vertices (coupled: ba_global.cu) / nothing to optimise
+  const int vfree = f0 ? v0 : v0 + 1, vother = nv == 2 ? (f0 ? v0 + 1 : v0) : -1;
+  auto load = [&](int v, SE3q& o) {
+    const double* T = a.poses + 12 * (size_t)v;
+    const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+    const double t[3] = {T[3], T[7], T[11]};
+    se3_from_Rt(R, t, o);
+  };
+  SE3q est, bak, other;
+  load(vfree, est);
+  if (vother >= 0) load(vother, other); else other = est;
+  bak = est;
+  // which vertex of each edge is free (0 = the object, 1 = the camera, -1 = none)
+  int bad = 0;
+  for (int e = lane; e < ne; e += 32) {
+    const int ge = e0 + e, vo = a.e_obj[ge], vc = a.e_cam[ge];
+    const bool in_range = (vo < 0 || vo == vfree || vo == vother) && (vc == vfree || vc == vother);
+    int8_t k = -1;
+    if (!in_range || (vo == vfree && vc == vfree)) bad = 1;
+    else if (vo == vfree) k = 0;
+    else if (vc == vfree) k = 1;
+    a.fv_kind[ge] = k;
+  }
+  if (__any_sync(0xffffffffu, bad)) { fail(-2); return; }
+
+  auto edge_error = [&](int ge) {   // computeError
+    double pw[3] = {a.p[3 * ge], a.p[3 * ge + 1], a.p[3 * ge + 2]}, pc[3];
+    if (a.e_obj[ge] >= 0) { double tmp[3]; se3_map(a.e_obj[ge] == vfree ? est : other, pw, tmp); pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; }
+    se3_map(a.e_cam[ge] == vfree ? est : other, pw, pc);
+    const double* k = a.cam_k + 4 * ge;
+    a.err[2 * ge] = a.uv[2 * ge] - (k[0] * pc[0] / pc[2] + k[2]);
+    a.err[2 * ge + 1] = a.uv[2 * ge + 1] - (k[1] * pc[1] / pc[2] + k[3]);
+  };
+  auto edge_chi2 = [&](int ge) {
+    const double* O = a.info + 4 * ge;
+    const double r0 = a.err[2 * ge], r1 = a.err[2 * ge + 1];
+    return r0 * (O[0] * r0 + O[1] * r1) + r1 * (O[2] * r0 + O[3] * r1);
+  };
+  auto is_active = [&](int ge) { return a.level[ge] == 0 && a.fv_kind[ge] >= 0; };
+  auto chi_sum = [&](int robust) {   // computeActiveErrors + activeRobustChi2
+    double part = 0;
+    for (int e = lane; e < ne; e += 32) {
+      const int ge = e0 + e;
+      if (!is_active(ge)) continue;
+      edge_error(ge);
+      const double c = edge_chi2(ge);
+      if (robust) { double r0, r1; huber(c, a.huber_delta, r0, r1); part += r0; } else part += c;
+    }
+    return warp_sum(part);
+  };
+
+  // ---- initial chi2 classification (object_slam.py:848-866) ----
+  int my_good = 0;
+  for (int e = lane; e < ne; e += 32) {
+    const int ge = e0 + e;
+    if (a.init_with_outliers) { a.level[ge] = 0; a.err[2 * ge] = 0.0; a.err[2 * ge + 1] = 0.0; my_good++; }
+    else {
+      edge_error(ge);
+      if (edge_chi2(ge) > a.chi2_gate) { a.level[ge] = 1; a.inliers[ge] = 0; }
+      else { a.level[ge] = 0; a.inliers[ge] = 1; my_good++; }
+    }
+  }
+  int num_good = warp_sum_i(my_good);
+  int robust = 1, rounds = 0, outer_total = 0, trials_total = 0;
+
+  for (int round = 0; round < a.n_rounds; ++round) {
+    if (ne < 4 || num_good < 4) break;
+    int any = 0;
+    for (int e = lane; e < ne; e += 32) any |= is_active(e0 + e) ? 1 : 0;
+    any = __any_sync(0xffffffffu, any);
+    ++rounds;
+    if (any) {
+      bool ok = true;
+      const int iters = a.its[round];
+      double lambda = 0, ni = 2;
+      for (int it = 0; it < iters && ok; ++it) {
+        const double currentChi0 = chi_sum(robust);
+        // buildSystem: b (6) and the upper triangle of H (21), lane-strided partial sums + shuffle tree
+        double acc[27];
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc[k] = 0;
+        for (int e = lane; e < ne; e += 32) {
+          const int ge = e0 + e;
+          if (!is_active(ge)) continue;
+          double pw[3] = {a.p[3 * ge], a.p[3 * ge + 1], a.p[3 * ge + 2]}, pc[3];
+          if (a.e_obj[ge] >= 0) { double tmp[3]; se3_map(a.e_obj[ge] == vfree ? est : other, pw, tmp); pw[0] = tmp[0]; pw[1] = tmp[1]; pw[2] = tmp[2]; }
+          const SE3q& Tcw = a.e_cam[ge] == vfree ? est : other;
+          se3_map(Tcw, pw, pc);
+          double Rcw[9], J[12], Jx[12];
+          se3_R(Tcw, Rcw);
+          const bool wrt_obj = a.fv_kind[ge] == 0;
+          edge_jacobians(Rcw, pw, pc, a.cam_k + 4 * ge, wrt_obj, !wrt_obj, wrt_obj ? J : Jx, wrt_obj ? Jx : J);
+          const double* O = a.info + 4 * ge;
+          const double r0 = a.err[2 * ge], r1 = a.err[2 * ge + 1];
+          double w = 1.0;
+          if (robust) { double h0; huber(r0 * (O[0] * r0 + O[1] * r1) + r1 * (O[2] * r0 + O[3] * r1), a.huber_delta, h0, w); }
+          const double or0 = -(O[0] * r0 + O[1] * r1) * w, or1 = -(O[2] * r0 + O[3] * r1) * w;
+          const double w00 = O[0] * w, w01 = O[1] * w, w10 = O[2] * w, w11 = O[3] * w;
+          int idx = 6;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            acc[c] += J[c] * or0 + J[6 + c] * or1;
+            const double a0 = J[c] * w00 + J[6 + c] * w10, a1 = J[c] * w01 + J[6 + c] * w11;
+#pragma unroll
+            for (int d = c; d < 6; ++d) acc[idx++] += a0 * J[d] + a1 * J[6 + d];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 27; ++k) acc[k] = warp_sum(acc[k]);
+        if (it == 0) {   // computeLambdaInit
+          double mx = 0;
+          int idx = 6;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { mx = fmax(fabs(acc[idx]), mx); idx += 6 - c; }
+          lambda = 1e-5 * mx; ni = 2.0;
+        }
+        double cur = currentChi0, rho = 0;
+        int qmax = 0;
+        bool lam_bad = false;
+        do {
+          bak = est;
+          double x[6];
+          int okv = 1;
+          if (lane == 0) {
+            double A[36], rhs[6];
+            int idx = 6;
+            for (int c = 0; c < 6; ++c) {
+              rhs[c] = acc[c];
+              for (int d = c; d < 6; ++d) { A[6 * c + d] = acc[idx]; A[6 * d + c] = acc[idx]; ++idx; }
+            }
+            for (int j = 0; j < 6; ++j) A[7 * j] += lambda;
+            okv = chol6(A, rhs) ? 1 : 0;
+            for (int j = 0; j < 6; ++j) x[j] = okv ? rhs[j] : 0.0;
+          }
+          okv = __shfl_sync(0xffffffffu, okv, 0);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) x[j] = __shfl_sync(0xffffffffu, x[j], 0);
+          SE3q nw;
+          se3_oplus(est, x, nw);
+          est = nw;
+          double tempChi = chi_sum(robust);
+          double scale = 0;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + acc[j]);   // computeScale
+          if (!okv) tempChi = 1.7976931348623157e308;
+          const double r = (cur - tempChi) / (scale + 1e-3);
+          int flag;
+          if (r > 0 && isfinite(tempChi)) {
+            double alpha = 1. - pow(2 * r - 1, 3.0);
+            alpha = fmin(alpha, 2. / 3.);
+            lambda *= fmax(1. / 3., alpha);
+            ni = 2; cur = tempChi; flag = 1;
+          } else {
+            lambda *= ni; ni *= 2; flag = 0;
+            if (!isfinite(lambda)) flag = 2;
+          }
+          rho = r;
+          if (flag != 1) est = bak;      // pop(): restore the vertex; edge errors stay those of the rejected trial
+          ++trials_total;
+          if (flag == 2) { lam_bad = true; break; }
+          qmax++;
+        } while (rho < 0 && qmax < 10);
+        ++outer_total;
+        if (qmax == 10 || rho == 0 || lam_bad) ok = false;   // Terminate
+      }
+    }
+    // ---------------- chi2 re-classification (object_slam.py:878-896) ----------------
+    my_good = 0;
+    for (int e = lane; e < ne; e += 32) {
+      const int ge = e0 + e;
+      if (!a.inliers[ge]) edge_error(ge);
+      if (edge_chi2(ge) > a.chi2_gate) { a.level[ge] = 1; a.inliers[ge] = 0; }
+      else { a.level[ge] = 0; a.inliers[ge] = 1; my_good++; }
+    }
+    num_good = warp_sum_i(my_good);
+    if (round == max(1, a.n_rounds / 2)) robust = 0;
+  }
+  if (lane == 0) {
+    double R[9];
+    se3_R(est, R);
+    double* T = a.poses + 12 * (size_t)vfree;
+    for (int r = 0; r < 3; ++r) { T[4 * r] = R[3 * r]; T[4 * r + 1] = R[3 * r + 1]; T[4 * r + 2] = R[3 * r + 2]; T[4 * r + 3] = est.t[r]; }
+    if (vother >= 0) {      // (ba_kernel rewrites fixed vertices too: normalised through the quaternion)
+      se3_R(other, R);
+      T = a.poses + 12 * (size_t)vother;
+      for (int r = 0; r < 3; ++r) { T[4 * r] = R[3 * r]; T[4 * r + 1] = R[3 * r + 1]; T[4 * r + 2] = R[3 * r + 2]; T[4 * r + 3] = other.t[r]; }
+    }
+    if (a.stats) { a.stats[3 * prob] = rounds; a.stats[3 * prob + 1] = outer_total; a.stats[3 * prob + 2] = trials_total; }
+  }
+}
+
 // error and both Jacobians of independent edges at given vertex poses (suo_edge_linearize): the device functions the LM
 // kernels use, exposed so that tests can compare them with central differences (the recipe left commented out in
 // types_object_slam.cpp:108-122).
@@ -328,9 +545,10 @@ int launch_edge_linearize(suo_ctx* ctx, int n_edges, const double* T_obj, const 
   return SUO_OK;
 }
 
-int launch_ba_kernel(suo_ctx* ctx, int n_prob, const BaArgs& args, cudaStream_t s) {
+int launch_ba_kernel(suo_ctx* ctx, int n_prob, const BaArgs& args, cudaStream_t s, int single_vertex) {
   if (n_prob <= 0) return SUO_OK;
-  ba_kernel<<<n_prob, BA_THREADS, 0, s>>>(args);
+  if (single_vertex) ba_warp_kernel<<<(n_prob + BAW_THREADS / 32 - 1) / (BAW_THREADS / 32), BAW_THREADS, 0, s>>>(args, n_prob);
+  else ba_kernel<<<n_prob, BA_THREADS, 0, s>>>(args);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
@@ -342,11 +560,11 @@ int launch_ba_batch_scratch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, 
                             const double* p, const double* uv, const double* info, uint8_t* inliers,
                             const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
                             int init_with_outliers, int32_t* stats, double* err_scratch, uint8_t* level_scratch,
-                            int8_t* fv_scratch, cudaStream_t s, const int32_t* vert_cnt, const int32_t* edge_cnt) {
+                            int8_t* fv_scratch, cudaStream_t s, const int32_t* vert_cnt, const int32_t* edge_cnt, int single_vertex) {
   BaArgs a;
   a.prob_vert = prob_vert; a.prob_edge = prob_edge; a.vert_cnt = vert_cnt; a.edge_cnt = edge_cnt; a.poses = poses; a.fixed = fixed; a.e_obj = e_obj; a.e_cam = e_cam;
   a.cam_k = cam_k; a.p = p; a.uv = uv; a.info = info; a.inliers = inliers; a.its = its; a.n_rounds = n_rounds;
   a.huber_delta = huber_delta; a.chi2_gate = chi2_gate; a.init_with_outliers = init_with_outliers; a.stats = stats;
   a.err = err_scratch; a.level = level_scratch; a.fv_kind = fv_scratch;
-  return launch_ba_kernel(ctx, n_prob, a, s);
+  return launch_ba_kernel(ctx, n_prob, a, s, single_vertex);
 }

@@ -135,7 +135,7 @@ int launch_ba_batch_scratch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, 
                             const int32_t* its, int n_rounds, double huber_delta, double chi2_gate,
                             int init_with_outliers, int32_t* stats, double* err_scratch, uint8_t* level_scratch,
                             int8_t* fv_scratch, cudaStream_t s, const int32_t* vert_cnt = nullptr,
-                            const int32_t* edge_cnt = nullptr);
+                            const int32_t* edge_cnt = nullptr, int single_vertex = 0);
 
 int launch_gate_compact(suo_ctx* ctx, const float* uv, const float* cov, const float* kp_mask, const uint8_t* model_mask,
                         const double* model_kps, const double* K_bbox, int L, int K, float kp_var_thresh, float bbox_thresh,
