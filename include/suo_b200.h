@@ -305,7 +305,8 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
  * and returns at once; suo_frames_wait blocks until that slot's results are in the host output buffers (and reports
  * the FP16-range flag like the synchronous call).  With two slots the copies of batch i+1 overlap the kernels of
  * batch i.  Input and output buffers must stay valid (and should be pinned) until the wait returns; a slot must be
- * waited for before it is submitted again.  slot in {0, 1}.  records_dev (DEVICE pointer, L records, or NULL): the
+ * waited for before it is submitted again, and both slots must use the SAME `stream` (they share the executor; a
+ * different stream while the other slot is pending is SUO_E_INVALID).  slot in {0, 1}.  records_dev (DEVICE pointer, L records, or NULL): the
  * batch's result records (suo_pack_records layout, crop_id = record_id_base + index) are also packed there on `stream`,
  * ready for suo_allgather_results — the multi-GPU exchange then needs no host round trip. */
 int suo_frames_u8_submit(suo_ctx* ctx, int slot, const uint8_t* images_hwc, int n_img, int H, int W,

@@ -189,6 +189,7 @@ struct CtxExtra {
     cudaEvent_t h2d_done = nullptr, done = nullptr;
     int* flag = nullptr;          // this batch's FP16-range flag: snapshot of the executor's flag taken (and the flag cleared) in stream order after the batch
     bool pending = false;
+    cudaStream_t stream = nullptr; // the stream the pending batch runs on
   } slot[2];
   cudaStream_t copy_stream = nullptr, aux_stream = nullptr;
   // NCCL entry point for suo_allgather_results, resolved at first use from the libnccl the process already loaded
@@ -1509,6 +1510,11 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
   cudaStream_t cs = s;
   if (sl) {
     if (sl->pending) { ctx->set_error("suo_frames_u8_submit: slot still pending (call suo_frames_wait first)", __FILE__, __LINE__); return SUO_E_STATE; }
+    // both batches run through the ONE executor (activations, keypoint buffers, solver workspace): only stream order keeps them apart
+    if (x->slot[slot ^ 1].pending && x->slot[slot ^ 1].stream != s) {
+      ctx->set_error("suo_frames_u8_submit: both slots must be submitted on the same stream", __FILE__, __LINE__);
+      return SUO_E_INVALID;
+    }
     if (!x->copy_stream) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
     if (!x->aux_stream) SUO_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&x->aux_stream, cudaStreamNonBlocking));
     if (!sl->flag) SUO_CUDA_TRY(ctx, cudaMalloc(&sl->flag, sizeof(int)));
@@ -1586,6 +1592,7 @@ static int frames_impl(suo_ctx* ctx, const void* images, int images_u8, int n_im
     SUO_CUDA_TRY(ctx, cudaMemsetAsync(N.range_flag, 0, sizeof(int), s));
     SUO_CUDA_TRY(ctx, cudaEventRecord(sl->done, s));
     sl->pending = true;
+    sl->stream = s;
     return SUO_OK;
   }
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));

@@ -282,11 +282,14 @@ def test_asynchronous_frame_batches_equal_the_synchronous_call(marker_model):
     recs = [torch.zeros((L, rb), dtype=torch.uint8, device="cuda") for _ in range(3)]
     stream = torch.cuda.current_stream().cuda_stream
 
-    def submit(i):
+    def submit(i, slot=None, stream=stream):
         a, o = ins[i], outs[i]
-        ctx.check(lib.suo_frames_u8_submit(ctx.handle, i % 2, p(a["img"]), 2, 480, 640, p(a["boxes"]), p(a["bi"]), L, p(a["mk"]), p(a["mm"]), p(a["kb"]), p(a["diam"]),
+        ctx.check(lib.suo_frames_u8_submit(ctx.handle, i % 2 if slot is None else slot, p(a["img"]), 2, 480, 640, p(a["boxes"]), p(a["bi"]), L, p(a["mk"]), p(a["mm"]), p(a["kb"]), p(a["diam"]),
                                            0.2, 0.9, 0, 1, p(o["T_pnp"]), p(o["T_ba"]), p(o["used"]), p(o["bain"]), p(o["uv"]), p(o["cov"]), p(recs[i]), 1000 * i, stream))
     submit(0)
+    other = torch.cuda.Stream()
+    with pytest.raises(_lib.SuoError, match="same stream"):
+        submit(1, stream=other.cuda_stream)           # the two slots share the executor: one stream only
     submit(1)
     with pytest.raises(_lib.SuoError, match="pending"):
         submit(2)                                     # slot 0 has not been waited for
