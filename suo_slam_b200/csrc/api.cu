@@ -160,8 +160,11 @@ struct NetState {
   std::vector<cudaEvent_t> op_done;
 };
 
-struct DevScratch {   // growable device + pinned staging for host-pointer calls
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DevScratch {   // growable device block (+ an optional pinned host mirror of it) for host-pointer calls
   void* d = nullptr; size_t dn = 0;
+  void* h = nullptr; size_t hn = 0;
   int grow(suo_ctx* ctx, size_t n) {
     if (n <= dn) return SUO_OK;
     if (d) { cudaDeviceSynchronize(); cudaFree(d); }      // enqueued work (asynchronous submits included) may still use the old block
@@ -170,6 +173,37 @@ struct DevScratch {   // growable device + pinned staging for host-pointer calls
     dn = n;
     return SUO_OK;
   }
+  int mirror(suo_ctx* ctx, size_t n) {                    // every user of the mirror synchronises its stream before it returns
+    if (n <= hn) return SUO_OK;
+    if (h) cudaFreeHost(h);
+    hn = 0; h = nullptr;
+    const size_t cap = align_up(n + n / 2, 4096);
+    SUO_CUDA_TRY(ctx, cudaHostAlloc(&h, cap, cudaHostAllocDefault));
+    hn = cap;
+    return SUO_OK;
+  }
+  void release() { if (d) cudaFree(d); if (h) cudaFreeHost(h); d = h = nullptr; dn = hn = 0; }
+};
+
+// Host-pointer calls with many SMALL arrays (pnp(), optimize(), a SLAM-mode view): a cudaMemcpyAsync from pageable memory costs 10-20 us
+// whatever its size, and these calls make 6-30 of them.  The arrays are packed with memcpy into the pinned mirror of the device block at
+// the offsets the device pointers have, and cross PCIe as ONE copy each way.
+struct Stage {
+  uint8_t* d0; uint8_t* h0;
+  size_t in_lo = SIZE_MAX, in_hi = 0, out_lo = SIZE_MAX, out_hi = 0;
+  Stage(const DevScratch& b) : d0(static_cast<uint8_t*>(b.d)), h0(static_cast<uint8_t*>(b.h)) {}
+  template <typename T> void in(const T* dev, const T* src, size_t n) {
+    const size_t o = reinterpret_cast<const uint8_t*>(dev) - d0;
+    std::memcpy(h0 + o, src, n * sizeof(T));
+    in_lo = std::min(in_lo, o); in_hi = std::max(in_hi, o + n * sizeof(T));
+  }
+  cudaError_t send(cudaStream_t s) const { return in_hi > in_lo ? cudaMemcpyAsync(d0 + in_lo, h0 + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s) : cudaSuccess; }
+  template <typename T> void want(const T* dev, size_t n) {
+    const size_t o = reinterpret_cast<const uint8_t*>(dev) - d0;
+    out_lo = std::min(out_lo, o); out_hi = std::max(out_hi, o + n * sizeof(T));
+  }
+  cudaError_t fetch(cudaStream_t s) const { return out_hi > out_lo ? cudaMemcpyAsync(h0 + out_lo, d0 + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
+  template <typename T> void out(T* dst, const T* dev, size_t n) const { if (dst) std::memcpy(dst, h0 + (reinterpret_cast<const uint8_t*>(dev) - d0), n * sizeof(T)); }
 };
 
 struct CtxExtra {
@@ -200,7 +234,6 @@ struct CtxExtra {
 
 CtxExtra* X(suo_ctx* c) { return reinterpret_cast<CtxExtra*>(c->net); }
 
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // bump allocator over one device scratch block
 struct Bump {
@@ -435,18 +468,14 @@ void suo_destroy(suo_ctx* ctx) {
     if (N.pooled) cudaFree(N.pooled);
     if (N.d_uv) cudaFree(N.d_uv);
     for (auto& sl : x->slot) {
-      if (sl.in.d) cudaFree(sl.in.d);
-      if (sl.out.d) cudaFree(sl.out.d);
+      sl.in.release(); sl.out.release();
       if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
       if (sl.done) cudaEventDestroy(sl.done);
       if (sl.flag) cudaFree(sl.flag);
     }
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->aux_stream) cudaStreamDestroy(x->aux_stream);
-    if (x->io.d) cudaFree(x->io.d);
-    if (x->ba.d) cudaFree(x->ba.d);
-    if (x->fr.d) cudaFree(x->fr.d);
-    if (x->bg.d) cudaFree(x->bg.d);
+    x->io.release(); x->ba.release(); x->fr.release(); x->bg.release();
     if (x->pnp_off) cudaFree(x->pnp_off);
     if (x->pnp_keys) cudaFree(x->pnp_keys);
     delete x;
@@ -1089,7 +1118,9 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
     max_pts = std::max(max_pts, offsets[o + 1] - offsets[o]);
   }
   CtxExtra* x = X(ctx);
-  rc = x->io.grow(ctx, (size_t)N * 5 * 8 + (size_t)n_obj * (16 * 8 + 5 * 4 + 8 + 4) + 8192);
+  const size_t io_bytes = (size_t)N * 5 * 8 + (size_t)n_obj * (16 * 8 + 5 * 4 + 8 + 4) + 8192;
+  rc = x->io.grow(ctx, io_bytes);
+  if (!rc) rc = x->io.mirror(ctx, io_bytes);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->io.d)};
   double* d_xs = bp.take<double>(3 * (size_t)N);
@@ -1098,15 +1129,16 @@ int suo_pnp_batch(suo_ctx* ctx, const double* xs, const double* ys, const int32_
   uint64_t* d_keys = obj_keys ? bp.take<uint64_t>(n_obj) : nullptr;
   double* d_T = bp.take<double>(16 * (size_t)n_obj);
   int32_t* d_st = bp.take<int32_t>(5 * (size_t)n_obj);
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_xs, xs, 3 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_ys, ys, 2 * (size_t)N * 8, cudaMemcpyHostToDevice, s));
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_off, offsets, (n_obj + 1) * 4, cudaMemcpyHostToDevice, s));
-  if (d_keys) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(d_keys, obj_keys, n_obj * 8, cudaMemcpyHostToDevice, s));
+  Stage st(x->io);
+  st.in(d_xs, xs, 3 * (size_t)N); st.in(d_ys, ys, 2 * (size_t)N); st.in(d_off, offsets, (size_t)n_obj + 1);
+  if (d_keys) st.in(d_keys, obj_keys, (size_t)n_obj);
+  SUO_CUDA_TRY(ctx, st.send(s));
   rc = launch_pnp_batch(ctx, d_xs, d_ys, d_off, n_obj, threshold, seed, d_keys, d_T, d_st, s, max_pts);
   if (rc) return rc;
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(T_out, d_T, 16 * (size_t)n_obj * 8, cudaMemcpyDeviceToHost, s));
-  if (stats) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(stats, d_st, 5 * (size_t)n_obj * 4, cudaMemcpyDeviceToHost, s));
+  st.want(d_T, 16 * (size_t)n_obj); st.want(d_st, 5 * (size_t)n_obj);
+  SUO_CUDA_TRY(ctx, st.fetch(s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  st.out(T_out, d_T, 16 * (size_t)n_obj); st.out(stats, d_st, 5 * (size_t)n_obj);
   return SUO_OK;
 }
 
@@ -1292,12 +1324,13 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
         ctx->set_error("suo_ba_batch: edge references a vertex outside its problem", __FILE__, __LINE__); return SUO_E_INVALID;
       }
   const bool global = ba_needs_global(n_prob, prob_vert, prob_edge, fixed, e_obj, e_cam);
-  rc = x->io.grow(ctx, (size_t)n_vert * (12 * 8 + 1) + (size_t)n_edges * (4 + 4 + (4 + 3 + 2 + 4) * 8 + 1) + (size_t)n_prob * (8 + 12) + 16 * 4 + 16384);
+  const size_t io_bytes = (size_t)n_vert * (12 * 8 + 1) + (size_t)n_edges * (4 + 4 + (4 + 3 + 2 + 4) * 8 + 1) + (size_t)n_prob * (8 + 12) + 16 * 4 + 16384;
+  rc = x->io.grow(ctx, io_bytes);
+  if (!rc) rc = x->io.mirror(ctx, io_bytes);
   if (rc) return rc;
   Bump bp{static_cast<uint8_t*>(x->io.d)};
   int32_t* d_pv = bp.take<int32_t>(n_prob + 1);
   int32_t* d_pe = bp.take<int32_t>(n_prob + 1);
-  double* d_poses = bp.take<double>(12 * (size_t)n_vert);
   uint8_t* d_fixed = bp.take<uint8_t>(n_vert);
   int32_t* d_eo = bp.take<int32_t>(n_edges);
   int32_t* d_ec = bp.take<int32_t>(n_edges);
@@ -1305,17 +1338,17 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
   double* d_p = bp.take<double>(3 * (size_t)n_edges);
   double* d_uv = bp.take<double>(2 * (size_t)n_edges);
   double* d_info = bp.take<double>(4 * (size_t)n_edges);
-  uint8_t* d_inl = bp.take<uint8_t>(n_edges);
   int32_t* d_its = bp.take<int32_t>(n_rounds);
+  double* d_poses = bp.take<double>(12 * (size_t)n_vert);        // the in/out arrays and the statistics last: they come back as one block
+  uint8_t* d_inl = bp.take<uint8_t>(n_edges);
   int32_t* d_st = bp.take<int32_t>(3 * (size_t)n_prob);
-#define H2D(dst, src, n) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyHostToDevice, s))
-  H2D(d_pv, prob_vert, (n_prob + 1) * 4); H2D(d_pe, prob_edge, (n_prob + 1) * 4);
-  H2D(d_poses, poses, 12 * (size_t)n_vert * 8); H2D(d_fixed, fixed, n_vert);
-  H2D(d_eo, e_obj, (size_t)n_edges * 4); H2D(d_ec, e_cam, (size_t)n_edges * 4);
-  H2D(d_k, cam_k, 4 * (size_t)n_edges * 8); H2D(d_p, p, 3 * (size_t)n_edges * 8);
-  H2D(d_uv, uv, 2 * (size_t)n_edges * 8); H2D(d_info, info, 4 * (size_t)n_edges * 8);
-  H2D(d_inl, inliers, n_edges); H2D(d_its, its, n_rounds * 4);
-#undef H2D
+  Stage st(x->io);
+  st.in(d_pv, prob_vert, (size_t)n_prob + 1); st.in(d_pe, prob_edge, (size_t)n_prob + 1);
+  st.in(d_fixed, fixed, (size_t)n_vert); st.in(d_eo, e_obj, (size_t)n_edges); st.in(d_ec, e_cam, (size_t)n_edges);
+  st.in(d_k, cam_k, 4 * (size_t)n_edges); st.in(d_p, p, 3 * (size_t)n_edges); st.in(d_uv, uv, 2 * (size_t)n_edges);
+  st.in(d_info, info, 4 * (size_t)n_edges); st.in(d_its, its, (size_t)n_rounds);
+  st.in(d_poses, static_cast<const double*>(poses), 12 * (size_t)n_vert); st.in(d_inl, static_cast<const uint8_t*>(inliers), (size_t)n_edges);
+  SUO_CUDA_TRY(ctx, st.send(s));
   if (global)   // coupled camera+object graph (global BA) or a graph too large for the shared-memory kernel
     rc = run_ba_global(ctx, n_prob, prob_vert, prob_edge, fixed, n_vert, e_obj, e_cam, n_edges,
                        base_args(d_pv, d_pe, d_poses, d_fixed, d_eo, d_ec, d_k, d_p, d_uv, d_info, d_inl, d_its, d_st), s);
@@ -1324,10 +1357,10 @@ int suo_ba_batch(suo_ctx* ctx, int n_prob, const int32_t* prob_vert, const int32
                                  n_rounds, huber_delta, chi2_gate, init_with_outliers, d_st, d_err, d_level, d_fv, s, nullptr, nullptr,
                                  ba_single_vertex(n_prob, prob_vert, fixed));
   if (rc) return rc;
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(poses, d_poses, 12 * (size_t)n_vert * 8, cudaMemcpyDeviceToHost, s));
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(inliers, d_inl, n_edges, cudaMemcpyDeviceToHost, s));
-  if (stats) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(stats, d_st, 3 * (size_t)n_prob * 4, cudaMemcpyDeviceToHost, s));
+  st.want(d_poses, 12 * (size_t)n_vert); st.want(d_inl, (size_t)n_edges); st.want(d_st, 3 * (size_t)n_prob);
+  SUO_CUDA_TRY(ctx, st.fetch(s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  st.out(poses, d_poses, 12 * (size_t)n_vert); st.out(inliers, d_inl, (size_t)n_edges); st.out(stats, d_st, 3 * (size_t)n_prob);
   return SUO_OK;
 }
 
@@ -1685,6 +1718,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   const size_t out_bytes = (size_t)L * (128 + 72 + 96 + 1 + 1 + 8 + 4) + LK * (1 + 1 + 8 + 16 + 8 + 1) + 96 + 32 + 32 * 256;
   const size_t work_bytes = (size_t)L * (72 + 4 + 20) + LK * (24 + 16 + 4 + 4 + 4 + 4 + 32 + 24 + 16 + 32 + 1 + 4 + 16 + 1 + 1) + 4096 + 48 * 256;
   rc = x->fr.grow(ctx, in_bytes + out_bytes + work_bytes);
+  if (!rc && !on_device) rc = x->fr.mirror(ctx, in_bytes + out_bytes);       // (inputs and outputs come first in the block)
   if (rc) return rc;
   rc = ensure_pnp_tables(ctx, L, s);
   if (rc) return rc;
@@ -1694,9 +1728,14 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   const double* d_diam = diameter; const uint8_t* d_mv = map_valid; const double* d_To = T_OtoG;
   const int32_t* d_hc = hist_crop; const double* d_hT = hist_T_GtoC; const double* d_hK = hist_K; const int32_t* d_ho = hist_off;
   const double* d_hm = hist_model_kp; const float* d_hu = hist_uv; const float* d_hcv = hist_cov;
+  Stage stg(x->fr);
   if (!on_device) {
-#define STAGE(T, dst, src, n) T* dst##_ = bp.take<T>(n); SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst##_, src, (n) * sizeof(T), cudaMemcpyHostToDevice, s)); dst = dst##_;
-    STAGE(uint8_t, d_im, image_hwc, n_im) STAGE(double, d_Kc, K_cam, 9) STAGE(float, d_box, boxes, 4 * (size_t)L) STAGE(double, d_mk, model_kps, 3 * LK)
+    // the frame goes straight from the caller's buffer (0.9 MB: one copy either way); the ~15 small arrays through the pinned mirror
+    uint8_t* im_ = bp.take<uint8_t>(n_im);
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(im_, image_hwc, n_im, cudaMemcpyHostToDevice, s));
+    d_im = im_;
+#define STAGE(T, dst, src, n) { T* dst##_ = bp.take<T>(n); stg.in(dst##_, src, n); dst = dst##_; }
+    STAGE(double, d_Kc, K_cam, 9) STAGE(float, d_box, boxes, 4 * (size_t)L) STAGE(double, d_mk, model_kps, 3 * LK)
     STAGE(uint8_t, d_mm, model_mask, LK) STAGE(double, d_diam, diameter, (size_t)L) STAGE(uint8_t, d_mv, map_valid, (size_t)L) STAGE(double, d_To, T_OtoG, 12 * (size_t)L)
     if (n_hist > 0) {
       STAGE(int32_t, d_hc, hist_crop, (size_t)n_hist) STAGE(double, d_hT, hist_T_GtoC, 12 * (size_t)n_hist) STAGE(double, d_hK, hist_K, 9 * (size_t)n_hist)
@@ -1704,6 +1743,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
       if (hist_cov) { STAGE(float, d_hcv, hist_cov, 4 * NH) }
     }
 #undef STAGE
+    SUO_CUDA_TRY(ctx, stg.send(s));
   }
   // ---- outputs (device side) ----
 #define OUT(T, name, user, n) T* name = (on_device && user) ? user : bp.take<T>(n);
@@ -1768,12 +1808,13 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   if (rc) return rc;
   rc = launch_slam_ba_scatter(ctx, L, K, b_ec, b_src, b_inl, b_poses, b_st, o_cam, o_bain, o_st, s);
   if (rc || on_device) return rc;
-#define D2H(dst, src, n) if (dst) SUO_CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, (n), cudaMemcpyDeviceToHost, s))
-  D2H(T_GtoC, o_cam, 96); D2H(status, o_st, 32); D2H(T_pnp, o_Tpnp, 128 * (size_t)L); D2H(kp_used, o_used, LK); D2H(ba_inliers, o_bain, LK);
-  D2H(uv, o_uv, 8 * LK); D2H(cov, o_cov, 16 * LK); D2H(prior_uv, o_puv, 8 * LK); D2H(prior_mask, o_pm, LK); D2H(K_bbox, o_kb, 72 * (size_t)L);
-  D2H(T_OtoG_out, o_To, 96 * (size_t)L); D2H(map_valid_out, o_mv, (size_t)L); D2H(reinit, o_ri, (size_t)L); D2H(reinit_counts, o_rc, 8 * (size_t)L);
-#undef D2H
+  // the outputs were taken back to back from the block: one copy into the pinned mirror, then memcpy into the caller's arrays
+  stg.want(o_cam, 12); stg.want(o_rc, 2 * (size_t)L);
+  SUO_CUDA_TRY(ctx, stg.fetch(s));
   SUO_CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  stg.out(T_GtoC, o_cam, 12); stg.out(status, o_st, 8); stg.out(T_pnp, o_Tpnp, 16 * (size_t)L); stg.out(kp_used, o_used, LK); stg.out(ba_inliers, o_bain, LK);
+  stg.out(uv, o_uv, 2 * LK); stg.out(cov, o_cov, 4 * LK); stg.out(prior_uv, o_puv, 2 * LK); stg.out(prior_mask, o_pm, LK); stg.out(K_bbox, o_kb, 9 * (size_t)L);
+  stg.out(T_OtoG_out, o_To, 12 * (size_t)L); stg.out(map_valid_out, o_mv, (size_t)L); stg.out(reinit, o_ri, (size_t)L); stg.out(reinit_counts, o_rc, 2 * (size_t)L);
   return suo_check_range(ctx);
 }
 
