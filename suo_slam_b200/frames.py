@@ -59,6 +59,78 @@ class FramePipeline:
         out["ba_inliers"] = out["ba_inliers"].astype(bool)
         return out
 
+    def stream(self, batches, run_ba=True):
+        """Generator: ``for out in pipe.stream(batches)`` yields, in order, what ``run(**batch)`` returns for every batch of an
+        iterable of dicts (keys: images [n_img,H,W,3] uint8, boxes, box_img, model_kps, model_mask, K_bbox, diameter; no priors).
+        Double-buffered through ``suo_frames_u8_submit`` / ``suo_frames_wait``: the batch is packed into the slot's pinned staging
+        tensors and submitted, and while it runs the frames of the next batch are already crossing PCIe; a result is yielded when
+        its slot is needed again (two batches later) or the input ends."""
+        import torch
+        ctx, lib, p = self.model.context(), _lib.lib(), _lib.ptr
+        stream = torch.cuda.current_stream().cuda_stream
+        slots = [dict(pending=False, bufs={}) for _ in range(2)]
+
+        def pinned(sl, name, shape, dtype):
+            t = sl["bufs"].get(name)
+            n = int(np.prod(shape))
+            if t is None or t.dtype != dtype or t.numel() < n:
+                t = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+                sl["bufs"][name] = t
+            return t[:n].view(*shape)
+
+        def finish(sl):
+            ctx.check(lib.suo_frames_wait(ctx.handle, sl["slot"]))
+            sl["pending"] = False
+            o, (L, K) = sl["out"], sl["LK"]
+            return dict(T_pnp=o["T_pnp"].numpy().reshape(L, 4, 4).copy(), T_ba=o["T_ba"].numpy().reshape(L, 3, 4).copy(),
+                        kp_used=o["used"].numpy().astype(bool), ba_inliers=o["bain"].numpy().astype(bool),
+                        uv=o["uv"].numpy().copy(), cov=o["cov"].numpy().reshape(L, K, 2, 2).copy())
+
+        try:
+            for i, b in enumerate(batches):
+                sl = slots[i % 2]
+                sl["slot"] = i % 2
+                if sl["pending"]:
+                    yield finish(sl)
+                images = b["images"]
+                if not str(images.dtype).endswith("uint8"):
+                    raise ValueError("FramePipeline.stream takes uint8 [n_img,H,W,3] frames")
+                n_img, H, W, _ = images.shape
+                L, K = b["model_mask"].shape
+                if L == 0:
+                    raise ValueError("FramePipeline.stream: a batch without crops (use run())")
+                ins = {}
+                for name, a, dt, tdt in (("images", images, np.uint8, torch.uint8), ("boxes", b["boxes"], np.float32, torch.float32),
+                                         ("box_img", b["box_img"], np.int32, torch.int32), ("model_kps", b["model_kps"], np.float64, torch.float64),
+                                         ("model_mask", b["model_mask"], np.uint8, torch.uint8), ("K_bbox", b["K_bbox"], np.float64, torch.float64),
+                                         ("diameter", b["diameter"], np.float64, torch.float64)):
+                    a = np.ascontiguousarray(a.numpy() if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray) else a, dtype=dt)
+                    t = pinned(sl, name, a.shape, tdt)
+                    t.numpy()[...] = a
+                    ins[name] = t
+                o = dict(T_pnp=pinned(sl, "T_pnp", (L, 16), torch.float64), T_ba=pinned(sl, "T_ba", (L, 12), torch.float64),
+                         used=pinned(sl, "used", (L, K), torch.uint8), bain=pinned(sl, "bain", (L, K), torch.uint8),
+                         uv=pinned(sl, "uv", (L, K, 2), torch.float32), cov=pinned(sl, "cov", (L, K, 4), torch.float32))
+                if not run_ba:
+                    o["T_ba"].zero_(); o["bain"].zero_()
+                sl["out"], sl["LK"] = o, (L, K)
+                ctx.check(lib.suo_frames_u8_submit(
+                    ctx.handle, sl["slot"], p(ins["images"]), n_img, H, W, p(ins["boxes"]), p(ins["box_img"]), L, p(ins["model_kps"]),
+                    p(ins["model_mask"]), p(ins["K_bbox"]), p(ins["diameter"]), float(self.kp_var_thresh), float(self.bbox_thresh),
+                    int(self.seed), int(run_ba), p(o["T_pnp"]), p(o["T_ba"]), p(o["used"]), p(o["bain"]), p(o["uv"]), p(o["cov"]),
+                    None, 0, stream))
+                sl["pending"] = True
+                last = i
+            if any(s_["pending"] for s_ in slots):
+                for sl in (slots[(last + 1) % 2], slots[last % 2]):      # oldest first
+                    if sl["pending"]:
+                        yield finish(sl)
+        finally:
+            for sl in slots:                                              # a consumer that stops early must not leave a slot pending
+                if sl["pending"]:
+                    lib.suo_frames_wait(ctx.handle, sl["slot"])
+                    sl["pending"] = False
+
 
 def solve_keypoints(ctx, uv, cov, kp_mask, box_img, model_kps, model_mask, K_bbox, diameter, kp_var_thresh=0.2,
                     bbox_thresh=0.9, seed=0, run_ba=True):

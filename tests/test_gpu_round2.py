@@ -307,6 +307,29 @@ def test_asynchronous_frame_batches_equal_the_synchronous_call(marker_model):
         assert recs[i].cpu().numpy().tobytes() == host.tobytes()
 
 
+def test_frame_pipeline_stream_equals_run(marker_model):
+    """FramePipeline.stream (the Python face of suo_frames_u8_submit / suo_frames_wait) yields, in order, exactly what run() returns
+    batch by batch — for an odd and an even number of batches, a batch size that changes, and a consumer that stops early."""
+    pipe = frames.FramePipeline(marker_model)
+    batches = [_marker_batch(2600 + 10 * i, 1 + i % 2) for i in range(5)]
+    keys = ("img", "boxes", "bi", "mk", "mm", "kb", "diam")
+    names = ("images", "boxes", "box_img", "model_kps", "model_mask", "K_bbox", "diameter")
+    as_kw = lambda b: {n: b[k] for n, k in zip(names, keys)}
+    want = [pipe.run(**as_kw(b)) for b in batches]
+    for n in (5, 4, 1):
+        got = list(pipe.stream(as_kw(b) for b in batches[:n]))
+        assert len(got) == n
+        for g, w in zip(got, want):
+            for k in w:
+                assert np.array_equal(g[k], w[k]), k
+    it = pipe.stream(as_kw(b) for b in batches)
+    first = next(it)
+    it.close()                                         # two batches are in flight: the generator's cleanup waits for them
+    assert np.array_equal(first["T_ba"], want[0]["T_ba"])
+    again = pipe.run(**as_kw(batches[0]))              # the context is usable (no slot left pending)
+    assert np.array_equal(again["T_pnp"], want[0]["T_pnp"])
+
+
 def test_g2o_dropin_chi2_is_the_error_the_kernel_left_in_the_edges():
     """ObjectSLAM.optimize() re-reads e.chi2() of inlier edges WITHOUT recomputing (lib/object_slam.py:881-883), so after a rejected LM
     trial it classifies with the rejected state's error.  The g2o drop-in copies the kernel's leftover errors into the edges
