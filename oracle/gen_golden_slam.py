@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/slam_seq.npz by running the UNMODIFIED reference class
+``lib.object_slam.ObjectSLAM`` (process_view in SLAM mode: the two __process_objects passes, __estimate_camera_pose,
+__maybe_reinit_objects, optimize(curr_only=True) with its rounds / chi2 gate / Huber strip — lib/object_slam.py:327-930,975-1072)
+on synthetic marker sequences, in THIS container (CPU; /root/reference is not on the GPU box, hence the committed fixture).
+
+What is the reference's and what is substituted:
+  * reference, unmodified: lib/object_slam.py (all control flow, gating, map bookkeeping, the optimize() loop), lib/models/pkpnet.py (the
+    network, torch CPU), lib/utils/utils.py (fix_K_for_bbox_ndc, make_prior_kp_input, invert_SE3, ...), lib/labeling/kp_config.py;
+  * the two native extension modules the reference imports and that cannot be built here (no Eigen / Ceres / SuiteSparse):
+      - ``lambdatwist``  -> oracle/geom.py lambdatwist_pnp (RANSAC + refine restatement; its P3P/P4P core is checked against the reference's
+                            own p4p.cpp compiled in place, tests/test_oracle_geom.py).  The RANSAC stream is keyed by the crop's position in
+                            the non-symmetric-first processing order (what the device kernels and oracle/slam_frame_oracle.py use); the shim
+                            recovers that position from the model keypoints it is handed.
+      - ``g2o``          -> suo_slam_b200/g2o.py container classes (the product's drop-in: vertices, edges, SparseOptimizer) with the LM solve
+                            routed to oracle/geom.py ba_optimize_err instead of the GPU — so the fixture also proves that the LITERAL reference
+                            optimize() runs on the drop-in's class surface;
+  * stubbed: thirdparty.bop_toolkit...renderer_py (needs glumpy; visualisation only), matplotlib (oracle/ref_shims.py).
+
+The fixture pins oracle/slam_frame_oracle.py + oracle/slam_oracle.py (tests/test_marker_cpu.py) and, through them and directly, the GPU path
+(tests/test_gpu_slam.py).
+
+    python -m oracle.gen_golden_slam        # ~1-2 min on 8 cores
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import geom, ref_shims  # noqa: E402
+from suo_slam_b200 import synth  # noqa: E402
+
+SEED = 0                     # RANSAC seed (slam_frame_oracle.process_view's default)
+
+
+class _CpuBa:
+    """Stands in for suo_slam_b200.ba inside the g2o drop-in: the same call, solved by the CPU oracle."""
+
+    @staticmethod
+    def ba_batch(prob_vert, prob_edge, poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, huber_delta, chi2_gate,
+                 init_with_outliers, return_errors=True):
+        assert list(prob_vert) == [0, len(poses)] and return_errors
+        P, inl, st, err = geom.ba_optimize_err(poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, huber_delta=huber_delta,
+                                               chi2_gate=chi2_gate, init_with_outliers=init_with_outliers)
+        return P, inl, np.array([[st["rounds"], st["outer"], st["trials"]]], np.int32), err
+
+
+class _PnpShim:
+    """lambdatwist.pnp(xs, ys, threshold) -> 4x4 (identity on failure).  `crops` = [(model_kps [K,3], key)] of the view being processed."""
+
+    def __init__(self):
+        self.crops = []
+        self.calls = []
+
+    def pnp(self, xs_in, ys_in, threshold=0.001):
+        xs_in = np.asarray(xs_in, np.float64)
+        key = [k for mk, k in self.crops if (mk == xs_in[0]).all(-1).any()]
+        assert len(key) == 1, "cannot tell which crop this pnp() call belongs to"
+        self.calls.append(key[0])
+        T, _ = geom.lambdatwist_pnp(xs_in, np.asarray(ys_in, np.float64), threshold, seed=SEED, obj_key=key[0])
+        return np.eye(4) if T is None else T
+
+
+def install():
+    ref_shims.install()
+    for name in ("thirdparty", "thirdparty.bop_toolkit", "thirdparty.bop_toolkit.bop_toolkit_lib", "thirdparty.bop_toolkit.bop_toolkit_lib.renderer_py"):
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    sys.modules["thirdparty.bop_toolkit.bop_toolkit_lib.renderer_py"].RendererPython = object
+    shim = _PnpShim()
+    lt = types.ModuleType("lambdatwist")
+    lt.pnp = shim.pnp
+    sys.modules["lambdatwist"] = lt
+    import suo_slam_b200.g2o as g2o_mod
+    g2o_mod._ba = _CpuBa
+    sys.modules["g2o"] = g2o_mod
+    torch.serialization.add_safe_globals([argparse.Namespace])
+    import importlib
+    return importlib.import_module("lib.object_slam"), shim
+
+
+def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, **kw):
+    objs = seq["objs"]
+    mesh_db = {o["obj_id"]: dict(is_symmetric=bool(o["is_symmetric"]), diameter=float(o["diameter"])) for o in objs}
+    with contextlib.redirect_stdout(io.StringIO()):
+        slam = osl_mod.ObjectSLAM(ckpt, mesh_db, **kw)
+    # ObjectSLAM builds PkpNet() with its default input_res whatever pred_res says (lib/object_slam.py:95 vs :1080): give the network the
+    # resolution the priors are made for — an attribute of the reference object, not a code change
+    slam.model.input_res = tuple(kw.get("pred_res", (256, 256)))
+    out = {}
+    is_sym = np.array([o["is_symmetric"] for o in objs])
+    order = np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]])
+    for i, v in enumerate(seq["views"][:n_views]):
+        shim.crops = [(objs[c]["model_kps"], pos) for pos, c in enumerate(order)]
+        shim.calls = []
+        obj_ids = np.array([d["obj_id"] for d in v["dets"]])
+        bboxes = np.stack([d["bbox"] for d in v["dets"]]).astype(np.float32)
+        mk, mm = np.stack([o["model_kps"] for o in objs]), np.stack([o["model_kps_mask"] for o in objs])
+        with contextlib.redirect_stdout(io.StringIO()):
+            slam.process_view(v["view_id"], v["img"], seq["K"], obj_ids, bboxes.copy(), mk, mm, mm.copy())
+        vid = v["view_id"]
+        assert vid in slam.cam_poses, "the reference lost the camera"
+        out[f"v{i}_cam"] = np.asarray(slam.cam_poses[vid], np.float64)[:3]
+        out[f"v{i}_pnp_keys"] = np.asarray(shim.calls, np.int32)
+        out[f"v{i}_obj_ids"] = np.array(sorted(slam.obj_poses), np.int32)
+        out[f"v{i}_obj_poses"] = np.stack([np.asarray(slam.obj_poses[o], np.float64)[:3] for o in sorted(slam.obj_poses)])
+        for o, d in slam.detections[vid].items():
+            out[f"v{i}_det{o}_kp_mask"] = d["kp_mask"].astype(np.uint8)
+            out[f"v{i}_det{o}_inliers"] = np.asarray(d["inliers"]).astype(np.uint8)
+            out[f"v{i}_det{o}_uv"] = d["uv_pred"].astype(np.float64)
+            out[f"v{i}_det{o}_cov"] = d["cov_pred"].astype(np.float32)
+            out[f"v{i}_det{o}_pose"] = np.zeros((0, 4)) if d["pose"] is None else np.asarray(d["pose"], np.float64)[:3]
+            out[f"v{i}_det{o}_prior_uv"] = np.zeros((0, 2), np.float32) if d["prior_uv"] is None else d["prior_uv"]
+        if corrupt_after_first is not None and i == 0:
+            T = np.array(slam.obj_poses[corrupt_after_first], np.float64)
+            T[:3, 3] += [70.0, -50.0, 40.0]
+            slam.obj_poses[corrupt_after_first] = T
+    return out
+
+
+def main():
+    torch.manual_seed(0)
+    osl_mod, shim = install()
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    ckpt = os.path.join(ROOT, "build", "marker_ckpt.pth.tar")
+    torch.save({"model": synth.make_marker_state_dict(0), "epoch": 0, "args": argparse.Namespace(synthetic=True)}, ckpt)
+    fix = {}
+    # (a) 4 views, 6 objects (3 symmetric), YCBV thresholds (evaluate.py:58-66): the scenario of tests/test_gpu_slam.py
+    seq = synth.make_slam_sequence(3, n_views=4, n_obj=6)
+    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 4).items():
+        fix["clean_" + k] = a
+    # (b) the same sequence with object 13's map pose pushed away after the first view: the vote must reject it, the re-initialisation
+    #     test must replace it from the PnP result (lib/object_slam.py:595-697)
+    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 3, corrupt_after_first=13).items():
+        fix["corrupt_" + k] = a
+    # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
+    seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
+    tl = dict(pred_res=(512, 512), kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, opt_init_with_outliers=True)
+    for k, a in run_sequence(osl_mod, shim, ckpt, seq5, 2, **tl).items():
+        fix["c5_" + k] = a
+    os.remove(ckpt)
+    path = os.path.join(ROOT, "tests", "golden", "slam_seq.npz")
+    np.savez_compressed(path, **fix)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(fix), "arrays")
+    for s in ("clean", "corrupt", "c5"):
+        n = len([k for k in fix if k.startswith(s + "_v") and k.endswith("_cam")])
+        print(s, "views", n, "objects in the map at the end", fix[f"{s}_v{n - 1}_obj_ids"].tolist(), "pnp keys of the last view", fix[f"{s}_v{n - 1}_pnp_keys"].tolist())
+
+
+if __name__ == "__main__":
+    main()

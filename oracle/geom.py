@@ -40,6 +40,8 @@ def lib():
         L.orc_pnp_refine.argtypes = [_dp, _dp, C.c_int, C.c_double, _dp, _ip]
         L.orc_ba_optimize.argtypes = [C.c_int, _dp, _bp, C.c_int, _ip, _ip, _dp, _dp, _dp, _dp, _bp, _ip, C.c_int,
                                       C.c_double, C.c_double, C.c_int, _ip]
+        L.orc_ba_optimize_err.argtypes = L.orc_ba_optimize.argtypes + [_dp]
+        L.orc_ba_optimize_err.restype = None
         L.orc_edge_eval.argtypes = [_dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.orc_se3_oplus.argtypes = [_dp, _dp, _dp]
         _LIB = L
@@ -130,6 +132,20 @@ def ba_optimize(poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, hu
                           _c(info).reshape(-1, 4), inl, its, len(its), float(huber_delta), float(chi2_gate),
                           int(init_with_outliers), stats)
     return poses.reshape(-1, 3, 4), inl.astype(bool), dict(rounds=int(stats[0]), outer=int(stats[1]), trials=int(stats[2]))
+
+
+def ba_optimize_err(poses, fixed, e_obj, e_cam, cam_k, p, uv, info, inliers, its, huber_delta=np.sqrt(5.991),
+                    chi2_gate=5.991, init_with_outliers=False):
+    """ba_optimize that also returns the error vector every edge is left holding (orc_ba_optimize_err): what e.chi2() reads next."""
+    poses = _c(poses).reshape(-1, 12).copy()
+    inl = _c(inliers, np.uint8).copy()
+    stats = np.zeros(3, np.int32)
+    its = _c(its, np.int32)
+    err = np.zeros((len(e_cam), 2))
+    lib().orc_ba_optimize_err(len(poses), poses, _c(fixed, np.uint8), len(e_cam), _c(e_obj, np.int32), _c(e_cam, np.int32),
+                              _c(cam_k).reshape(-1, 4), _c(p).reshape(-1, 3), _c(uv).reshape(-1, 2), _c(info).reshape(-1, 4), inl, its,
+                              len(its), float(huber_delta), float(chi2_gate), int(init_with_outliers), stats, err)
+    return poses.reshape(-1, 3, 4), inl.astype(bool), dict(rounds=int(stats[0]), outer=int(stats[1]), trials=int(stats[2])), err
 
 
 def edge_eval(T_obj, T_cam, cam_k, p, uv):

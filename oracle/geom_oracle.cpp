@@ -869,10 +869,25 @@ void orc_pnp_refine(const double* xs, const double* ys, int n, double threshold,
 //  inliers    n_edges in/out (detections[...]["inliers"])
 //  its        iterations per round (n_rounds entries)
 //  stats      [rounds_run, total_outer_iterations, total_lm_trials]
+//  err_out    (orc_ba_optimize_err) 2 * n_edges: the error vector each edge holds when optimize() returns — for an edge of the active set
+//             after a rejected LM trial that is the REJECTED state's error (g2o computes the trial's errors into the edges and pops only
+//             the vertices, optimization_algorithm_levenberg.cpp:118-146), which ObjectSLAM.optimize() then reads through e.chi2()
+//             without recomputing (lib/object_slam.py:881-883)
+void orc_ba_optimize_err(int n_vert, double* poses, const uint8_t* fixed, int n_edges, const int* e_obj, const int* e_cam,
+                         const double* cam_k, const double* p, const double* uv, const double* info, uint8_t* inliers,
+                         const int* its, int n_rounds, double huber_delta, double chi2_gate, int init_with_outliers,
+                         int* stats, double* err_out);
 void orc_ba_optimize(int n_vert, double* poses, const uint8_t* fixed, int n_edges, const int* e_obj, const int* e_cam,
                      const double* cam_k, const double* p, const double* uv, const double* info, uint8_t* inliers,
                      const int* its, int n_rounds, double huber_delta, double chi2_gate, int init_with_outliers,
                      int* stats) {
+  orc_ba_optimize_err(n_vert, poses, fixed, n_edges, e_obj, e_cam, cam_k, p, uv, info, inliers, its, n_rounds, huber_delta, chi2_gate,
+                      init_with_outliers, stats, nullptr);
+}
+void orc_ba_optimize_err(int n_vert, double* poses, const uint8_t* fixed, int n_edges, const int* e_obj, const int* e_cam,
+                         const double* cam_k, const double* p, const double* uv, const double* info, uint8_t* inliers,
+                         const int* its, int n_rounds, double huber_delta, double chi2_gate, int init_with_outliers,
+                         int* stats, double* err_out) {
   Graph G;
   G.n_vert = n_vert; G.n_edges = n_edges;
   G.e_obj = e_obj; G.e_cam = e_cam; G.cam_k = cam_k; G.p = p; G.uv = uv; G.info = info;
@@ -913,6 +928,7 @@ void orc_ba_optimize(int n_vert, double* poses, const uint8_t* fixed, int n_edge
     for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) T[4 * r + c] = R(r, c); T[4 * r + 3] = G.est[v].t[r]; }
   }
   if (stats) { stats[0] = rounds; stats[1] = outer; stats[2] = trials; }
+  if (err_out) std::copy(G.err.begin(), G.err.end(), err_out);
 }
 
 // Edge residual + analytic Jacobians for one binary edge (finite-difference checks in tests).

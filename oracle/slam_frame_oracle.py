@@ -3,8 +3,11 @@ lib/object_slam.py:327-451) restated on the CPU over the other oracles: network 
 (prior_oracle), PnP and the curr_only LM (geom), camera-pose vote and re-initialisation test (slam_oracle).  Only tests/, smoke()
 and bench.py's CPU legs may import this; the product path never does.
 
-"parity unpinned": lib/object_slam.py cannot be imported here (needs g2o / lambdatwist / glumpy) and no reference
-test covers process_view; the flow follows the cited lines.  Not restated (bookkeeping outside the hot path):
+Pinned: tests/golden/slam_seq.npz holds the state the UNMODIFIED reference class reaches (lib/object_slam.py imported from /root/reference by
+oracle/gen_golden_slam.py: reference control flow, reference network, reference utils; its two native extension modules replaced by the oracle's
+PnP / LM) on three marker sequences — 4 views clean, 3 views with a corrupted map pose (vote rejection + re-initialisation), 2 views at 512x512
+with the T-LESS thresholds; tests/test_marker_cpu.py replays them here: gating, chi2 classifications, re-init decisions identical, keypoints 1e-5,
+poses 1e-6 of the scene scale.  Not restated (bookkeeping outside the hot path; none of it triggers on those sequences):
 __backup_estimate_camera_pose (:933-973, bbox-centroid PnP when no non-symmetric object is in view), the removal of objects with
 too few inliers (:913-930) and the periodic global optimisation (:443-451; csrc/ba_global.cu has its own parity tests)."""
 from __future__ import annotations

@@ -2,9 +2,11 @@
 frame: ObjectSLAM.__estimate_camera_pose (reference lib/object_slam.py:975-1072) and
 __maybe_reinit_objects (:595-697).  Only tests/ may import this; the product path never does.
 
-"parity unpinned": lib/object_slam.py cannot be imported here (it needs g2o / lambdatwist / glumpy) and
-the reference has no test or golden vector for these two methods; the restatement follows the cited lines, including
-the float32 staging of poses and np.linalg.inv on the float32 covariances."""
+Pinned through oracle/slam_frame_oracle.py: tests/golden/slam_seq.npz holds what the UNMODIFIED reference class reaches on marker sequences
+(oracle/gen_golden_slam.py imports lib/object_slam.py with its two native extension modules replaced by the oracle's PnP / LM); one of the
+sequences corrupts a map pose so that the vote has to reject an object and __maybe_reinit_objects has to replace it — the restatement takes
+the same decisions and reaches the same poses (tests/test_marker_cpu.py).  It follows the cited lines, including the float32 staging of
+poses and np.linalg.inv on the float32 covariances."""
 from __future__ import annotations
 
 import numpy as np

@@ -1,6 +1,8 @@
 """CPU: the synthetic fiducial ("marker") network and frames that make the frame path do real solver work
 (suo_slam_b200/synth.py), checked through the CPU oracle; and the reference's own PnP Monte-Carlo assertion
 (thirdparty/lambdatwist/test_pnp.cpp:68-147) on the oracle's RANSAC + refine restatement."""
+import os
+
 import numpy as np
 import torch
 
@@ -79,22 +81,82 @@ def test_oracle_pnp_passes_the_reference_monte_carlo_assertion():
         assert (np.array(errs) > 0.05).mean() < 0.05, (sigma, (np.array(errs) > 0.05).mean())
 
 
-def test_slam_frame_oracle_tracks_a_marker_sequence():
+def _slam_args(seq, v):
+    objs = seq["objs"]
+    return (v["view_id"], v["img"], seq["K"], [d["obj_id"] for d in v["dets"]], np.stack([d["bbox"] for d in v["dets"]]),
+            np.stack([o["model_kps"] for o in objs]), np.stack([o["model_kps_mask"] for o in objs]),
+            np.array([o["is_symmetric"] for o in objs]), np.array([o["diameter"] for o in objs]))
+
+
+def _check_view_against_reference(G, name, i, st, vid, ret):
+    """One view of oracle/slam_frame_oracle.py against what the UNMODIFIED reference ObjectSLAM.process_view left in its state
+    (tests/golden/slam_seq.npz, made by oracle/gen_golden_slam.py).  Gating and chi2 classification: identical.  Keypoints: the functional
+    network restatement against the reference's nn.Module, 1e-5.  Poses: 1e-6 of the scene scale — the residue is utils.fix_K_for_bbox_ndc on a float32
+    bbox (lib/utils/utils.py:416-429: ``x2 - x1`` and, from NumPy 2 on, ``2.0 / w`` stay float32), which the restatement does in float64."""
+    # (rotation entries to 1e-6, translations to 1e-3 mm in a scene ~1 m across: 1e-6 of the scale; the first camera IS the world frame,
+    # so a relative error of its own near-zero translation would say nothing)
+    rel = lambda a, b: max(float(np.abs(np.asarray(a)[:3, :3] - b[:3, :3]).max()), 1e-3 * float(np.abs(np.asarray(a)[:3, 3] - b[:3, 3]).max()))
+    assert rel(st.cam_poses[vid], G[f"{name}_v{i}_cam"]) < 1e-6
+    ids = G[f"{name}_v{i}_obj_ids"].tolist()
+    assert sorted(st.obj_poses) == ids
+    for j, o in enumerate(ids):
+        assert rel(st.obj_poses[o], G[f"{name}_v{i}_obj_poses"][j]) < 1e-6, o
+    for o, d in st.detections[vid].items():
+        assert np.array_equal(d["kp_mask"], G[f"{name}_v{i}_det{o}_kp_mask"].astype(bool)), o
+        assert np.array_equal(np.asarray(d["inliers"]).astype(bool), G[f"{name}_v{i}_det{o}_inliers"].astype(bool)), o
+        np.testing.assert_allclose(d["uv_pred"], G[f"{name}_v{i}_det{o}_uv"], atol=1e-5)
+        np.testing.assert_allclose(d["cov_pred"], G[f"{name}_v{i}_det{o}_cov"], rtol=1e-3, atol=1e-7)
+        gp, gu = G[f"{name}_v{i}_det{o}_pose"], G[f"{name}_v{i}_det{o}_prior_uv"]
+        assert (d["pose"] is None) == (gp.shape[0] == 0) and (d["prior_uv"] is None) == (gu.shape[0] == 0), o
+        if d["pose"] is not None:
+            assert rel(d["pose"], gp) < 1e-6, o
+        if d["prior_uv"] is not None:
+            np.testing.assert_allclose(d["prior_uv"], gu, atol=1e-5)
+    # the RANSAC streams were keyed alike: one pnp() call per crop with >= 4 gated keypoints, in processing order
+    assert G[f"{name}_v{i}_pnp_keys"].tolist() == sorted(G[f"{name}_v{i}_pnp_keys"].tolist())
+
+
+def test_slam_frame_oracle_vs_the_unmodified_reference_process_view(golden_dir):
     """The CPU restatement of ObjectSLAM.process_view in SLAM mode (two forwards per view, priors for the symmetric objects, camera-pose
-    vote, curr_only LM) recovers the ground-truth camera motion of a synthetic sequence to a few millimetres over ~1 m."""
+    vote, object initialisation, curr_only LM with its rounds) (a) reproduces, view by view, the state the UNMODIFIED reference class reaches on
+    the same marker sequence, and (b) recovers the ground-truth camera motion to a few millimetres over ~1 m."""
     from oracle import slam_frame_oracle as sfo
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
     sd = synth.make_marker_state_dict(0)
     seq = synth.make_slam_sequence(3, n_views=3, n_obj=6)
     st = sfo.State()
     objs = seq["objs"]
-    for v in seq["views"]:
-        r = sfo.process_view(st, sd, v["view_id"], v["img"], seq["K"], [d["obj_id"] for d in v["dets"]], np.stack([d["bbox"] for d in v["dets"]]),
-                             np.stack([o["model_kps"] for o in objs]), np.stack([o["model_kps_mask"] for o in objs]),
-                             np.array([o["is_symmetric"] for o in objs]), np.array([o["diameter"] for o in objs]))
+    for i, v in enumerate(seq["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq, v))
         assert r["cam_ok"] and r["reinit"] == []
+        _check_view_against_reference(G, "clean", i, st, v["view_id"], r)
         cam = st.cam_poses[v["view_id"]]
         assert np.linalg.norm(cam[:, 3] - v["T_GtoC"][:3, 3]) < 10.0 and np.abs(cam[:, :3] - v["T_GtoC"][:3, :3]).max() < 0.01
         sym_with_prior = [o["obj_id"] for o in objs if o["is_symmetric"] and st.detections[v["view_id"]][o["obj_id"]]["prior_uv"] is not None]
         assert (len(sym_with_prior) == 3) == (v["view_id"] != 100)        # priors exist once the symmetric objects are in the map
     assert len(st.obj_poses) == 6
+
+
+def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
+    """(a) One object's map pose is pushed away after the first view: the reference's camera-pose vote rejects it and __maybe_reinit_objects
+    (lib/object_slam.py:595-697) replaces it in view 1 — the restatement takes the same decisions and reaches the same state.
+    (b) 512x512 crops with the T-LESS thresholds and opt_init_with_outliers (evaluate.py:68-76), BASELINE configs[4]'s shape."""
+    from oracle import slam_frame_oracle as sfo
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    sd = synth.make_marker_state_dict(0)
+    seq = synth.make_slam_sequence(3, n_views=2, n_obj=6)
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq, v))
+        assert r["reinit"] == ([13] if i == 1 else [])
+        _check_view_against_reference(G, "corrupt", i, st, v["view_id"], r)
+        if i == 0:
+            st.obj_poses[13] = st.obj_poses[13].copy()
+            st.obj_poses[13][:3, 3] += [70.0, -50.0, 40.0]
+    seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
+    st = sfo.State()
+    for i, v in enumerate(seq5["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq5, v), res=512, kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, init_with_outliers=True)
+        _check_view_against_reference(G, "c5", i, st, v["view_id"], r)
