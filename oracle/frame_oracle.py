@@ -2,7 +2,12 @@
 PkpNet forward (oracle/net_oracle.py) -> keypoint gating (lib/object_slam.py:1100-1115) ->
 per-object pnp() (:1123-1165, oracle/geom.py) -> optimize() in single-view mode
 (:703-930: camera fixed, one vertex per object, its=[10]*4).  Used by tests/ and by
-bench.py's cpu_baseline / --impl reference legs only."""
+bench.py's cpu_baseline / --impl reference legs only.
+
+Pinned: tests/golden/slam_seq.npz ("sv_*") holds what the UNMODIFIED reference ObjectSLAM(single_view_mode=True).process_view leaves in
+its state for two marker frames with real outliers (oracle/gen_golden_slam.py: lib/object_slam.py imported from /root/reference, its two
+native extension modules replaced by oracle/geom.py's PnP / LM); tests/test_marker_cpu.py replays them here: gating, PnP acceptance and
+BA inlier sets identical, poses 1e-6 of the scene scale."""
 from __future__ import annotations
 
 import numpy as np

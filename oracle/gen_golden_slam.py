@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY — generates tests/golden/slam_seq.npz by running the UNMODIFIED reference class
 ``lib.object_slam.ObjectSLAM`` (process_view in SLAM mode: the two __process_objects passes, __estimate_camera_pose,
 __maybe_reinit_objects, optimize(curr_only=True) with its rounds / chi2 gate / Huber strip — lib/object_slam.py:327-930,975-1072)
-on synthetic marker sequences, in THIS container (CPU; /root/reference is not on the GPU box, hence the committed fixture).
+on synthetic marker sequences — and, in single_view_mode, on single marker frames (process_view + the full optimize() with the camera
+fixed, the path BASELINE configs[1] times) — in THIS container (CPU; /root/reference is not on the GPU box, hence the committed fixture).
 
 What is the reference's and what is substituted:
   * reference, unmodified: lib/object_slam.py (all control flow, gating, map bookkeeping, the optimize() loop), lib/models/pkpnet.py (the
@@ -128,6 +129,39 @@ def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, **
     return out
 
 
+def run_single_view_frames(osl_mod, shim, ckpt, seed0, n_frames, n_obj=8):
+    """single_view_mode (what evaluate.py runs for the single-view tables and what BASELINE configs[1] times): every frame on its own —
+    process_view = one __process_objects pass over all crops + the full optimize() with the camera vertex fixed and its = [10] * 4
+    (lib/object_slam.py:362-364,443-451,842-846).  RANSAC keys = the crop's index in the batch of frames, as suo_frames / frame_oracle use."""
+    out = {}
+    for f in range(n_frames):
+        fr = synth.make_marker_frame(seed0 + f, n_obj=n_obj)
+        objs = fr["objs"]
+        ids = np.arange(n_obj) + 100 * (f + 1)
+        mesh_db = {int(i): dict(is_symmetric=False, diameter=float(o["diameter"])) for i, o in zip(ids, objs)}
+        with contextlib.redirect_stdout(io.StringIO()):
+            slam = osl_mod.ObjectSLAM(ckpt, mesh_db, single_view_mode=True)
+        shim.crops = [(o["model_kps"], n_obj * f + k) for k, o in enumerate(objs)]
+        shim.calls = []
+        mk, mm = np.stack([o["model_kps"] for o in objs]), np.stack([o["model_kps_mask"] for o in objs])
+        bboxes = np.stack([o["bbox"] for o in objs]).astype(np.float32)
+        with contextlib.redirect_stdout(io.StringIO()):
+            slam.process_view(f, fr["img"], fr["K"], ids, bboxes.copy(), mk, mm, mm.copy())
+        out[f"f{f}_pnp_keys"] = np.asarray(shim.calls, np.int32)
+        out[f"f{f}_kept"] = np.array([int(i) in slam.obj_poses for i in ids], np.uint8)           # (objects optimize() did not remove, :899-930)
+        out[f"f{f}_T_ba"] = np.stack([np.asarray(slam.obj_poses[int(i)], np.float64)[:3] if int(i) in slam.obj_poses else np.zeros((3, 4)) for i in ids])
+        det = slam.detections[f]
+        out[f"f{f}_kp_used"] = np.stack([det[int(i)]["kp_mask"] for i in ids]).astype(np.uint8)
+        out[f"f{f}_accepted"] = np.array([det[int(i)]["pose"] is not None for i in ids], np.uint8)
+        out[f"f{f}_T_pnp"] = np.stack([np.asarray(det[int(i)]["pose"], np.float64)[:3] if det[int(i)]["pose"] is not None else np.zeros((3, 4)) for i in ids])
+        K = mm.shape[1]
+        inl = np.zeros((n_obj, K), np.uint8)
+        for k, i in enumerate(ids):
+            inl[k, det[int(i)]["kp_mask"]] = np.asarray(det[int(i)]["inliers"]).astype(np.uint8)
+        out[f"f{f}_ba_inliers"] = inl
+    return out
+
+
 def main():
     torch.manual_seed(0)
     osl_mod, shim = install()
@@ -148,10 +182,16 @@ def main():
     tl = dict(pred_res=(512, 512), kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, opt_init_with_outliers=True)
     for k, a in run_sequence(osl_mod, shim, ckpt, seq5, 2, **tl).items():
         fix["c5_" + k] = a
+    # (d) single-view mode: the two frames of tests/test_gpu_round2.py::test_pixels_to_poses (8 crops each)
+    for k, a in run_single_view_frames(osl_mod, shim, ckpt, 2000, 2).items():
+        fix["sv_" + k] = a
     os.remove(ckpt)
     path = os.path.join(ROOT, "tests", "golden", "slam_seq.npz")
     np.savez_compressed(path, **fix)
     print("wrote", path, os.path.getsize(path), "bytes,", len(fix), "arrays")
+    for f in range(2):
+        print("single view frame", f, "accepted", fix[f"sv_f{f}_accepted"].tolist(), "kept", fix[f"sv_f{f}_kept"].tolist(), "gated", fix[f"sv_f{f}_kp_used"].sum(1).tolist(),
+              "BA inliers", fix[f"sv_f{f}_ba_inliers"].sum(1).tolist())
     for s in ("clean", "corrupt", "c5"):
         n = len([k for k in fix if k.startswith(s + "_v") and k.endswith("_cam")])
         print(s, "views", n, "objects in the map at the end", fix[f"{s}_v{n - 1}_obj_ids"].tolist(), "pnp keys of the last view", fix[f"{s}_v{n - 1}_pnp_keys"].tolist())

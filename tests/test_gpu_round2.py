@@ -2,6 +2,8 @@
 range guard through the frame call, converted checkpoints, the edge Jacobians against central differences through the C
 ABI, the reference's PnP Monte-Carlo assertion (250 points), result records, the asynchronous frame batches and the g2o
 drop-in's chi2 semantics."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -47,7 +49,7 @@ def _decisive(ref_logits, got_logits):
     return (top2[..., 1] - top2[..., 0]) > 4 * err, flat.argmax(-1), err
 
 
-def test_pixels_to_poses_on_marker_frames_vs_the_cpu_oracle(marker_sd, marker_model):
+def test_pixels_to_poses_on_marker_frames_vs_the_cpu_oracle(marker_sd, marker_model, golden_dir):
     """u8 frames -> suo_frames_u8 (crop, hourglass, reduction, gating, PnP, single-view BA) against the CPU frame oracle run on the
     same pixels (torch-CPU FP32 network + FP64 solver restatements): network outputs to the conv tolerance, identical gating
     away from the thresholds, decisive hard argmax bit-exact, and poses within the north-star bar wherever both sides solved
@@ -82,6 +84,19 @@ def test_pixels_to_poses_on_marker_frames_vs_the_cpu_oracle(marker_sd, marker_mo
     assert np.median(d_ba) < 1e-4 and (d_ba < 1e-3).mean() >= 0.8      # an inlier flipping at the 1e-3 RANSAC threshold moves a pose by more
     t_err = np.array([rel(got["T_ba"][c][:, 3], b["T_gt"][c][:3, 3]) for c in np.nonzero(same)[0]])
     assert np.median(t_err) < 0.01
+    # the same two frames through the UNMODIFIED reference ObjectSLAM(single_view_mode=True) (tests/golden/slam_seq.npz "sv_*", made by
+    # oracle/gen_golden_slam.py: reference control flow + network, leaf solvers = the oracle)
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    g_used = np.concatenate([G[f"sv_f{f}_kp_used"] for f in range(2)]).astype(bool)
+    g_inl = np.concatenate([G[f"sv_f{f}_ba_inliers"] for f in range(2)]).astype(bool)
+    g_pnp, g_ba = np.concatenate([G[f"sv_f{f}_T_pnp"] for f in range(2)]), np.concatenate([G[f"sv_f{f}_T_ba"] for f in range(2)])
+    same_g = np.all(got["kp_used"] == g_used, axis=1)
+    d_pnp = np.array([rel(got["T_pnp"][c][:3], g_pnp[c]) for c in np.nonzero(same_g)[0]])
+    d_ba = np.array([rel(got["T_ba"][c], g_ba[c]) for c in np.nonzero(same_g)[0]])
+    inl_same = np.array([np.array_equal(got["ba_inliers"][c], g_inl[c]) for c in np.nonzero(same_g)[0]])
+    print(f"[marker 256 vs the reference fixture] {int(same_g.sum())} of 16 objects with identical gating: rel pose diff PnP median {np.median(d_pnp):.2e} "
+          f"max {d_pnp.max():.2e}, BA median {np.median(d_ba):.2e} max {d_ba.max():.2e}; identical BA inlier sets {int(inl_same.sum())}")
+    assert same_g.sum() >= 10 and np.median(d_ba) < 1e-4 and (d_ba < 1e-3).mean() >= 0.8 and inl_same.mean() >= 0.8
 
 
 @pytest.mark.parametrize("res", [64, 256, 512])

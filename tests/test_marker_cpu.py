@@ -138,6 +138,37 @@ def test_slam_frame_oracle_vs_the_unmodified_reference_process_view(golden_dir):
     assert len(st.obj_poses) == 6
 
 
+def test_frame_oracle_vs_the_unmodified_reference_in_single_view_mode(golden_dir):
+    """The single-view frame path (BASELINE configs[1]: model -> gating -> pnp per object -> optimize() with the camera fixed, its = [10] * 4)
+    as oracle/frame_oracle.py restates it, against the UNMODIFIED reference ObjectSLAM(single_view_mode=True).process_view on the same two
+    marker frames (tests/golden/slam_seq.npz "sv_*", oracle/gen_golden_slam.py).  The frames carry real outliers (same-colour discs of other
+    objects): 11 of the 16 objects lose 1-3 keypoints to the chi2 gate.  Gating, PnP acceptance and BA inlier sets: identical; poses: 1e-6 of
+    the scene scale (the float32 bbox arithmetic of utils.fix_K_for_bbox_ndc, see _check_view_against_reference)."""
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    sd = synth.make_marker_state_dict(0)
+    imgs, boxes, bi, mk, mm, kb, diam = [], [], [], [], [], [], []
+    for f in range(2):
+        fr = synth.make_marker_frame(2000 + f, n_obj=8)
+        bb = [o["bbox"] for o in fr["objs"]]
+        imgs.append(fr["img"]); boxes += bb; bi += [f] * 8
+        mk += [o["model_kps"] for o in fr["objs"]]; mm += [o["model_kps_mask"] for o in fr["objs"]]; diam += [o["diameter"] for o in fr["objs"]]
+        kb.append(frames.k_bbox_for(fr["K"], bb))
+    im = np.ascontiguousarray(np.stack(imgs).transpose(0, 3, 1, 2).astype(np.float32) / 255)
+    ref = frame_oracle.run_frames(sd, im, np.stack(boxes).astype(np.float32), np.asarray(bi, np.int32), np.stack(mk), np.stack(mm), np.concatenate(kb), np.asarray(diam))
+    n_gated_out = 0
+    for f in range(2):
+        s = slice(8 * f, 8 * f + 8)
+        assert np.array_equal(ref["kp_used"][s], G[f"sv_f{f}_kp_used"].astype(bool))
+        assert np.array_equal(ref["accepted"][s], G[f"sv_f{f}_accepted"].astype(bool)) and G[f"sv_f{f}_kept"].all()
+        assert np.array_equal(ref["ba_inliers"][s], G[f"sv_f{f}_ba_inliers"].astype(bool))
+        assert G[f"sv_f{f}_pnp_keys"].tolist() == list(range(8 * f, 8 * f + 8))
+        n_gated_out += int((G[f"sv_f{f}_kp_used"].sum(1) > G[f"sv_f{f}_ba_inliers"].sum(1)).sum())
+        for got, want in ((ref["T_pnp"][s][:, :3], G[f"sv_f{f}_T_pnp"]), (ref["T_ba"][s], G[f"sv_f{f}_T_ba"])):
+            assert np.abs(got[:, :, :3] - want[:, :, :3]).max() < 1e-6 and np.abs(got[:, :, 3] - want[:, :, 3]).max() < 1e-3      # mm, scene ~1 m
+    assert n_gated_out >= 8                                       # the chi2 gate really had outliers to reject
+
+
 def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
     """(a) One object's map pose is pushed away after the first view: the reference's camera-pose vote rejects it and __maybe_reinit_objects
     (lib/object_slam.py:595-697) replaces it in view 1 — the restatement takes the same decisions and reaches the same state.
