@@ -177,6 +177,10 @@ def main():
     #     test must replace it from the PnP result (lib/object_slam.py:595-697)
     for k, a in run_sequence(osl_mod, shim, ckpt, seq, 3, corrupt_after_first=13).items():
         fix["corrupt_" + k] = a
+    # (b2) the clean sequence with the periodic GLOBAL optimize() (cameras and objects free, LinearSolverCholmod, its = [10, 10, 40, 40],
+    #      lib/object_slam.py:443-451,736-778) after views 2 and 4
+    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 4, global_opt_every=2).items():
+        fix["glob_" + k] = a
     # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
     seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
     tl = dict(pred_res=(512, 512), kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, opt_init_with_outliers=True)
@@ -192,7 +196,7 @@ def main():
     for f in range(2):
         print("single view frame", f, "accepted", fix[f"sv_f{f}_accepted"].tolist(), "kept", fix[f"sv_f{f}_kept"].tolist(), "gated", fix[f"sv_f{f}_kp_used"].sum(1).tolist(),
               "BA inliers", fix[f"sv_f{f}_ba_inliers"].sum(1).tolist())
-    for s in ("clean", "corrupt", "c5"):
+    for s in ("clean", "corrupt", "glob", "c5"):
         n = len([k for k in fix if k.startswith(s + "_v") and k.endswith("_cam")])
         print(s, "views", n, "objects in the map at the end", fix[f"{s}_v{n - 1}_obj_ids"].tolist(), "pnp keys of the last view", fix[f"{s}_v{n - 1}_pnp_keys"].tolist())
 

@@ -7,9 +7,10 @@ Pinned: tests/golden/slam_seq.npz holds the state the UNMODIFIED reference class
 oracle/gen_golden_slam.py: reference control flow, reference network, reference utils; its two native extension modules replaced by the oracle's
 PnP / LM) on three marker sequences — 4 views clean, 3 views with a corrupted map pose (vote rejection + re-initialisation), 2 views at 512x512
 with the T-LESS thresholds; tests/test_marker_cpu.py replays them here: gating, chi2 classifications, re-init decisions identical, keypoints 1e-5,
-poses 1e-6 of the scene scale.  Not restated (bookkeeping outside the hot path; none of it triggers on those sequences):
-__backup_estimate_camera_pose (:933-973, bbox-centroid PnP when no non-symmetric object is in view), the removal of objects with
-too few inliers (:913-930) and the periodic global optimisation (:443-451; csrc/ba_global.cu has its own parity tests)."""
+poses 1e-6 of the scene scale.  A fourth sequence runs with
+global_opt_every = 2, i.e. the periodic full optimize() (:443-451, :736-778: cameras AND objects free, its = [10, 10, 40, 40]) after views 2 and 4.
+Not restated (bookkeeping outside the hot path; it does not trigger on those sequences): __backup_estimate_camera_pose (:933-973,
+bbox-centroid PnP when no non-symmetric object is in view)."""
 from __future__ import annotations
 
 import numpy as np
@@ -35,6 +36,7 @@ class State:
 
     def __init__(self):
         self.obj_poses, self.cam_poses, self.detections, self.view_ids = {}, {}, {}, []
+        self.num_dets, self.diam = {}, {}          # obj_num_dets (:149,1153) and mesh_db[obj]["diameter"]
 
 
 def _to44(T):
@@ -87,6 +89,9 @@ def _process_objects(st, sd, is_sym, view_id, img, K, idx, keys, obj_ids, bboxes
                 prior_uv[o] = full
                 priors[q] = prior_oracle.make_prior_kp_input(full, m, (res, res), ndc=True)
     dets = _run_kp_model(sd, img, K, keys[idx], bboxes[idx], model_kps[idx], model_masks[idx], diameters[idx], priors, res, kvt, bt, seed)
+    for c in idx:
+        st.num_dets[obj_ids[c]] = st.num_dets.get(obj_ids[c], 0) + 1          # :1153
+        st.diam[obj_ids[c]] = float(diameters[c])
     detection = {}
     for q, c in enumerate(idx):
         o = obj_ids[c]
@@ -138,12 +143,91 @@ def _optimize_curr_only(st, view_id, init_with_outliers):
     st.cam_poses[view_id] = P[0]
     for (o, k), v in zip(owner, inl):
         st.detections[view_id][o]["inliers"][k] = v
-    return stats
+    return dict(stats, culled=_cull_objects(st))          # (optimize() ends with the inlier-count check in either mode, :913-930)
+
+
+def _edge_arrays(T_obj, d):
+    """cam_k / uv / information of the edges of one detection (:805-832); p in the frame of T_obj (None: the object's own frame)."""
+    p, cam_k, uv, info = [], [], [], []
+    for k in range(len(d["uv_pred"])):
+        p.append(d["model_kp"][k] if T_obj is None else T_obj[:3, :3] @ d["model_kp"][k] + T_obj[:3, 3])
+        cam_k.append([d["K"][0, 0], d["K"][1, 1], d["K"][0, 2], d["K"][1, 2]])
+        uv.append(d["uv_pred"][k])
+        S = d["cov_pred"][k].astype(np.float64)
+        det = S[0, 0] * S[1, 1] - S[0, 1] * S[1, 0]
+        info.append([S[1, 1] / det, -S[0, 1] / det, -S[1, 0] / det, S[0, 0] / det])
+    return p, cam_k, uv, info
+
+
+def _cull_objects(st):
+    """The end of optimize() (:913-930): objects whose detections hold too few inliers over all views leave the map."""
+    removed = []
+    for o in list(st.obj_poses):
+        need = 3 if st.num_dets.get(o, 0) < 3 else 6
+        n = sum(int(np.count_nonzero(det[o]["inliers"])) for det in st.detections.values() if o in det)
+        if n < need:
+            st.obj_poses.pop(o)
+            removed.append(o)
+    return removed
+
+
+def _optimize_global(st, its=(10, 10, 40, 40)):
+    """optimize(curr_only=False) in SLAM mode (:703-930): one vertex per mapped object (id = its position in obj_poses) and per view with a
+    camera pose (id = position in cam_poses + len(obj_poses), the first one fixed), one EdgeSE3ProjectFromObject per gated keypoint of every
+    detection of a mapped object, chi2 classification of all edges, its = [10, 10, 40, 40] with the Huber kernel stripped after round 2,
+    then the objects that ended up behind the current camera (:899-911) or with too few inliers (:913-930) are removed."""
+    if not st.view_ids:
+        return None
+    obj_ids = list(st.obj_poses)
+    n_cam_e, n_obj_e = {}, {}
+    for v, det in st.detections.items():
+        if v in st.cam_poses:
+            for o, d in det.items():
+                if o in st.obj_poses:
+                    n = int(np.count_nonzero(d["inliers"]))
+                    n_cam_e[v] = n_cam_e.get(v, 0) + n
+                    n_obj_e[o] = n_obj_e.get(o, 0) + n
+    overts = [o for o in obj_ids if n_obj_e.get(o, 0) > 0]
+    cverts = [(i, v) for i, v in enumerate(st.cam_poses) if n_cam_e.get(v, 0) > 0]
+    if not cverts or not overts:
+        return None
+    oi = {o: j for j, o in enumerate(overts)}
+    ci = {v: len(overts) + j for j, (_, v) in enumerate(cverts)}
+    poses = np.stack([_to44(st.obj_poses[o])[:3] for o in overts] + [np.asarray(st.cam_poses[v], np.float64)[:3] for _, v in cverts])
+    fixed = np.array([0] * len(overts) + [1 if i == 0 else 0 for i, _ in cverts], np.uint8)
+    e_obj, e_cam, P_, K_, U_, I_, owner = [], [], [], [], [], [], []
+    for v, det in st.detections.items():
+        for o, d in det.items():
+            if v in ci and o in oi:
+                p, cam_k, uv, info = _edge_arrays(None, d)
+                e_obj += [oi[o]] * len(p); e_cam += [ci[v]] * len(p)
+                P_ += p; K_ += cam_k; U_ += uv; I_ += info
+                owner += [(v, o, k) for k in range(len(p))]
+    n = len(P_)
+    if n == 0:
+        return None
+    P, inl, stats = geom.ba_optimize(poses, fixed, np.asarray(e_obj, np.int32), np.asarray(e_cam, np.int32), np.asarray(K_), np.asarray(P_), np.asarray(U_),
+                                     np.asarray(I_), np.ones(n), list(its))
+    for (v, o, k), f in zip(owner, inl):
+        st.detections[v][o]["inliers"][k] = f
+    for _, v in cverts:
+        st.cam_poses[v] = P[ci[v]]
+    cur = st.view_ids[-1]
+    behind = []
+    for o in overts:
+        st.obj_poses[o] = P[oi[o]]
+        if cur in st.cam_poses:
+            Tc = np.asarray(st.cam_poses[cur])
+            if (Tc[:3, :3] @ st.obj_poses[o][:3, 3] + Tc[:3, 3])[2] < 0.5 * st.diam[o]:
+                st.obj_poses.pop(o)
+                behind.append(o)
+    return dict(stats, behind=behind, culled=_cull_objects(st))
 
 
 def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, model_masks, is_sym, diameters, res=256,
-                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0):
-    """process_view (:327-451), SLAM mode, no external camera pose, bbox_inflate = 0.  Symmetric crops get the prior heat maps."""
+                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, global_opt_every=None):
+    """process_view (:327-451), SLAM mode, no external camera pose, bbox_inflate = 0.  Symmetric crops get the prior heat maps.
+    global_opt_every: the periodic full optimize() of :443-451 (None: never, as on sequences shorter than ObjectSLAM's default of 10)."""
     obj_ids, bboxes = list(obj_ids), np.asarray(bboxes, np.float32)
     model_kps, model_masks, is_sym, diameters = np.asarray(model_kps), np.asarray(model_masks).astype(bool), np.asarray(is_sym, bool), np.asarray(diameters, float)
     first = len(st.view_ids) == 0
@@ -164,4 +248,7 @@ def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, 
     for o, T in reinit.items():                                  # :683-690
         st.obj_poses[o] = T
     stats = _optimize_curr_only(st, view_id, init_with_outliers)
-    return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats)
+    glob = None
+    if global_opt_every and len(st.view_ids) > 1 and len(st.view_ids) % global_opt_every == 0:      # :443-451
+        glob = _optimize_global(st)
+    return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats, global_stats=glob)

@@ -117,13 +117,18 @@ class SlamTracker:
     """Host mirror of ObjectSLAM's per-view tracking state around ONE ``suo_slam_frame`` call per view (lib/object_slam.py:327-421):
     the map ``obj_poses`` {obj: T_OtoG [3,4]}, ``cam_poses`` {view: T_GtoC [3,4]}, ``detections`` {view: {obj: det}} and
     ``view_ids`` — the same containers, with the same detection keys (pose, inliers, kp_mask, model_kp, uv_pred, cov_pred, K, bbox,
-    prior_uv), so the reference's own bookkeeping (object culling, global optimize(), collect_results) can run on top of it."""
+    prior_uv), so the reference's own bookkeeping (collect_results, ...) can run on top of it.  The two pieces of optimize() that follow
+    the per-view solve are here too: the inlier-count check that ends every optimize() (:913-930) and, every ``global_opt_every`` views,
+    the full graph (:443-451, :736-778: cameras and objects free) as ONE coupled ``suo_ba_batch`` problem (csrc/ba_global.cu)."""
 
-    def __init__(self, model, kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, check_n_views=15):
+    def __init__(self, model, kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, check_n_views=15,
+                 global_opt_every=10):
         self.model = model
         self.kp_var_thresh, self.bbox_thresh, self.manual_kp_std = kp_var_thresh, bbox_thresh, manual_kp_std
         self.init_with_outliers, self.seed, self.check_n_views = init_with_outliers, seed, check_n_views
+        self.global_opt_every = global_opt_every
         self.obj_poses, self.cam_poses, self.detections, self.view_ids = {}, {}, {}, []
+        self.obj_num_dets, self.diameters = {}, {}          # ObjectSLAM.obj_num_dets (:149,1153); mesh_db[obj]["diameter"]
         self.record = None        # set to a list to keep the packed input arrays of every suo_slam_frame call (bench.py replays them from HBM)
 
     def process_view(self, view_id, img, K, obj_ids, bboxes, model_kps, model_kps_masks, is_sym, diameters):
@@ -189,6 +194,10 @@ class SlamTracker:
                           kp_mask=m, model_kp=mk[q][m], uv_pred=out["uv"][q][m].astype(np.float64), cov_pred=out["cov"][q][m], K=out["K_bbox"][q].copy(),
                           bbox=boxes[q], prior_uv=out["prior_uv"][q] if out["prior_mask"][q].any() else None, crop=int(order[q]))
         self.detections[view_id] = det
+        for q, o in enumerate(ids):
+            self.diameters[o] = float(diam[q])
+            if q < n1 or cam_ok:
+                self.obj_num_dets[o] = self.obj_num_dets.get(o, 0) + 1           # one per crop that went through the network (:1153)
         if cam_ok:
             self.cam_poses[view_id] = out["T_GtoC"].copy()
             self.view_ids.append(view_id)
@@ -199,4 +208,74 @@ class SlamTracker:
         res = {k: (v[inv] if isinstance(v, np.ndarray) and v.shape[:1] == (L,) and k not in ("status",) else v) for k, v in out.items()}
         res["cam_ok"] = cam_ok
         res["reinit_ids"] = sorted(ids[q] for q in range(L) if out["reinit"][q])
+        res["culled"] = self._cull_objects() if cam_ok and out["status"][3] >= 3 else []       # optimize(curr_only=True) ran to its end
+        res["global_stats"] = None
+        if cam_ok and self.global_opt_every and len(self.view_ids) > 1 and len(self.view_ids) % self.global_opt_every == 0:      # :443-451
+            res["global_stats"] = self.optimize_global()
         return res
+
+    def _cull_objects(self):
+        """The end of ObjectSLAM.optimize() (:913-930): objects whose detections hold too few inliers over all views leave the map."""
+        removed = []
+        for o in list(self.obj_poses):
+            need = 3 if self.obj_num_dets.get(o, 0) < 3 else 6
+            n = sum(int(np.count_nonzero(det[o]["inliers"])) for det in self.detections.values() if o in det)
+            if n < need:
+                self.obj_poses.pop(o)
+                removed.append(o)
+        return removed
+
+    def optimize_global(self, its=(10, 10, 40, 40)):
+        """ObjectSLAM.optimize(curr_only=False) in SLAM mode (:703-930): one vertex per mapped object (ordered as obj_poses) and per view with a
+        camera pose (ordered as cam_poses, the first one fixed), one binary edge per gated keypoint of every detection of a mapped object;
+        chi2 classification, four rounds with the Huber kernel stripped after the third, all inside one ``suo_ba_batch`` call whose graph
+        couples cameras and objects (Schur-complement LM, csrc/ba_global.cu).  Then the objects behind the current camera (:899-911) and
+        those with too few inliers (:913-930) are removed."""
+        from . import ba
+        if not self.view_ids:
+            return None
+        n_cam_e, n_obj_e = {}, {}
+        for v, det in self.detections.items():
+            if v in self.cam_poses:
+                for o, d in det.items():
+                    if o in self.obj_poses:
+                        n = int(np.count_nonzero(d["inliers"]))
+                        n_cam_e[v] = n_cam_e.get(v, 0) + n
+                        n_obj_e[o] = n_obj_e.get(o, 0) + n
+        overts = [o for o in self.obj_poses if n_obj_e.get(o, 0) > 0]
+        cverts = [(i, v) for i, v in enumerate(self.cam_poses) if n_cam_e.get(v, 0) > 0]
+        if not cverts or not overts:
+            return None
+        oi = {o: j for j, o in enumerate(overts)}
+        ci = {v: len(overts) + j for j, (_, v) in enumerate(cverts)}
+        poses = np.stack([np.asarray(self.obj_poses[o], np.float64)[:3] for o in overts] + [np.asarray(self.cam_poses[v], np.float64)[:3] for _, v in cverts])
+        fixed = np.array([0] * len(overts) + [1 if i == 0 else 0 for i, _ in cverts], np.uint8)
+        e_obj, e_cam, P_, K_, U_, I_, owner = [], [], [], [], [], [], []
+        for v, det in self.detections.items():
+            for o, d in det.items():
+                if v in ci and o in oi:
+                    n = len(d["uv_pred"])
+                    S = np.asarray(d["cov_pred"], np.float64).reshape(n, 2, 2)
+                    dt = S[:, 0, 0] * S[:, 1, 1] - S[:, 0, 1] * S[:, 1, 0]
+                    I_.append(np.stack([S[:, 1, 1] / dt, -S[:, 0, 1] / dt, -S[:, 1, 0] / dt, S[:, 0, 0] / dt], 1))
+                    K_.append(np.tile([d["K"][0, 0], d["K"][1, 1], d["K"][0, 2], d["K"][1, 2]], (n, 1)))
+                    P_.append(np.asarray(d["model_kp"], np.float64)); U_.append(np.asarray(d["uv_pred"], np.float64))
+                    e_obj += [oi[o]] * n; e_cam += [ci[v]] * n
+                    owner += [(v, o, k) for k in range(n)]
+        if not owner:
+            return None
+        P, inl, stats = ba.ba_batch([0, len(poses)], [0, len(owner)], poses, fixed, e_obj, e_cam, np.concatenate(K_), np.concatenate(P_), np.concatenate(U_),
+                                    np.concatenate(I_), np.ones(len(owner), np.uint8), list(its), ctx=self.model.context())
+        for (v, o, k), f in zip(owner, inl):
+            self.detections[v][o]["inliers"][k] = f
+        for _, v in cverts:
+            self.cam_poses[v] = P[ci[v]].copy()
+        cur, behind = self.view_ids[-1], []
+        for o in overts:
+            self.obj_poses[o] = np.vstack([P[oi[o]], [0, 0, 0, 1.0]])
+            if cur in self.cam_poses:
+                Tc = self.cam_poses[cur]
+                if (Tc[:3, :3] @ self.obj_poses[o][:3, 3] + Tc[:3, 3])[2] < 0.5 * self.diameters[o]:
+                    self.obj_poses.pop(o)
+                    behind.append(o)
+        return dict(rounds=int(stats[0, 0]), outer=int(stats[0, 1]), trials=int(stats[0, 2]), behind=behind, culled=self._cull_objects())

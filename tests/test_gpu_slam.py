@@ -107,6 +107,33 @@ def test_slam_sequence_vs_the_cpu_oracle_and_the_reference_fixture(marker_model,
             assert bad in out["reinit_ids"]
 
 
+def test_slam_sequence_with_the_periodic_global_optimisation(marker_model, golden_dir):
+    """global_opt_every = 2: after views 2 and 4 the tracker runs the full graph (cameras and objects free, its = [10, 10, 40, 40]) as one
+    coupled suo_ba_batch problem (csrc/ba_global.cu) — against the oracle's restatement AND against the state the unmodified reference class
+    reaches with global_opt_every = 2 (fixture "glob_*": its optimize() over LinearSolverCholmod moved the cameras by 1-4 mm)."""
+    sd = synth.make_marker_state_dict(0)
+    seq = synth.make_slam_sequence(3, n_views=4, n_obj=6)
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    trk = slam.SlamTracker(marker_model, global_opt_every=2)
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        a = _view_args(seq, v)
+        out = trk.process_view(*a)
+        ref = sfo.process_view(st, sd, *a, global_opt_every=2)
+        vid = v["view_id"]
+        assert (out["global_stats"] is not None) == (ref["global_stats"] is not None) == (i in (1, 3))
+        if i in (1, 3):
+            print(f"[slam global view {i}] GPU {out['global_stats']}, oracle {ref['global_stats']}; moved the camera by "
+                  f"{np.abs(G[f'clean_v{i}_cam'] - G[f'glob_v{i}_cam']).max():.2f} mm against the run without it")
+            assert out["global_stats"]["culled"] == ref["global_stats"]["culled"] == [] and out["global_stats"]["behind"] == []
+        for w in trk.cam_poses:                                   # the global step rewrites EVERY camera and object
+            assert _rel(trk.cam_poses[w], st.cam_poses[w]) < 1e-3
+        assert set(trk.obj_poses) == set(st.obj_poses)
+        for o in st.obj_poses:
+            assert _rel(trk.obj_poses[o], st.obj_poses[o]) < 1e-3, o
+        _check_vs_reference_fixture(G, "glob", i, trk, vid)
+
+
 def test_slam_views_at_512_with_symmetric_priors(golden_dir):
     """BASELINE configs[4] shape: 512x512 crops -> 128x128 heat-maps (the CTA-per-map reduction kernel, the 48-channel stem fed by device-rendered
     priors), 4 objects of which 2 symmetric, 2 views — the same comparison as above at the T-LESS resolution and thresholds (evaluate.py:68-76)."""

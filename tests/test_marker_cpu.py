@@ -172,7 +172,8 @@ def test_frame_oracle_vs_the_unmodified_reference_in_single_view_mode(golden_dir
 def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
     """(a) One object's map pose is pushed away after the first view: the reference's camera-pose vote rejects it and __maybe_reinit_objects
     (lib/object_slam.py:595-697) replaces it in view 1 — the restatement takes the same decisions and reaches the same state.
-    (b) 512x512 crops with the T-LESS thresholds and opt_init_with_outliers (evaluate.py:68-76), BASELINE configs[4]'s shape."""
+    (b) 512x512 crops with the T-LESS thresholds and opt_init_with_outliers (evaluate.py:68-76), BASELINE configs[4]'s shape.
+    (c) the periodic global optimize() (cameras and objects free) of a run with global_opt_every = 2."""
     from oracle import slam_frame_oracle as sfo
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
     G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
@@ -186,6 +187,13 @@ def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
         if i == 0:
             st.obj_poses[13] = st.obj_poses[13].copy()
             st.obj_poses[13][:3, 3] += [70.0, -50.0, 40.0]
+    # (c) global_opt_every = 2: the periodic full optimize() (:443-451, :736-778) after the second view
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq, v), global_opt_every=2)
+        assert (r["global_stats"] is not None) == (i == 1)
+        _check_view_against_reference(G, "glob", i, st, v["view_id"], r)
+    assert np.abs(G["clean_v1_cam"] - G["glob_v1_cam"]).max() > 0.5          # (the global step moved the camera by ~1 mm in the reference)
     seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
     st = sfo.State()
     for i, v in enumerate(seq5["views"]):
