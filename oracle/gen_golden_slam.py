@@ -162,41 +162,53 @@ def run_single_view_frames(osl_mod, shim, ckpt, seed0, n_frames, n_obj=8):
     return out
 
 
-def main():
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "slam_seq.npz"))
+    ap.add_argument("--scenarios", default="clean,corrupt,glob,c5,sv")
+    a = ap.parse_args(argv)
+    want = a.scenarios.split(",")
     torch.manual_seed(0)
     osl_mod, shim = install()
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
-    ckpt = os.path.join(ROOT, "build", "marker_ckpt.pth.tar")
+    ckpt = os.path.join(ROOT, "build", f"marker_ckpt_{os.getpid()}.pth.tar")
     torch.save({"model": synth.make_marker_state_dict(0), "epoch": 0, "args": argparse.Namespace(synthetic=True)}, ckpt)
     fix = {}
-    # (a) 4 views, 6 objects (3 symmetric), YCBV thresholds (evaluate.py:58-66): the scenario of tests/test_gpu_slam.py
-    seq = synth.make_slam_sequence(3, n_views=4, n_obj=6)
-    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 4).items():
-        fix["clean_" + k] = a
-    # (b) the same sequence with object 13's map pose pushed away after the first view: the vote must reject it, the re-initialisation
-    #     test must replace it from the PnP result (lib/object_slam.py:595-697)
-    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 3, corrupt_after_first=13).items():
-        fix["corrupt_" + k] = a
-    # (b2) the clean sequence with the periodic GLOBAL optimize() (cameras and objects free, LinearSolverCholmod, its = [10, 10, 40, 40],
-    #      lib/object_slam.py:443-451,736-778) after views 2 and 4
-    for k, a in run_sequence(osl_mod, shim, ckpt, seq, 4, global_opt_every=2).items():
-        fix["glob_" + k] = a
-    # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
-    seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
-    tl = dict(pred_res=(512, 512), kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, opt_init_with_outliers=True)
-    for k, a in run_sequence(osl_mod, shim, ckpt, seq5, 2, **tl).items():
-        fix["c5_" + k] = a
-    # (d) single-view mode: the two frames of tests/test_gpu_round2.py::test_pixels_to_poses (8 crops each)
-    for k, a in run_single_view_frames(osl_mod, shim, ckpt, 2000, 2).items():
-        fix["sv_" + k] = a
-    os.remove(ckpt)
-    path = os.path.join(ROOT, "tests", "golden", "slam_seq.npz")
-    np.savez_compressed(path, **fix)
-    print("wrote", path, os.path.getsize(path), "bytes,", len(fix), "arrays")
-    for f in range(2):
-        print("single view frame", f, "accepted", fix[f"sv_f{f}_accepted"].tolist(), "kept", fix[f"sv_f{f}_kept"].tolist(), "gated", fix[f"sv_f{f}_kp_used"].sum(1).tolist(),
-              "BA inliers", fix[f"sv_f{f}_ba_inliers"].sum(1).tolist())
-    for s in ("clean", "corrupt", "glob", "c5"):
+    try:
+        seq = synth.make_slam_sequence(3, n_views=4, n_obj=6)
+        if "clean" in want:
+            # (a) 4 views, 6 objects (3 symmetric), YCBV thresholds (evaluate.py:58-66): the scenario of tests/test_gpu_slam.py
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq, 4).items():
+                fix["clean_" + k] = v
+        if "corrupt" in want:
+            # (b) the same sequence with object 13's map pose pushed away after the first view: the vote must reject it, the
+            #     re-initialisation test must replace it from the PnP result (lib/object_slam.py:595-697)
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq, 3, corrupt_after_first=13).items():
+                fix["corrupt_" + k] = v
+        if "glob" in want:
+            # (b2) the clean sequence with the periodic GLOBAL optimize() (cameras and objects free, LinearSolverCholmod, its = [10, 10, 40, 40],
+            #      lib/object_slam.py:443-451,736-778) after views 2 and 4
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq, 4, global_opt_every=2).items():
+                fix["glob_" + k] = v
+        if "c5" in want:
+            # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
+            seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
+            tl = dict(pred_res=(512, 512), kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, opt_init_with_outliers=True)
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq5, 2, **tl).items():
+                fix["c5_" + k] = v
+        if "sv" in want:
+            # (d) single-view mode: the two frames of tests/test_gpu_round2.py::test_pixels_to_poses (8 crops each)
+            for k, v in run_single_view_frames(osl_mod, shim, ckpt, 2000, 2).items():
+                fix["sv_" + k] = v
+    finally:
+        os.remove(ckpt)
+    np.savez_compressed(a.out, **fix)
+    print("wrote", a.out, os.path.getsize(a.out), "bytes,", len(fix), "arrays")
+    if "sv" in want:
+        for f in range(2):
+            print("single view frame", f, "accepted", fix[f"sv_f{f}_accepted"].tolist(), "kept", fix[f"sv_f{f}_kept"].tolist(), "gated", fix[f"sv_f{f}_kp_used"].sum(1).tolist(),
+                  "BA inliers", fix[f"sv_f{f}_ba_inliers"].sum(1).tolist())
+    for s in [w for w in want if w != "sv"]:
         n = len([k for k in fix if k.startswith(s + "_v") and k.endswith("_cam")])
         print(s, "views", n, "objects in the map at the end", fix[f"{s}_v{n - 1}_obj_ids"].tolist(), "pnp keys of the last view", fix[f"{s}_v{n - 1}_pnp_keys"].tolist())
 

@@ -4,9 +4,10 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
-from oracle import frame_oracle, geom
+from oracle import frame_oracle, geom, ref_shims
 from suo_slam_b200 import arch, frames, synth, weights
 
 
@@ -199,3 +200,24 @@ def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
     for i, v in enumerate(seq5["views"]):
         r = sfo.process_view(st, sd, *_slam_args(seq5, v), res=512, kp_var_thresh=0.5, bbox_thresh=1.0, manual_kp_std=0.1, init_with_outliers=True)
         _check_view_against_reference(G, "c5", i, st, v["view_id"], r)
+
+
+@pytest.mark.skipif(not ref_shims.reference_available(), reason="reference tree not mounted")
+def test_the_committed_reference_fixture_is_what_the_reference_produces_here(golden_dir, tmp_path):
+    """Re-runs oracle/gen_golden_slam.py (the UNMODIFIED lib/object_slam.py over the oracle's solvers) for two of its scenarios in a fresh
+    process and compares with the committed tests/golden/slam_seq.npz: discrete results identical, floats to 1e-5 (torch's CPU convolutions
+    may reduce in another order on another thread count)."""
+    import subprocess
+    import sys
+    out = tmp_path / "slam_live.npz"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.gen_golden_slam", "--out", str(out), "--scenarios", "sv,corrupt"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    live, G = np.load(out), np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    assert len(live.files) > 100 and set(live.files) <= set(G.files)
+    for k in live.files:
+        if live[k].dtype.kind in "ui":
+            assert np.array_equal(live[k], G[k]), k
+        else:
+            np.testing.assert_allclose(live[k], G[k], rtol=1e-5, atol=1e-5, err_msg=k)
