@@ -913,7 +913,7 @@ def run_native_c5(args):
         ctx.check(lib.suo_slam_frame(hdl, p(d["img"]), H, W, p(d["K"]), p(d["boxes"]), d["L"], d["n1"], p(d["mk"]), p(d["mm"]), p(d["diam"]), p(d["mv"]), p(d["Tm"]), d["n_views"], d["nh"],
                                      *((p(h["crop"]), p(h["T"]), p(h["K"]), p(h["off"]), p(h["mk"]), p(h["uv"]), p(h["cov"])) if h is not None else (None,) * 7),
                                      tless["kp_var_thresh"], tless["bbox_thresh"], tless["manual_kp_std"], 1, 0, p(o["cam"]), p(o["st"]), p(o["Tp"]), p(o["used"]), p(o["bain"]),
-                                     p(o["uv"]), p(o["cov"]), None, None, None, p(o["To"]), p(o["mv"]), None, None, 1, sp))
+                                     p(o["uv"]), p(o["cov"]), None, None, None, p(o["To"]), p(o["mv"]), None, None, None, 0, 1, sp))
 
     def timed(fn, steps, warm):
         fn(warm)

@@ -286,8 +286,15 @@ int suo_frames_u8(suo_ctx* ctx, const uint8_t* images_hwc, int n_img, int H, int
  * hypothesis, number of hypotheses, curr_only edges, LM trials, curr_only inlier edges, 0, 0}; T_pnp [L,16]; kp_used, ba_inliers
  * [L,K] u8; uv [L,K,2], cov [L,K,4] f32; prior_uv [L,K,2] f32 + prior_mask [L,K] u8 (what the symmetric crops were given);
  * K_bbox [L,9] f64; T_OtoG_out [L,12] + map_valid_out [L] (the updated map); reinit [L] u8, reinit_counts [L,2] i32 (pnp, estim).
- * Not covered (bookkeeping the caller keeps): __backup_estimate_camera_pose (:933-973) when no non-symmetric object
- * is in view (status[0] = 0 then), object culling (:913-930), the periodic global optimize() (suo_ba_batch). */
+ * Camera pose known to the caller — T_GtoC_init [12] f64 (NULL with cam_init_mode 0 = the vote above): the vote is skipped, status =
+ * {1, 0, 0, ...} and the view proceeds from that pose (priors, object initialisation, re-initialisation test, curr_only solve).
+ *   cam_init_mode 1: known BEFORE the view — external odometry (process_view's cam_pose, :349-353, pass n_nonsym = 0 as the reference treats
+ *                    every object as symmetric then) or __backup_estimate_camera_pose called because no non-symmetric object is in view (:372-391);
+ *   cam_init_mode 2: __backup_estimate_camera_pose after a FAILED vote (:404-411; a first call with mode 0 returned status[0] = 0): as mode 1,
+ *                    but the unmapped objects of the non-symmetric group are not initialised (their pass returned at :566-575).
+ * The backup pose itself (bbox-centroid PnP = one suo_pnp_batch object, or the constant-velocity guess, :933-973) is the caller's:
+ * slam.SlamTracker does it.  Not covered (bookkeeping the caller keeps; slam.SlamTracker mirrors both): object culling
+ * (:913-930), the periodic global optimize() (one coupled suo_ba_batch problem). */
 int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const double* K_cam,
                    const float* boxes, int L, int n_nonsym,
                    const double* model_kps, const uint8_t* model_mask, const double* diameter,
@@ -298,7 +305,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
                    double* T_GtoC, int32_t* status, double* T_pnp, uint8_t* kp_used, uint8_t* ba_inliers,
                    float* uv, float* cov, float* prior_uv, uint8_t* prior_mask, double* K_bbox,
                    double* T_OtoG_out, uint8_t* map_valid_out, uint8_t* reinit, int32_t* reinit_counts,
-                   int on_device, void* stream);
+                   const double* T_GtoC_init, int cam_init_mode, int on_device, void* stream);
 
 /* Asynchronous, double-buffered form of suo_frames_u8 for a STREAM of frame batches (host pointers, priors == NULL):
  * submit enqueues the host->device copies of the batch on the library's copy stream and the frame path on `stream`

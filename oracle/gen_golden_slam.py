@@ -41,6 +41,7 @@ from oracle import geom, ref_shims  # noqa: E402
 from suo_slam_b200 import synth  # noqa: E402
 
 SEED = 0                     # RANSAC seed (slam_frame_oracle.process_view's default)
+BACKUP_KEY = 10 ** 6         # = oracle/slam_frame_oracle.py BACKUP_KEY
 
 
 class _CpuBa:
@@ -65,7 +66,9 @@ class _PnpShim:
     def pnp(self, xs_in, ys_in, threshold=0.001):
         xs_in = np.asarray(xs_in, np.float64)
         key = [k for mk, k in self.crops if (mk == xs_in[0]).all(-1).any()]
-        assert len(key) == 1, "cannot tell which crop this pnp() call belongs to"
+        assert len(key) <= 1, "cannot tell which crop this pnp() call belongs to"
+        if not key:                                # not a crop's model keypoints: the bbox-centroid PnP of __backup_estimate_camera_pose (:953)
+            key = [BACKUP_KEY]
         self.calls.append(key[0])
         T, _ = geom.lambdatwist_pnp(xs_in, np.asarray(ys_in, np.float64), threshold, seed=SEED, obj_key=key[0])
         return np.eye(4) if T is None else T
@@ -90,7 +93,7 @@ def install():
     return importlib.import_module("lib.object_slam"), shim
 
 
-def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, **kw):
+def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, view_objs=None, **kw):
     objs = seq["objs"]
     mesh_db = {o["obj_id"]: dict(is_symmetric=bool(o["is_symmetric"]), diameter=float(o["diameter"])) for o in objs}
     with contextlib.redirect_stdout(io.StringIO()):
@@ -99,14 +102,15 @@ def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, **
     # resolution the priors are made for — an attribute of the reference object, not a code change
     slam.model.input_res = tuple(kw.get("pred_res", (256, 256)))
     out = {}
-    is_sym = np.array([o["is_symmetric"] for o in objs])
-    order = np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]])
     for i, v in enumerate(seq["views"][:n_views]):
+        present = list(range(len(objs))) if view_objs is None else list(view_objs(i))          # indices of the objects detected in this view
+        is_sym = np.array([objs[c]["is_symmetric"] for c in present])
+        order = [present[j] for j in np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]])]
         shim.crops = [(objs[c]["model_kps"], pos) for pos, c in enumerate(order)]
         shim.calls = []
-        obj_ids = np.array([d["obj_id"] for d in v["dets"]])
-        bboxes = np.stack([d["bbox"] for d in v["dets"]]).astype(np.float32)
-        mk, mm = np.stack([o["model_kps"] for o in objs]), np.stack([o["model_kps_mask"] for o in objs])
+        obj_ids = np.array([v["dets"][c]["obj_id"] for c in present])
+        bboxes = np.stack([v["dets"][c]["bbox"] for c in present]).astype(np.float32)
+        mk, mm = np.stack([objs[c]["model_kps"] for c in present]), np.stack([objs[c]["model_kps_mask"] for c in present])
         with contextlib.redirect_stdout(io.StringIO()):
             slam.process_view(v["view_id"], v["img"], seq["K"], obj_ids, bboxes.copy(), mk, mm, mm.copy())
         vid = v["view_id"]
@@ -165,7 +169,7 @@ def run_single_view_frames(osl_mod, shim, ckpt, seed0, n_frames, n_obj=8):
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "slam_seq.npz"))
-    ap.add_argument("--scenarios", default="clean,corrupt,glob,c5,sv")
+    ap.add_argument("--scenarios", default="clean,corrupt,glob,allsym,newnon,cv,c5,sv")
     a = ap.parse_args(argv)
     want = a.scenarios.split(",")
     torch.manual_seed(0)
@@ -190,6 +194,19 @@ def main(argv=None):
             #      lib/object_slam.py:443-451,736-778) after views 2 and 4
             for k, v in run_sequence(osl_mod, shim, ckpt, seq, 4, global_opt_every=2).items():
                 fix["glob_" + k] = v
+        # (b3-b5) __backup_estimate_camera_pose (:933-973)
+        if "allsym" in want:       # every object symmetric: bbox-centroid PnP BEFORE the passes (:372-391), every crop gets a prior
+            sq = synth.make_slam_sequence(5, n_views=3, n_obj=6, n_sym=6)
+            for k, v in run_sequence(osl_mod, shim, ckpt, sq, 3).items():
+                fix["allsym_" + k] = v
+        if "newnon" in want:       # view 0 sees only the 4 symmetric objects; the 4 non-symmetric ones appear in view 1 and are not in the map:
+            sq = synth.make_slam_sequence(6, n_views=3, n_obj=8, n_sym=4)      # the vote has no hypothesis -> centroid PnP AFTER the first pass (:404-411)
+            for k, v in run_sequence(osl_mod, shim, ckpt, sq, 3, view_objs=lambda i: range(4) if i == 0 else range(8)).items():
+                fix["newnon_" + k] = v
+        if "cv" in want:           # three objects: the centroid PnP has < 4 points -> last pose (view 1), constant-velocity guess (view 2)
+            sq = synth.make_slam_sequence(7, n_views=3, n_obj=3, n_sym=3)
+            for k, v in run_sequence(osl_mod, shim, ckpt, sq, 3).items():
+                fix["cv_" + k] = v
         if "c5" in want:
             # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
             seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)

@@ -9,8 +9,9 @@ PnP / LM) on three marker sequences — 4 views clean, 3 views with a corrupted 
 with the T-LESS thresholds; tests/test_marker_cpu.py replays them here: gating, chi2 classifications, re-init decisions identical, keypoints 1e-5,
 poses 1e-6 of the scene scale.  A fourth sequence runs with
 global_opt_every = 2, i.e. the periodic full optimize() (:443-451, :736-778: cameras AND objects free, its = [10, 10, 40, 40]) after views 2 and 4.
-Not restated (bookkeeping outside the hot path; it does not trigger on those sequences): __backup_estimate_camera_pose (:933-973,
-bbox-centroid PnP when no non-symmetric object is in view)."""
+Three more exercise __backup_estimate_camera_pose (:933-973): every object symmetric (bbox-centroid PnP before the passes), the non-symmetric
+objects new to the map (the vote has no hypothesis: centroid PnP after the first pass), and three objects only (centroid PnP impossible:
+last pose, then the constant-velocity guess)."""
 from __future__ import annotations
 
 import numpy as np
@@ -146,6 +147,28 @@ def _optimize_curr_only(st, view_id, init_with_outliers):
     return dict(stats, culled=_cull_objects(st))          # (optimize() ends with the inlier-count check in either mode, :913-930)
 
 
+BACKUP_KEY = 10 ** 6        # RANSAC stream of the bbox-centroid PnP (the per-crop streams use the crop's position 0..L-1)
+
+
+def _backup_estimate_camera_pose(st, view_id, obj_ids, bboxes, K, seed):
+    """__backup_estimate_camera_pose (:933-973): PnP of the bbox centres against the map positions of the objects in view; if that fails
+    (fewer than 4 mapped objects, or PnP returns identity) a constant-velocity guess from the last two camera poses, or the last pose.
+    Always produces a pose and registers the view."""
+    assert st.view_ids and view_id not in st.view_ids and view_id not in st.cam_poses
+    cen = [0.5 * (bboxes[i, :2] + bboxes[i, 2:]) for i, o in enumerate(obj_ids) if o in st.obj_poses]
+    ctr = [_to44(st.obj_poses[o])[:3, 3] for o in obj_ids if o in st.obj_poses]
+    r = geom.pnp(np.stack(ctr), np.stack(cen), np.asarray(K, np.float64), seed=seed, obj_key=BACKUP_KEY) if cen else None
+    if r is not None:
+        st.cam_poses[view_id], how = r[0], "pnp"
+    elif len(st.view_ids) > 1:
+        T1, T2 = _to44(st.cam_poses[st.view_ids[-2]]), _to44(st.cam_poses[st.view_ids[-1]])
+        st.cam_poses[view_id], how = (T2 @ slam_oracle._inv_se3(T1)) @ T2, "const_vel"
+    else:
+        st.cam_poses[view_id], how = st.cam_poses[st.view_ids[-1]], "last"
+    st.view_ids.append(view_id)
+    return how
+
+
 def _edge_arrays(T_obj, d):
     """cam_k / uv / information of the edges of one detection (:805-832); p in the frame of T_obj (None: the object's own frame)."""
     p, cam_k, uv, info = [], [], [], []
@@ -235,13 +258,16 @@ def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, 
     keys = np.zeros(len(obj_ids), int)
     keys[np.concatenate([non, sym]).astype(int)] = np.arange(len(obj_ids))
     args = (keys, obj_ids, bboxes, model_kps, model_masks, diameters, res, kp_var_thresh, bbox_thresh, seed, first)
+    backup = None
+    if not first and len(non) == 0:                              # :372-391: no non-symmetric object to vote with
+        backup = _backup_estimate_camera_pose(st, view_id, obj_ids, bboxes, K, seed)
     _process_objects(st, sd, False, view_id, img_u8, K, non, *args)
     if view_id not in st.cam_poses:                              # :404-411
         if first:
             st.view_ids.append(view_id)
             st.cam_poses[view_id] = np.eye(4)[:3]
-        else:
-            return dict(cam_ok=False)                            # (the reference would try __backup_estimate_camera_pose here)
+        else:                                                    # the vote failed (no mapped non-symmetric object with a PnP pose / < 4 inliers)
+            backup = _backup_estimate_camera_pose(st, view_id, obj_ids, bboxes, K, seed)
     if len(sym):
         _process_objects(st, sd, True, view_id, img_u8, K, sym, *args)
     reinit, counts, _ = slam_oracle.maybe_reinit_objects(st.obj_poses, st.cam_poses, st.detections, st.view_ids, view_id, 15, manual_kp_std)
@@ -251,4 +277,4 @@ def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, 
     glob = None
     if global_opt_every and len(st.view_ids) > 1 and len(st.view_ids) % global_opt_every == 0:      # :443-451
         glob = _optimize_global(st)
-    return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats, global_stats=glob)
+    return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats, global_stats=glob, backup=backup)

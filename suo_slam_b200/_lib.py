@@ -71,7 +71,7 @@ def lib():
         L.suo_activation_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
         L.suo_activation_bytes.restype = C.c_size_t
         L.suo_slam_frame.argtypes = ([vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int] + [vp] * 7 +
-                                     [C.c_double, C.c_double, C.c_double, C.c_int, C.c_uint64] + [vp] * 14 + [C.c_int, vp])
+                                     [C.c_double, C.c_double, C.c_double, C.c_int, C.c_uint64] + [vp] * 14 + [vp, C.c_int, C.c_int, vp])
         L.suo_record_bytes.argtypes = [C.c_int]
         L.suo_record_bytes.restype = C.c_size_t
         L.suo_pack_records.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]

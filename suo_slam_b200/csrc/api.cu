@@ -1694,11 +1694,16 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
                    const double* hist_model_kp, const float* hist_uv, const float* hist_cov, double kp_var_thresh, double bbox_thresh,
                    double manual_kp_std, int init_with_outliers, uint64_t seed, double* T_GtoC, int32_t* status, double* T_pnp, uint8_t* kp_used,
                    uint8_t* ba_inliers, float* uv, float* cov, float* prior_uv, uint8_t* prior_mask, double* K_bbox, double* T_OtoG_out,
-                   uint8_t* map_valid_out, uint8_t* reinit, int32_t* reinit_counts, int on_device, void* stream) {
+                   uint8_t* map_valid_out, uint8_t* reinit, int32_t* reinit_counts, const double* T_GtoC_init, int cam_init_mode,
+                   int on_device, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   CtxExtra* x = X(ctx);
   if (!x->loaded) { ctx->set_error("suo_slam_frame before suo_load_weights", __FILE__, __LINE__); return SUO_E_STATE; }
+  if (cam_init_mode < 0 || cam_init_mode > 2 || (cam_init_mode != 0) != (T_GtoC_init != nullptr)) {
+    ctx->set_error("suo_slam_frame: cam_init_mode must be 0 (vote), 1 or 2 (camera pose given in T_GtoC_init)", __FILE__, __LINE__);
+    return SUO_E_INVALID;
+  }
   if (L <= 0 || L > ctx->max_crops || L > 128 || n_nonsym < 0 || n_nonsym > L || n_views < 1 || n_hist < 0 || !image_hwc || !K_cam || !boxes || !model_kps ||
       !model_mask || !diameter || !map_valid || !T_OtoG || (n_hist > 0 && (!hist_crop || !hist_T_GtoC || !hist_K || !hist_off || !hist_model_kp || !hist_uv)) ||
       !(manual_kp_std > 0)) {
@@ -1714,7 +1719,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
     for (int h = 0; h < n_hist; ++h) if (hist_off[h + 1] < hist_off[h] || hist_crop[h] < 0 || hist_crop[h] >= L) { ctx->set_error("suo_slam_frame: bad history arrays", __FILE__, __LINE__); return SUO_E_INVALID; }
     NH = (size_t)hist_off[n_hist];
   }
-  const size_t in_bytes = n_im + (size_t)L * (16 + 8 + 1 + 96) + LK * 25 + 72 + (size_t)n_hist * (4 + 96 + 72 + 4) + 4 + NH * (24 + 8 + 16) + 32 * 256;
+  const size_t in_bytes = n_im + (size_t)L * (16 + 8 + 1 + 96) + LK * 25 + 72 + 96 + (size_t)n_hist * (4 + 96 + 72 + 4) + 4 + NH * (24 + 8 + 16) + 32 * 256;
   const size_t out_bytes = (size_t)L * (128 + 72 + 96 + 1 + 1 + 8 + 4) + LK * (1 + 1 + 8 + 16 + 8 + 1) + 96 + 32 + 32 * 256;
   const size_t work_bytes = (size_t)L * (72 + 4 + 20) + LK * (24 + 16 + 4 + 4 + 4 + 4 + 32 + 24 + 16 + 32 + 1 + 4 + 16 + 1 + 1) + 4096 + 48 * 256;
   rc = x->fr.grow(ctx, in_bytes + out_bytes + work_bytes);
@@ -1728,6 +1733,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   const double* d_diam = diameter; const uint8_t* d_mv = map_valid; const double* d_To = T_OtoG;
   const int32_t* d_hc = hist_crop; const double* d_hT = hist_T_GtoC; const double* d_hK = hist_K; const int32_t* d_ho = hist_off;
   const double* d_hm = hist_model_kp; const float* d_hu = hist_uv; const float* d_hcv = hist_cov;
+  const double* d_Ti = T_GtoC_init;
   Stage stg(x->fr);
   if (!on_device) {
     // the frame goes straight from the caller's buffer (0.9 MB: one copy either way); the ~15 small arrays through the pinned mirror
@@ -1736,6 +1742,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
     d_im = im_;
 #define STAGE(T, dst, src, n) { T* dst##_ = bp.take<T>(n); stg.in(dst##_, src, n); dst = dst##_; }
     STAGE(double, d_Kc, K_cam, 9) STAGE(float, d_box, boxes, 4 * (size_t)L) STAGE(double, d_mk, model_kps, 3 * LK)
+    if (T_GtoC_init) { STAGE(double, d_Ti, T_GtoC_init, 12) }
     STAGE(uint8_t, d_mm, model_mask, LK) STAGE(double, d_diam, diameter, (size_t)L) STAGE(uint8_t, d_mv, map_valid, (size_t)L) STAGE(double, d_To, T_OtoG, 12 * (size_t)L)
     if (n_hist > 0) {
       STAGE(int32_t, d_hc, hist_crop, (size_t)n_hist) STAGE(double, d_hT, hist_T_GtoC, 12 * (size_t)n_hist) STAGE(double, d_hK, hist_K, 9 * (size_t)n_hist)
@@ -1784,8 +1791,16 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   else {
     SUO_CUDA_TRY(ctx, cudaMemsetAsync(o_used, 0, LK, s));
   }
-  rc = launch_slam_vote(ctx, n1, K, n_views == 1, o_Tpnp, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, d_diam, d_mv, d_To, manual_kp_std, 5.991, o_cam, o_st, s);
-  if (rc) return rc;
+  if (cam_init_mode == 0) {
+    rc = launch_slam_vote(ctx, n1, K, n_views == 1, o_Tpnp, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, d_diam, d_mv, d_To, manual_kp_std, 5.991, o_cam, o_st, s);
+    if (rc) return rc;
+  } else {
+    // the caller knows the camera pose (external odometry :349-353, or __backup_estimate_camera_pose :933-973 before the passes / after a
+    // failed vote): no vote; status = {1, 0, 0, ...}
+    static const int32_t one = 1;
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(o_cam, d_Ti, 12 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    SUO_CUDA_TRY(ctx, cudaMemcpyAsync(o_st, &one, sizeof(one), cudaMemcpyHostToDevice, s));
+  }
   if (n2 > 0) {
     rc = launch_slam_prior_uv(ctx, n1, L, K, o_st, o_cam, d_mv, d_To, d_mk, d_mm, w_kraw, o_puv, o_pm, s);
     if (rc) return rc;
@@ -1795,7 +1810,7 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
     if (rc) return rc;
   }
   rc = launch_slam_map_update(ctx, L, K, n_views, n_hist, o_st, o_cam, o_Tpnp, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, d_diam, d_mv, d_To, o_mv, o_To,
-                              d_hc, d_hT, d_hK, d_ho, d_hm, d_hu, d_hcv, manual_kp_std, 5.991, o_rc, o_ri, s);
+                              d_hc, d_hT, d_hK, d_ho, d_hm, d_hu, d_hcv, manual_kp_std, 5.991, o_rc, o_ri, s, cam_init_mode == 2 ? n1 : 0);
   if (rc) return rc;
   rc = launch_slam_ba_assemble(ctx, L, K, o_st, o_cam, o_mv, o_To, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, b_poses, b_fixed, b_pv, b_vc, b_pe, b_ec, b_eo, b_ecam,
                                b_ck, b_p, b_uv, b_info, b_inl, b_src, s);

@@ -169,7 +169,7 @@ int launch_slam_map_update(suo_ctx* ctx, int L, int K, int n_views, int n_hist, 
                            const double* diameter, const uint8_t* map_valid_in, const double* T_OtoG_in, uint8_t* map_valid, double* T_OtoG,
                            const int32_t* hist_crop, const double* hist_T_GtoC, const double* hist_K, const int32_t* hist_off,
                            const double* hist_model_kp, const float* hist_uv, const float* hist_cov, double manual_kp_std, double gate,
-                           int32_t* rcounts, uint8_t* reinit, cudaStream_t s);
+                           int32_t* rcounts, uint8_t* reinit, cudaStream_t s, int init_from = 0);
 int launch_slam_ba_assemble(suo_ctx* ctx, int L, int K, const int32_t* status, const double* T_GtoC, const uint8_t* map_valid, const double* T_OtoG,
                             const int32_t* counts, const int32_t* kp_index, const double* xs, const float* uv, const float* cov, const double* Kb,
                             double* poses, uint8_t* fixed, int32_t* prob_vert, int32_t* vert_cnt, int32_t* prob_edge, int32_t* edge_cnt, int32_t* e_obj,

@@ -185,6 +185,7 @@ struct MapArgs {
   double inv_manual_var, gate;
   int32_t* rcounts;      // [L,2]: keypoints explained by the PnP pose / by the map pose over the checked views
   uint8_t* reinit;       // [L]
+  int init_from;         // first crop whose object may be initialised in this view (n_nonsym after a failed vote, :566-575 returns before :577-592)
 };
 
 // copy the map, then initialise unmapped objects that got a PnP pose in this view: T_OtoG = inv(T_GtoC) T_OtoC (:541-556, :577-592)
@@ -193,7 +194,7 @@ __global__ void slam_init_objects_kernel(const MapArgs a) {
     bool valid = a.map_valid_in[c] != 0;
     double T[12];
     for (int q = 0; q < 12; ++q) T[q] = valid ? a.T_OtoG_in[12 * (size_t)c + q] : ((q % 5 == 0) ? 1.0 : 0.0);
-    if (!valid && a.status[0] && pnp_accepted(a.T_pnp + 16 * (size_t)c, a.counts[c], a.diameter[c])) {
+    if (!valid && c >= a.init_from && a.status[0] && pnp_accepted(a.T_pnp + 16 * (size_t)c, a.counts[c], a.diameter[c])) {
       double inv[12];
       se3_inv34(a.T_GtoC, inv);
       mat34_to44_mul(inv, a.T_pnp + 16 * (size_t)c, T);
@@ -355,9 +356,10 @@ int launch_slam_map_update(suo_ctx* ctx, int L, int K, int n_views, int n_hist, 
                            const double* diameter, const uint8_t* map_valid_in, const double* T_OtoG_in, uint8_t* map_valid, double* T_OtoG,
                            const int32_t* hist_crop, const double* hist_T_GtoC, const double* hist_K, const int32_t* hist_off,
                            const double* hist_model_kp, const float* hist_uv, const float* hist_cov, double manual_kp_std, double gate,
-                           int32_t* rcounts, uint8_t* reinit, cudaStream_t s) {
+                           int32_t* rcounts, uint8_t* reinit, cudaStream_t s, int init_from) {
   MapArgs a{L, K, n_views, n_hist, status, T_GtoC, T_pnp, counts, kp_index, xs, uv, cov, Kb, diameter, map_valid_in, T_OtoG_in, map_valid, T_OtoG,
-            hist_crop, hist_T_GtoC, hist_K, hist_off, hist_model_kp, hist_uv, hist_cov, 1.0 / (manual_kp_std * manual_kp_std), gate, rcounts, reinit};
+            hist_crop, hist_T_GtoC, hist_K, hist_off, hist_model_kp, hist_uv, hist_cov, 1.0 / (manual_kp_std * manual_kp_std), gate, rcounts, reinit,
+            init_from};
   slam_init_objects_kernel<<<1, 128, 0, s>>>(a);
   slam_reinit_count_kernel<<<n_hist + L, 32, 0, s>>>(a);
   slam_reinit_apply_kernel<<<1, 128, 0, s>>>(a);

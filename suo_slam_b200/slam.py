@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib, runtime
 
 CHI2_GATE = 5.991
+BACKUP_KEY = 10 ** 6        # RANSAC stream of the bbox-centroid PnP of __backup_estimate_camera_pose (the crops use 0..L-1)
 
 
 def invert_SE3(T):
@@ -119,7 +120,9 @@ class SlamTracker:
     ``view_ids`` — the same containers, with the same detection keys (pose, inliers, kp_mask, model_kp, uv_pred, cov_pred, K, bbox,
     prior_uv), so the reference's own bookkeeping (collect_results, ...) can run on top of it.  The two pieces of optimize() that follow
     the per-view solve are here too: the inlier-count check that ends every optimize() (:913-930) and, every ``global_opt_every`` views,
-    the full graph (:443-451, :736-778: cameras and objects free) as ONE coupled ``suo_ba_batch`` problem (csrc/ba_global.cu)."""
+    the full graph (:443-451, :736-778: cameras and objects free) as ONE coupled ``suo_ba_batch`` problem (csrc/ba_global.cu) — and so is
+    __backup_estimate_camera_pose (:933-973) for views without a usable vote (``_backup_camera_pose`` + suo_slam_frame's cam_init_mode).
+    tests/test_gpu_slam.py replays seven sequences whose states the UNMODIFIED reference class produced (tests/golden/slam_seq.npz)."""
 
     def __init__(self, model, kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, check_n_views=15,
                  global_opt_every=10):
@@ -172,17 +175,31 @@ class SlamTracker:
                    T_OtoG=np.zeros((L, 3, 4)), map_valid=np.zeros(L, np.uint8), reinit=np.zeros(L, np.uint8), reinit_counts=np.zeros((L, 2), np.int32))
         p = _lib.ptr
         n_views = len(self.view_ids) + 1
-        if self.record is not None:
-            self.record.append(dict(img=img, K=c(K, np.float64), boxes=boxes, L=L, n1=int((~is_sym).sum()), mk=mk, mm=mm, diam=diam, map_valid=map_valid,
-                                    T_map=c(T_map, np.float64), n_views=n_views, hist=h))
-        ctx.check(_lib.lib().suo_slam_frame(
-            ctx.handle, p(img), H, W, p(c(K, np.float64)), p(boxes), L, int((~is_sym).sum()), p(mk), p(mm), p(diam), p(map_valid), p(c(T_map, np.float64)),
-            n_views, nh, *((p(h["crop"]), p(h["T"]), p(h["K"]), p(h["off"]), p(h["mk"]), p(h["uv"]), p(h["cov"])) if nh else (None,) * 7),
-            float(self.kp_var_thresh), float(self.bbox_thresh), float(self.manual_kp_std), int(self.init_with_outliers), int(self.seed),
-            p(out["T_GtoC"]), p(out["status"]), p(out["T_pnp"]), p(out["kp_used"]), p(out["ba_inliers"]), p(out["uv"]), p(out["cov"]), p(out["prior_uv"]),
-            p(out["prior_mask"]), p(out["K_bbox"]), p(out["T_OtoG"]), p(out["map_valid"]), p(out["reinit"]), p(out["reinit_counts"]), 0, None))
-        cam_ok = bool(out["status"][0])
         n1 = int((~is_sym).sum())
+        if self.record is not None:
+            self.record.append(dict(img=img, K=c(K, np.float64), boxes=boxes, L=L, n1=n1, mk=mk, mm=mm, diam=diam, map_valid=map_valid,
+                                    T_map=c(T_map, np.float64), n_views=n_views, hist=h))
+
+        def call(T_init, mode):
+            T_init = None if T_init is None else c(np.asarray(T_init)[:3], np.float64)
+            ctx.check(_lib.lib().suo_slam_frame(
+                ctx.handle, p(img), H, W, p(c(K, np.float64)), p(boxes), L, n1, p(mk), p(mm), p(diam), p(map_valid), p(c(T_map, np.float64)),
+                n_views, nh, *((p(h["crop"]), p(h["T"]), p(h["K"]), p(h["off"]), p(h["mk"]), p(h["uv"]), p(h["cov"])) if nh else (None,) * 7),
+                float(self.kp_var_thresh), float(self.bbox_thresh), float(self.manual_kp_std), int(self.init_with_outliers), int(self.seed),
+                p(out["T_GtoC"]), p(out["status"]), p(out["T_pnp"]), p(out["kp_used"]), p(out["ba_inliers"]), p(out["uv"]), p(out["cov"]), p(out["prior_uv"]),
+                p(out["prior_mask"]), p(out["K_bbox"]), p(out["T_OtoG"]), p(out["map_valid"]), p(out["reinit"]), p(out["reinit_counts"]),
+                p(T_init), int(mode), 0, None))
+
+        backup = None
+        if self.view_ids and n1 == 0:                      # no non-symmetric object to vote with (:372-391): the backup pose BEFORE the passes
+            T_b, backup = self._backup_camera_pose(obj_ids, bboxes, K)
+            call(T_b, 1)
+        else:
+            call(None, 0)
+            if not out["status"][0] and self.view_ids:     # the vote failed (:404-411): backup pose, then the symmetric pass from it
+                T_b, backup = self._backup_camera_pose(obj_ids, bboxes, K)
+                call(T_b, 2)
+        cam_ok = bool(out["status"][0])
         det = {}
         for q, o in enumerate(ids):
             if q >= n1 and not cam_ok:                    # symmetric objects leave no detection without a camera pose (:413-418)
@@ -208,11 +225,31 @@ class SlamTracker:
         res = {k: (v[inv] if isinstance(v, np.ndarray) and v.shape[:1] == (L,) and k not in ("status",) else v) for k, v in out.items()}
         res["cam_ok"] = cam_ok
         res["reinit_ids"] = sorted(ids[q] for q in range(L) if out["reinit"][q])
+        res["backup"] = backup
         res["culled"] = self._cull_objects() if cam_ok and out["status"][3] >= 3 else []       # optimize(curr_only=True) ran to its end
         res["global_stats"] = None
         if cam_ok and self.global_opt_every and len(self.view_ids) > 1 and len(self.view_ids) % self.global_opt_every == 0:      # :443-451
             res["global_stats"] = self.optimize_global()
         return res
+
+    def _backup_camera_pose(self, obj_ids, bboxes, K):
+        """ObjectSLAM.__backup_estimate_camera_pose (:933-973): PnP of the bbox centres against the map positions of the objects in view (one
+        ``suo_pnp_batch`` object; the objects in the ORDER process_view received them); if that fails — fewer than four mapped objects, or
+        PnP reports identity — the constant-velocity guess from the last two camera poses, or the last pose.  -> (T_GtoC [4,4], how)."""
+        from . import geometry
+        bboxes = np.asarray(bboxes, np.float32)
+        cen = [0.5 * (bboxes[i, :2] + bboxes[i, 2:]) for i, o in enumerate(obj_ids) if o in self.obj_poses]
+        ctr = [np.asarray(self.obj_poses[o], np.float64)[:3, 3] for o in obj_ids if o in self.obj_poses]
+        if len(cen) >= 4:                                   # pnp() (:25-41): normalise with K, lambdatwist.pnp, identity = failure
+            KinvT = np.linalg.inv(np.asarray(K, np.float64)).T
+            p2n = np.stack(cen) @ KinvT[:2, :2] + KinvT[2:3, :2]
+            T = geometry.pnp_batch([np.stack(ctr)], [p2n], seed=self.seed, obj_keys=[BACKUP_KEY], ctx=self.model.context())[0]
+            if not np.allclose(T, np.eye(4)):
+                return T, "pnp"
+        if len(self.view_ids) > 1:
+            T1, T2 = _as44(self.cam_poses[self.view_ids[-2]]), _as44(self.cam_poses[self.view_ids[-1]])
+            return (T2 @ invert_SE3(T1)) @ T2, "const_vel"
+        return _as44(self.cam_poses[self.view_ids[-1]]), "last"
 
     def _cull_objects(self):
         """The end of ObjectSLAM.optimize() (:913-930): objects whose detections hold too few inliers over all views leave the map."""

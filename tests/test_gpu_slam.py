@@ -134,6 +134,39 @@ def test_slam_sequence_with_the_periodic_global_optimisation(marker_model, golde
         _check_vs_reference_fixture(G, "glob", i, trk, vid)
 
 
+@pytest.mark.parametrize("name", ["allsym", "newnon", "cv"])
+def test_slam_backup_camera_pose_paths(marker_model, golden_dir, name):
+    """__backup_estimate_camera_pose (lib/object_slam.py:933-973) through the tracker: the bbox-centroid PnP (one suo_pnp_batch object) or the
+    constant-velocity guess on the host, then suo_slam_frame with the pose given (cam_init_mode 1: before the passes, every crop symmetric;
+    cam_init_mode 2: after a failed vote, the non-symmetric group's new objects stay out of the map) — against the oracle's restatement and the
+    state the unmodified reference class reaches (fixtures allsym_* / newnon_* / cv_*)."""
+    sd = synth.make_marker_state_dict(0)
+    seq, present, how = {"allsym": (synth.make_slam_sequence(5, n_views=3, n_obj=6, n_sym=6), None, [None, "pnp", "pnp"]),
+                         "newnon": (synth.make_slam_sequence(6, n_views=3, n_obj=8, n_sym=4), lambda i: range(4) if i == 0 else range(8), [None, "pnp", "pnp"]),
+                         "cv": (synth.make_slam_sequence(7, n_views=3, n_obj=3, n_sym=3), None, [None, "last", "const_vel"])}[name]
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    objs = seq["objs"]
+    trk = slam.SlamTracker(marker_model)
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        pr = list(range(len(objs))) if present is None else list(present(i))
+        a = (v["view_id"], v["img"], seq["K"], [v["dets"][c]["obj_id"] for c in pr], np.stack([v["dets"][c]["bbox"] for c in pr]),
+             np.stack([objs[c]["model_kps"] for c in pr]), np.stack([objs[c]["model_kps_mask"] for c in pr]),
+             np.array([objs[c]["is_symmetric"] for c in pr]), np.array([objs[c]["diameter"] for c in pr]))
+        out = trk.process_view(*a)
+        ref = sfo.process_view(st, sd, *a)
+        vid = v["view_id"]
+        assert out["backup"] == ref["backup"] == how[i] and out["cam_ok"]
+        print(f"[slam backup {name} view {i}] how = {out['backup']}, cam rel diff vs oracle {_rel(trk.cam_poses[vid], st.cam_poses[vid]):.2e}, map {sorted(trk.obj_poses)}, "
+              f"status {out['status'][:6].tolist()}, reinit {out['reinit_ids']}, culled {out['culled']}")
+        assert _rel(trk.cam_poses[vid], st.cam_poses[vid]) < 1e-3
+        assert out["reinit_ids"] == ref["reinit"]
+        assert set(trk.obj_poses) == set(st.obj_poses)
+        for o in st.obj_poses:
+            assert _rel(trk.obj_poses[o], st.obj_poses[o]) < 1e-3, o
+        _check_vs_reference_fixture(G, name, i, trk, vid)
+
+
 def test_slam_views_at_512_with_symmetric_priors(golden_dir):
     """BASELINE configs[4] shape: 512x512 crops -> 128x128 heat-maps (the CTA-per-map reduction kernel, the 48-channel stem fed by device-rendered
     priors), 4 objects of which 2 symmetric, 2 views — the same comparison as above at the T-LESS resolution and thresholds (evaluate.py:68-76)."""

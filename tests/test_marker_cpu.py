@@ -89,7 +89,7 @@ def _slam_args(seq, v):
             np.array([o["is_symmetric"] for o in objs]), np.array([o["diameter"] for o in objs]))
 
 
-def _check_view_against_reference(G, name, i, st, vid, ret):
+def _check_view_against_reference(G, name, i, st, vid, ret, tol=1e-6):
     """One view of oracle/slam_frame_oracle.py against what the UNMODIFIED reference ObjectSLAM.process_view left in its state
     (tests/golden/slam_seq.npz, made by oracle/gen_golden_slam.py).  Gating and chi2 classification: identical.  Keypoints: the functional
     network restatement against the reference's nn.Module, 1e-5.  Poses: 1e-6 of the scene scale — the residue is utils.fix_K_for_bbox_ndc on a float32
@@ -97,11 +97,11 @@ def _check_view_against_reference(G, name, i, st, vid, ret):
     # (rotation entries to 1e-6, translations to 1e-3 mm in a scene ~1 m across: 1e-6 of the scale; the first camera IS the world frame,
     # so a relative error of its own near-zero translation would say nothing)
     rel = lambda a, b: max(float(np.abs(np.asarray(a)[:3, :3] - b[:3, :3]).max()), 1e-3 * float(np.abs(np.asarray(a)[:3, 3] - b[:3, 3]).max()))
-    assert rel(st.cam_poses[vid], G[f"{name}_v{i}_cam"]) < 1e-6
+    assert rel(st.cam_poses[vid], G[f"{name}_v{i}_cam"]) < tol
     ids = G[f"{name}_v{i}_obj_ids"].tolist()
     assert sorted(st.obj_poses) == ids
     for j, o in enumerate(ids):
-        assert rel(st.obj_poses[o], G[f"{name}_v{i}_obj_poses"][j]) < 1e-6, o
+        assert rel(st.obj_poses[o], G[f"{name}_v{i}_obj_poses"][j]) < tol, o
     for o, d in st.detections[vid].items():
         assert np.array_equal(d["kp_mask"], G[f"{name}_v{i}_det{o}_kp_mask"].astype(bool)), o
         assert np.array_equal(np.asarray(d["inliers"]).astype(bool), G[f"{name}_v{i}_det{o}_inliers"].astype(bool)), o
@@ -110,11 +110,13 @@ def _check_view_against_reference(G, name, i, st, vid, ret):
         gp, gu = G[f"{name}_v{i}_det{o}_pose"], G[f"{name}_v{i}_det{o}_prior_uv"]
         assert (d["pose"] is None) == (gp.shape[0] == 0) and (d["prior_uv"] is None) == (gu.shape[0] == 0), o
         if d["pose"] is not None:
-            assert rel(d["pose"], gp) < 1e-6, o
+            assert rel(d["pose"], gp) < tol, o
         if d["prior_uv"] is not None:
             np.testing.assert_allclose(d["prior_uv"], gu, atol=1e-5)
     # the RANSAC streams were keyed alike: one pnp() call per crop with >= 4 gated keypoints, in processing order
-    assert G[f"{name}_v{i}_pnp_keys"].tolist() == sorted(G[f"{name}_v{i}_pnp_keys"].tolist())
+    # (10 ** 6 = the bbox-centroid PnP of __backup_estimate_camera_pose)
+    keys = [k for k in G[f"{name}_v{i}_pnp_keys"].tolist() if k != 10 ** 6]
+    assert keys == sorted(keys)
 
 
 def test_slam_frame_oracle_vs_the_unmodified_reference_process_view(golden_dir):
@@ -137,6 +139,38 @@ def test_slam_frame_oracle_vs_the_unmodified_reference_process_view(golden_dir):
         sym_with_prior = [o["obj_id"] for o in objs if o["is_symmetric"] and st.detections[v["view_id"]][o["obj_id"]]["prior_uv"] is not None]
         assert (len(sym_with_prior) == 3) == (v["view_id"] != 100)        # priors exist once the symmetric objects are in the map
     assert len(st.obj_poses) == 6
+
+
+def test_slam_frame_oracle_vs_the_reference_backup_camera_pose(golden_dir):
+    """__backup_estimate_camera_pose (lib/object_slam.py:933-973) in its three forms, against the unmodified reference:
+    allsym — every object symmetric: bbox-centroid PnP BEFORE the passes (:372-391), every crop gets a prior from that rough pose, one object
+             ends up culled by the inlier-count check (:913-930);
+    newnon — the non-symmetric objects are new to the map: the vote has no hypothesis, centroid PnP AFTER the first pass (:404-411), and those
+             objects are NOT initialised (their pass returned at :566-575);
+    cv     — three objects only: the centroid PnP has fewer than four points -> last pose, then the constant-velocity guess.
+    (The centroid pose is 0.3-1.5 m off on these scenes and the reference leaves it so: what is checked is fidelity, not tracking quality.
+    Poses that hang on such a start agree to 1e-5 of the scene scale.)"""
+    from oracle import slam_frame_oracle as sfo
+    torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    sd = synth.make_marker_state_dict(0)
+    cases = (("allsym", synth.make_slam_sequence(5, n_views=3, n_obj=6, n_sym=6), None, [None, "pnp", "pnp"]),
+             ("newnon", synth.make_slam_sequence(6, n_views=3, n_obj=8, n_sym=4), lambda i: range(4) if i == 0 else range(8), [None, "pnp", "pnp"]),
+             ("cv", synth.make_slam_sequence(7, n_views=3, n_obj=3, n_sym=3), None, [None, "last", "const_vel"]))
+    for name, seq, present, how in cases:
+        st = sfo.State()
+        objs = seq["objs"]
+        for i, v in enumerate(seq["views"]):
+            pr = list(range(len(objs))) if present is None else list(present(i))
+            r = sfo.process_view(st, sd, v["view_id"], v["img"], seq["K"], [v["dets"][c]["obj_id"] for c in pr], np.stack([v["dets"][c]["bbox"] for c in pr]),
+                                 np.stack([objs[c]["model_kps"] for c in pr]), np.stack([objs[c]["model_kps_mask"] for c in pr]),
+                                 np.array([objs[c]["is_symmetric"] for c in pr]), np.array([objs[c]["diameter"] for c in pr]))
+            assert r["backup"] == how[i], (name, i, r["backup"])
+            _check_view_against_reference(G, name, i, st, v["view_id"], r, tol=1e-5)
+        if name == "allsym":
+            assert 11 not in st.obj_poses                       # culled in the reference too
+        if name == "newnon":
+            assert sorted(st.obj_poses) == [10, 11, 12, 13]     # the four non-symmetric objects never enter the map
 
 
 def test_frame_oracle_vs_the_unmodified_reference_in_single_view_mode(golden_dir):
