@@ -93,7 +93,7 @@ def install():
     return importlib.import_module("lib.object_slam"), shim
 
 
-def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, view_objs=None, **kw):
+def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, view_objs=None, ext_cam=None, **kw):
     objs = seq["objs"]
     mesh_db = {o["obj_id"]: dict(is_symmetric=bool(o["is_symmetric"]), diameter=float(o["diameter"])) for o in objs}
     with contextlib.redirect_stdout(io.StringIO()):
@@ -104,7 +104,7 @@ def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, vi
     out = {}
     for i, v in enumerate(seq["views"][:n_views]):
         present = list(range(len(objs))) if view_objs is None else list(view_objs(i))          # indices of the objects detected in this view
-        is_sym = np.array([objs[c]["is_symmetric"] for c in present])
+        is_sym = np.array([objs[c]["is_symmetric"] or ext_cam is not None for c in present])     # (an external pose makes every object "symmetric", :353)
         order = [present[j] for j in np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]])]
         shim.crops = [(objs[c]["model_kps"], pos) for pos, c in enumerate(order)]
         shim.calls = []
@@ -112,7 +112,8 @@ def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, vi
         bboxes = np.stack([v["dets"][c]["bbox"] for c in present]).astype(np.float32)
         mk, mm = np.stack([objs[c]["model_kps"] for c in present]), np.stack([objs[c]["model_kps_mask"] for c in present])
         with contextlib.redirect_stdout(io.StringIO()):
-            slam.process_view(v["view_id"], v["img"], seq["K"], obj_ids, bboxes.copy(), mk, mm, mm.copy())
+            slam.process_view(v["view_id"], v["img"], seq["K"], obj_ids, bboxes.copy(), mk, mm, mm.copy(),
+                              cam_pose=None if ext_cam is None else ext_cam(i, v))
         vid = v["view_id"]
         assert vid in slam.cam_poses, "the reference lost the camera"
         out[f"v{i}_cam"] = np.asarray(slam.cam_poses[vid], np.float64)[:3]
@@ -169,7 +170,7 @@ def run_single_view_frames(osl_mod, shim, ckpt, seed0, n_frames, n_obj=8):
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "slam_seq.npz"))
-    ap.add_argument("--scenarios", default="clean,corrupt,glob,allsym,newnon,cv,c5,sv")
+    ap.add_argument("--scenarios", default="clean,corrupt,glob,allsym,newnon,cv,extcam,c5,sv")
     a = ap.parse_args(argv)
     want = a.scenarios.split(",")
     torch.manual_seed(0)
@@ -207,6 +208,17 @@ def main(argv=None):
             sq = synth.make_slam_sequence(7, n_views=3, n_obj=3, n_sym=3)
             for k, v in run_sequence(osl_mod, shim, ckpt, sq, 3).items():
                 fix["cv_" + k] = v
+        if "extcam" in want:       # external camera poses (process_view's cam_pose, :349-353): the ground truth perturbed by a few mm / mrad
+            def noisy(i, v):
+                rng = np.random.default_rng(900 + i)
+                w = rng.normal(scale=2e-3, size=3)
+                Wx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+                T = np.array(v["T_GtoC"][:3], np.float64)
+                T[:, :3] = (np.eye(3) + Wx + 0.5 * Wx @ Wx) @ T[:, :3]
+                T[:, 3] += rng.normal(scale=3.0, size=3)
+                return T
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq, 3, ext_cam=noisy).items():
+                fix["extcam_" + k] = v
         if "c5" in want:
             # (c) configs[4] shape: 512x512 crops, T-LESS thresholds (evaluate.py:68-76), 4 objects of which 2 symmetric, 2 views
             seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)

@@ -248,18 +248,22 @@ def _optimize_global(st, its=(10, 10, 40, 40)):
 
 
 def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, model_masks, is_sym, diameters, res=256,
-                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, global_opt_every=None):
+                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, global_opt_every=None, cam_pose=None):
     """process_view (:327-451), SLAM mode, no external camera pose, bbox_inflate = 0.  Symmetric crops get the prior heat maps.
     global_opt_every: the periodic full optimize() of :443-451 (None: never, as on sequences shorter than ObjectSLAM's default of 10)."""
     obj_ids, bboxes = list(obj_ids), np.asarray(bboxes, np.float32)
     model_kps, model_masks, is_sym, diameters = np.asarray(model_kps), np.asarray(model_masks).astype(bool), np.asarray(is_sym, bool), np.asarray(diameters, float)
     first = len(st.view_ids) == 0
+    if cam_pose is not None:                                     # :349-353: external camera pose, every object gets the prior treatment
+        st.cam_poses[view_id] = np.asarray(cam_pose, np.float64)
+        st.view_ids.append(view_id)
+        is_sym = np.ones(len(obj_ids), bool)
     non, sym = np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]
     keys = np.zeros(len(obj_ids), int)
     keys[np.concatenate([non, sym]).astype(int)] = np.arange(len(obj_ids))
     args = (keys, obj_ids, bboxes, model_kps, model_masks, diameters, res, kp_var_thresh, bbox_thresh, seed, first)
     backup = None
-    if not first and len(non) == 0:                              # :372-391: no non-symmetric object to vote with
+    if cam_pose is None and not first and len(non) == 0:         # :372-391: no non-symmetric object to vote with
         backup = _backup_estimate_camera_pose(st, view_id, obj_ids, bboxes, K, seed)
     _process_objects(st, sd, False, view_id, img_u8, K, non, *args)
     if view_id not in st.cam_poses:                              # :404-411

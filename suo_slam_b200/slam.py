@@ -134,13 +134,14 @@ class SlamTracker:
         self.obj_num_dets, self.diameters = {}, {}          # ObjectSLAM.obj_num_dets (:149,1153); mesh_db[obj]["diameter"]
         self.record = None        # set to a list to keep the packed input arrays of every suo_slam_frame call (bench.py replays them from HBM)
 
-    def process_view(self, view_id, img, K, obj_ids, bboxes, model_kps, model_kps_masks, is_sym, diameters):
+    def process_view(self, view_id, img, K, obj_ids, bboxes, model_kps, model_kps_masks, is_sym, diameters, cam_pose=None):
         """img [H,W,3] u8; K [3,3]; per detected object: id, bbox xyxy, model keypoints [41,3], their mask [41], symmetric flag
-        (mesh_db[obj]["is_symmetric"]), diameter.  Returns the call's raw outputs (per crop, in the ORIGINAL object order)."""
+        (mesh_db[obj]["is_symmetric"]), diameter; cam_pose: optional external T_GtoC [>=3,4] (process_view's cam_pose, :349-353: no vote,
+        every object is treated as symmetric).  Returns the call's raw outputs (per crop, in the ORIGINAL object order)."""
         assert view_id not in self.cam_poses, f"Repeat view_id {view_id}"                      # :329-330
         ctx = self.model.context()
         obj_ids = list(obj_ids)
-        is_sym = np.asarray(is_sym, bool)
+        is_sym = np.ones(len(obj_ids), bool) if cam_pose is not None else np.asarray(is_sym, bool)
         order = np.concatenate([np.nonzero(~is_sym)[0], np.nonzero(is_sym)[0]]).astype(int)    # non-symmetric crops first (:394-418)
         L, Kk = len(order), self.model.num_kp
         c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
@@ -191,7 +192,9 @@ class SlamTracker:
                 p(T_init), int(mode), 0, None))
 
         backup = None
-        if self.view_ids and n1 == 0:                      # no non-symmetric object to vote with (:372-391): the backup pose BEFORE the passes
+        if cam_pose is not None:
+            call(cam_pose, 1)
+        elif self.view_ids and n1 == 0:                    # no non-symmetric object to vote with (:372-391): the backup pose BEFORE the passes
             T_b, backup = self._backup_camera_pose(obj_ids, bboxes, K)
             call(T_b, 1)
         else:

@@ -167,6 +167,39 @@ def test_slam_backup_camera_pose_paths(marker_model, golden_dir, name):
         _check_vs_reference_fixture(G, name, i, trk, vid)
 
 
+def _noisy_gt_cam(i, v):
+    """The external camera poses of the "extcam" fixture (oracle/gen_golden_slam.py): ground truth perturbed by a few mm / mrad."""
+    rng = np.random.default_rng(900 + i)
+    w = rng.normal(scale=2e-3, size=3)
+    Wx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    T = np.array(v["T_GtoC"][:3], np.float64)
+    T[:, :3] = (np.eye(3) + Wx + 0.5 * Wx @ Wx) @ T[:, :3]
+    T[:, 3] += rng.normal(scale=3.0, size=3)
+    return T
+
+
+def test_slam_views_with_external_camera_poses(marker_model, golden_dir):
+    """process_view's cam_pose argument (lib/object_slam.py:349-353): the pose is given (here the ground truth perturbed by a few mm / mrad), there
+    is no vote, every crop is treated as symmetric (priors from the given pose) and the curr_only solve refines the pose — suo_slam_frame with
+    cam_init_mode 1, against the oracle and the unmodified reference's states (fixture extcam_*)."""
+    sd = synth.make_marker_state_dict(0)
+    seq = synth.make_slam_sequence(3, n_views=3, n_obj=6)
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    trk = slam.SlamTracker(marker_model)
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        a = _view_args(seq, v)
+        out = trk.process_view(*a, cam_pose=_noisy_gt_cam(i, v))
+        sfo.process_view(st, sd, *a, cam_pose=_noisy_gt_cam(i, v))
+        vid = v["view_id"]
+        print(f"[slam extcam view {i}] cam rel diff vs oracle {_rel(trk.cam_poses[vid], st.cam_poses[vid]):.2e}, vs ground truth "
+              f"{np.linalg.norm(trk.cam_poses[vid][:, 3] - v['T_GtoC'][:3, 3]):.2f} mm (given: {np.linalg.norm(_noisy_gt_cam(i, v)[:, 3] - v['T_GtoC'][:3, 3]):.2f} mm), "
+              f"priors for {int(out['prior_mask'].any(1).sum())} crops")
+        assert _rel(trk.cam_poses[vid], st.cam_poses[vid]) < 1e-3 and set(trk.obj_poses) == set(st.obj_poses)
+        assert int(out["prior_mask"].any(1).sum()) == (0 if i == 0 else 6)
+        _check_vs_reference_fixture(G, "extcam", i, trk, vid)
+
+
 def test_slam_views_at_512_with_symmetric_priors(golden_dir):
     """BASELINE configs[4] shape: 512x512 crops -> 128x128 heat-maps (the CTA-per-map reduction kernel, the 48-channel stem fed by device-rendered
     priors), 4 objects of which 2 symmetric, 2 views — the same comparison as above at the T-LESS resolution and thresholds (evaluate.py:68-76)."""

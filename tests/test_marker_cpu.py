@@ -141,6 +141,17 @@ def test_slam_frame_oracle_vs_the_unmodified_reference_process_view(golden_dir):
     assert len(st.obj_poses) == 6
 
 
+def _noisy_gt_cam(i, v):
+    """The external camera poses of the "extcam" fixture (oracle/gen_golden_slam.py): ground truth perturbed by a few mm / mrad."""
+    rng = np.random.default_rng(900 + i)
+    w = rng.normal(scale=2e-3, size=3)
+    Wx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    T = np.array(v["T_GtoC"][:3], np.float64)
+    T[:, :3] = (np.eye(3) + Wx + 0.5 * Wx @ Wx) @ T[:, :3]
+    T[:, 3] += rng.normal(scale=3.0, size=3)
+    return T
+
+
 def test_slam_frame_oracle_vs_the_reference_backup_camera_pose(golden_dir):
     """__backup_estimate_camera_pose (lib/object_slam.py:933-973) in its three forms, against the unmodified reference:
     allsym — every object symmetric: bbox-centroid PnP BEFORE the passes (:372-391), every crop gets a prior from that rough pose, one object
@@ -169,6 +180,12 @@ def test_slam_frame_oracle_vs_the_reference_backup_camera_pose(golden_dir):
             _check_view_against_reference(G, name, i, st, v["view_id"], r, tol=1e-5)
         if name == "allsym":
             assert 11 not in st.obj_poses                       # culled in the reference too
+    # external camera poses (process_view's cam_pose argument, :349-353): no vote, every crop gets the prior treatment
+    seq = synth.make_slam_sequence(3, n_views=3, n_obj=6)
+    st = sfo.State()
+    for i, v in enumerate(seq["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq, v), cam_pose=_noisy_gt_cam(i, v))
+        _check_view_against_reference(G, "extcam", i, st, v["view_id"], r, tol=1e-5)
         if name == "newnon":
             assert sorted(st.obj_poses) == [10, 11, 12, 13]     # the four non-symmetric objects never enter the map
 
