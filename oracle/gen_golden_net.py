@@ -44,7 +44,25 @@ def small_case(seed, with_prior, ref_utils):
     return img, boxes, prior
 
 
+def kbbox_f32():
+    """kbbox_f32.npz: the reference's utils.fix_K_for_bbox_ndc on FLOAT32 bboxes (what lib/datasets/bop.py:540-552 produces and
+    lib/object_slam.py:1086 passes) with fractional coordinates, as the reference stores it (float32, :1082) — the float32 scalar
+    arithmetic of ``x2 - x1`` and ``2.0 / w`` is part of the result.  `python -m oracle.gen_golden_net --kbbox-f32` writes only this file."""
+    ref_utils = ref_shims.import_reference_utils()
+    rng = np.random.default_rng(12)
+    bbs = np.stack([np.array([x, y, x + w, y + h], np.float32) for x, y, w, h in
+                    zip(rng.uniform(0, 400, 64), rng.uniform(0, 300, 64), rng.uniform(20, 240, 64), rng.uniform(20, 180, 64))])
+    raw = np.stack([ref_utils.fix_K_for_bbox_ndc(synth.K_YCBV, bb) for bb in bbs])
+    f32 = np.zeros((len(bbs), 3, 3), np.float32)
+    for k, bb in enumerate(bbs):
+        f32[k] = ref_utils.fix_K_for_bbox_ndc(synth.K_YCBV, bb)
+    np.savez(os.path.join(OUT, "kbbox_f32.npz"), K=synth.K_YCBV, bbox=bbs, K_bbox=raw, K_bbox_f32=f32, numpy=np.__version__)
+    print("wrote kbbox_f32.npz (numpy", np.__version__ + ")")
+
+
 def main():
+    if "--kbbox-f32" in sys.argv:
+        return kbbox_f32()
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shims.import_reference_pkpnet()
     ref_utils = ref_shims.import_reference_utils()
@@ -91,6 +109,7 @@ def main():
         bbs.append(bb)
         outs.append(ref_utils.fix_K_for_bbox_ndc(synth.K_YCBV, bb))
     np.savez(os.path.join(OUT, "kbbox.npz"), K=np.array(Ks), bbox=np.array(bbs), K_bbox=np.array(outs))
+    kbbox_f32()
     print("done")
 
 

@@ -125,6 +125,7 @@ def run_sequence(osl_mod, shim, ckpt, seq, n_views, corrupt_after_first=None, vi
             out[f"v{i}_det{o}_inliers"] = np.asarray(d["inliers"]).astype(np.uint8)
             out[f"v{i}_det{o}_uv"] = d["uv_pred"].astype(np.float64)
             out[f"v{i}_det{o}_cov"] = d["cov_pred"].astype(np.float32)
+            out[f"v{i}_det{o}_K"] = np.asarray(d["K"], np.float64)                 # utils.fix_K_for_bbox_ndc on the float32 bbox, through float32 (:1082-1086,1140)
             out[f"v{i}_det{o}_pose"] = np.zeros((0, 4)) if d["pose"] is None else np.asarray(d["pose"], np.float64)[:3]
             out[f"v{i}_det{o}_prior_uv"] = np.zeros((0, 2), np.float32) if d["prior_uv"] is None else d["prior_uv"]
         if corrupt_after_first is not None and i == 0:

@@ -23,10 +23,14 @@ from . import geom, net_oracle, prior_oracle, slam_oracle
 def fix_K_for_bbox_ndc(K, bbox, f32=True):
     """utils.fix_K_for_bbox_ndc (lib/utils/utils.py:416-429).  f32: rounded through float32 as __run_kp_model stores it
     (K_bbox_np float32, :1082,1086) and widened again (:1140); the prior projection (:500) uses the FP64 product as it is."""
-    x1, y1, x2, y2 = [float(v) for v in bbox]
-    w, h = x2 - x1, y2 - y1
+    b = np.asarray(bbox)
+    if b.dtype == np.float32:        # the reference's float32 scalar arithmetic on a float32 bbox (NumPy >= 2 semantics, see synth.fix_K_for_bbox_ndc)
+        sx, sy = float(np.float32(2.0) / np.float32(b[2] - b[0])), float(np.float32(-2.0) / np.float32(b[3] - b[1]))
+    else:
+        sx, sy = 2.0 / (float(b[2]) - float(b[0])), -2.0 / (float(b[3]) - float(b[1]))
+    x1, y1 = float(b[0]), float(b[1])
     T = np.eye(3); T[0, 2], T[1, 2] = -x1, -y1
-    S = np.eye(3); S[0, :] *= 2.0 / w; S[1, :] *= -2.0 / h; S[0, 2] -= 1.0; S[1, 2] += 1.0
+    S = np.eye(3); S[0, :] *= sx; S[1, :] *= sy; S[0, 2] -= 1.0; S[1, 2] += 1.0
     Kb = S @ T @ np.asarray(K, np.float64)
     return Kb.astype(np.float32).astype(np.float64) if f32 else Kb
 

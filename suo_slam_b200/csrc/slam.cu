@@ -50,9 +50,11 @@ __global__ void slam_kbbox_kernel(const double* __restrict__ Kc, const float* __
                                   double* __restrict__ f32) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= L) return;
-  const double x1 = boxes[4 * c], y1 = boxes[4 * c + 1], x2 = boxes[4 * c + 2], y2 = boxes[4 * c + 3];
-  const double w = x2 - x1, h = y2 - y1;
-  const double sx = 2.0 / w, sy = -2.0 / h;
+  // the boxes are float32 and so is the reference's scalar arithmetic on them (utils.fix_K_for_bbox_ndc on a float32 bbox, NumPy >= 2:
+  // w = x2 - x1 and 2.0 / w in float32, IEEE-rounded — __fsub_rn / __fdiv_rn keep the compiler from contracting or approximating them)
+  const double x1 = boxes[4 * c], y1 = boxes[4 * c + 1];
+  const float w = __fsub_rn(boxes[4 * c + 2], boxes[4 * c]), h = __fsub_rn(boxes[4 * c + 3], boxes[4 * c + 1]);
+  const double sx = (double)__fdiv_rn(2.0f, w), sy = (double)__fdiv_rn(-2.0f, h);
   // S T = [[sx, 0, sx * (-x1) - 1], [0, sy, sy * (-y1) + 1], [0, 0, 1]]
   const double M[9] = {sx, 0.0, sx * (-x1) + (-1.0), 0.0, sy, sy * (-y1) + 1.0, 0.0, 0.0, 1.0};
   for (int r = 0; r < 3; ++r)

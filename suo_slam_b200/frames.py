@@ -15,7 +15,7 @@ def k_bbox_for(K, bboxes):
     ``K_bbox_np`` (float32 array, lib/object_slam.py:1082,1086) before .astype(float64) (:1140)."""
     out = np.zeros((len(bboxes), 3, 3), dtype=np.float32)
     for i, bb in enumerate(bboxes):
-        out[i] = synth.fix_K_for_bbox_ndc(K, bb)
+        out[i] = synth.fix_K_for_bbox_ndc(K, np.asarray(bb, np.float32))       # (the boxes of the C ABI are float32, as the reference's are)
     return out.astype(np.float64)
 
 

@@ -79,14 +79,23 @@ def so3_exp(w: np.ndarray) -> np.ndarray:
 
 def fix_K_for_bbox_ndc(K: np.ndarray, bbox) -> np.ndarray:
     """K_bbox = S·T·K: camera matrix projecting into the bbox's NDC square
-    [-1,1]² with *negative* fy (reference lib/utils/utils.py:416-429)."""
-    x1, y1, x2, y2 = [float(v) for v in bbox]
-    w, h = x2 - x1, y2 - y1
+    [-1,1]² with *negative* fy (reference lib/utils/utils.py:416-429).
+    A float32 bbox — what the reference's data loader hands over (lib/datasets/bop.py:540-552) — keeps the reference's float32
+    scalar arithmetic: ``w = x2 - x1`` is a float32 subtraction and ``2.0 / w`` a float32 division (NumPy >= 2: the Python
+    float is weakly typed; NumPy 1.x divided in float64 — the 6e-8 this moves the scale by is the reference's own
+    environment dependence, and this repo follows the NumPy it is tested with); everything after that is float64."""
+    b = np.asarray(bbox)
+    if b.dtype == np.float32:
+        w32, h32 = np.float32(b[2] - b[0]), np.float32(b[3] - b[1])
+        sx, sy = float(np.float32(2.0) / w32), float(np.float32(-2.0) / h32)
+    else:
+        sx, sy = 2.0 / (float(b[2]) - float(b[0])), -2.0 / (float(b[3]) - float(b[1]))
+    x1, y1 = float(b[0]), float(b[1])
     T = np.eye(3)
     T[0, 2], T[1, 2] = -x1, -y1
     S = np.eye(3)
-    S[0, :] *= 2.0 / w
-    S[1, :] *= -2.0 / h
+    S[0, :] *= sx
+    S[1, :] *= sy
     S[0, 2] -= 1.0
     S[1, 2] += 1.0
     return S @ T @ np.asarray(K, dtype=np.float64)

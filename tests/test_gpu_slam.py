@@ -25,6 +25,8 @@ def _check_vs_reference_fixture(G, name, i, trk, vid):
         assert _rel(trk.obj_poses[o], G[f"{name}_v{i}_obj_poses"][j]) < 1e-3, o
     flips = 0
     for o, g in trk.detections[vid].items():
+        # K_bbox from the device (slam_kbbox_kernel): the reference's float32 scalar arithmetic on the float32 bbox, bit for bit
+        assert np.array_equal(g["K"], G[f"{name}_v{i}_det{o}_K"]), o
         gm = G[f"{name}_v{i}_det{o}_kp_mask"].astype(bool)
         if np.array_equal(g["kp_mask"], gm):                  # (a gate within the conv tolerance of its threshold is checked against the oracle)
             np.testing.assert_allclose(g["uv_pred"], G[f"{name}_v{i}_det{o}_uv"], atol=2e-4)

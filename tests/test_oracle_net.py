@@ -55,6 +55,23 @@ def test_kbbox_golden(golden_dir):
         np.testing.assert_allclose(synth.fix_K_for_bbox_ndc(K, bb), ref, rtol=1e-14, atol=1e-12)
 
 
+def test_kbbox_float32_golden(golden_dir):
+    """utils.fix_K_for_bbox_ndc on float32 bboxes with fractional coordinates (what the reference's loader produces): the host function and
+    the SLAM oracle's copy reproduce the reference's result — including its float32 `x2 - x1` and `2.0 / w` — to the last bits, and exactly
+    after the float32 staging of lib/object_slam.py:1082-1086."""
+    from oracle import slam_frame_oracle as sfo
+    from suo_slam_b200 import frames
+    g = np.load(f"{golden_dir}/kbbox_f32.npz")
+    for bb, raw, f32 in zip(g["bbox"], g["K_bbox"], g["K_bbox_f32"]):
+        np.testing.assert_allclose(synth.fix_K_for_bbox_ndc(g["K"], bb), raw, rtol=2e-15, atol=1e-13)
+        np.testing.assert_allclose(sfo.fix_K_for_bbox_ndc(g["K"], bb, f32=False), raw, rtol=2e-15, atol=1e-13)
+        assert np.array_equal(sfo.fix_K_for_bbox_ndc(g["K"], bb), f32.astype(np.float64))
+    assert np.array_equal(frames.k_bbox_for(g["K"], g["bbox"]), g["K_bbox_f32"].astype(np.float64))
+    # the float64 arithmetic the restatements used before differs in the scale factors (this is what the float32 path is for)
+    d = [abs(2.0 / (float(bb[2]) - float(bb[0])) - raw[0, 0] / g["K"][0, 0]) for bb, raw in zip(g["bbox"], g["K_bbox"])]
+    assert max(d) > 1e-10
+
+
 def test_state_dict_spec_counts():
     spec = arch.state_dict_spec()
     assert len(spec) == 1274                         # reference PkpNet().state_dict() (SURVEY §2.2 probe)
