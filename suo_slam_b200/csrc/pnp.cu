@@ -509,7 +509,11 @@ __device__ int warp_lm(QPose& P, const double* xs, const double* ys, const uint8
   return iter;
 }
 
-__global__ void __launch_bounds__(PNP_THREADS)
+// NT threads = NT RANSAC hypotheses evaluated per batch.  The accept rule is replayed sequentially, so the result does not depend on NT:
+// 128 for large batches of objects (two CTAs per SM), 256 when a call brings only a few objects (the drop-in's one-object pnp() calls:
+// an object with outliers needs ~400 iterations = 2 batches instead of 4, and the kernel is latency-bound).
+template <int NT>
+__global__ void __launch_bounds__(NT)
 pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all, const int32_t* __restrict__ offsets,
            const int32_t* __restrict__ npts, int max_pts, double threshold, uint64_t seed, const uint64_t* __restrict__ keys,
            double* __restrict__ T_out, int32_t* __restrict__ stats) {
@@ -518,7 +522,7 @@ pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all,
   double* ys = xs + 3 * max_pts;
   uint8_t* sel = reinterpret_cast<uint8_t*>(ys + 2 * max_pts);
   uint8_t* sel0 = sel + max_pts;
-  __shared__ int counts[PNP_THREADS];
+  __shared__ int counts[NT];
   __shared__ int sh_best_inl, sh_best_it, sh_iters, sh_done;
   const int obj = blockIdx.x;
   const int off = offsets[obj];
@@ -529,15 +533,15 @@ pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all,
     return;
   }
   const uint64_t key = keys ? keys[obj] : (uint64_t)obj;
-  for (int i = threadIdx.x; i < 3 * n; i += PNP_THREADS) xs[i] = xs_all[3 * off + i];
-  for (int i = threadIdx.x; i < 2 * n; i += PNP_THREADS) ys[i] = ys_all[2 * off + i];
+  for (int i = threadIdx.x; i < 3 * n; i += NT) xs[i] = xs_all[3 * off + i];
+  for (int i = threadIdx.x; i < 2 * n; i += NT) ys[i] = ys_all[2 * off + i];
   if (threadIdx.x == 0) { sh_best_inl = 0; sh_best_it = -1; sh_iters = n >= 4 ? ransac_budget(0.0) : 0; sh_done = 0; }
   __syncthreads();
   const double thr2 = threshold * threshold;
 
   // ---- RANSAC in batches of PNP_THREADS hypotheses, sequential accept rule replayed per batch ----
   int total = 0;
-  for (int base = 0; base < MAX_RANSAC_ITERS; base += PNP_THREADS) {
+  for (int base = 0; base < MAX_RANSAC_ITERS; base += NT) {
     if (base >= sh_iters) break;
     const int it = base + threadIdx.x;
     int cnt = -1;
@@ -551,7 +555,7 @@ pnp_kernel(const double* __restrict__ xs_all, const double* __restrict__ ys_all,
     __syncthreads();
     if (threadIdx.x == 0) {
       int iters = sh_iters, best = sh_best_inl, bit = sh_best_it, i = 0;
-      for (; i < PNP_THREADS && base + i < iters; ++i) {
+      for (; i < NT && base + i < iters; ++i) {
         if (counts[i] > best) { best = counts[i]; bit = base + i; iters = ransac_budget(best / (double)n); }
       }
       sh_iters = iters; sh_best_inl = best; sh_best_it = bit; sh_done = base + i;
@@ -615,9 +619,14 @@ int launch_pnp_batch_counts(suo_ctx* ctx, const double* xs, const double* ys, co
   const size_t smem = (size_t)max_pts * PNP_SMEM_BYTES_PER_POINT;
   if (smem > 200 * 1024) { ctx->set_error("suo_pnp_batch: more than " + std::to_string(200 * 1024 / PNP_SMEM_BYTES_PER_POINT) + " points in one object", __FILE__, __LINE__); return SUO_E_INVALID; }
   static bool configured[64] = {};
-  if (smem > 40 * 1024 && first_use_on_device(configured, nullptr))
-    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(pnp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  pnp_kernel<<<n_obj, PNP_THREADS, smem, s>>>(xs, ys, offsets, counts, max_pts, threshold, seed, obj_keys, T_out, stats);
+  if (smem > 40 * 1024 && first_use_on_device(configured, nullptr)) {
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(pnp_kernel<PNP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SUO_CUDA_TRY(ctx, cudaFuncSetAttribute(pnp_kernel<2 * PNP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  if (n_obj <= 64)
+    pnp_kernel<2 * PNP_THREADS><<<n_obj, 2 * PNP_THREADS, smem, s>>>(xs, ys, offsets, counts, max_pts, threshold, seed, obj_keys, T_out, stats);
+  else
+    pnp_kernel<PNP_THREADS><<<n_obj, PNP_THREADS, smem, s>>>(xs, ys, offsets, counts, max_pts, threshold, seed, obj_keys, T_out, stats);
   ctx->launches++;
   SUO_CUDA_TRY(ctx, cudaGetLastError());
   return SUO_OK;
