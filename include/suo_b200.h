@@ -62,6 +62,8 @@ enum {
                                    reported per problem through stats[.,0] = -1 / -2 / -3).  2 = additionally every problem has ONE free vertex and at
                                    most one fixed one (BASELINE config 3, the curr_only camera solve): one warp per problem, state in registers.
                                    0 (default) = inspect the structure (host-pointer calls always do, and pick the same kernels) */
+  , SUO_OPT_SLAM_SFM = 13       /* 1 = suo_slam_frame's curr_only solve runs its = [10, 10, 40, 40] as ObjectSLAM does in sfm_mode
+                                   (lib/object_slam.py:843-846); 0 (default) = [10] * 4 (SLAM mode) */
 };
 
 /* BA vertex/edge conventions (see suo_ba_batch) */

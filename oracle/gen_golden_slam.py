@@ -171,7 +171,7 @@ def run_single_view_frames(osl_mod, shim, ckpt, seed0, n_frames, n_obj=8):
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "slam_seq.npz"))
-    ap.add_argument("--scenarios", default="clean,corrupt,glob,allsym,newnon,cv,extcam,c5,sv")
+    ap.add_argument("--scenarios", default="clean,corrupt,glob,allsym,newnon,cv,sfm,extcam,c5,sv")
     a = ap.parse_args(argv)
     want = a.scenarios.split(",")
     torch.manual_seed(0)
@@ -209,6 +209,9 @@ def main(argv=None):
             sq = synth.make_slam_sequence(7, n_views=3, n_obj=3, n_sym=3)
             for k, v in run_sequence(osl_mod, shim, ckpt, sq, 3).items():
                 fix["cv_" + k] = v
+        if "sfm" in want:          # sfm_mode: re-initialisation test over all views, its = [10, 10, 40, 40] for the per-view solve too, global optimize() after EVERY view
+            for k, v in run_sequence(osl_mod, shim, ckpt, seq, 3, sfm_mode=True).items():
+                fix["sfm_" + k] = v
         if "extcam" in want:       # external camera poses (process_view's cam_pose, :349-353): the ground truth perturbed by a few mm / mrad
             def noisy(i, v):
                 rng = np.random.default_rng(900 + i)

@@ -120,7 +120,7 @@ def _process_objects(st, sd, is_sym, view_id, img, K, idx, keys, obj_ids, bboxes
     return detection
 
 
-def _optimize_curr_only(st, view_id, init_with_outliers):
+def _optimize_curr_only(st, view_id, init_with_outliers, its=(10, 10, 10, 10)):
     """optimize(curr_only=True) (:703-930): one free camera vertex, one EdgeSE3ProjectFromFixedObject per gated keypoint of every
     mapped object of the current view, its = [10] * 4."""
     if view_id not in st.cam_poses:
@@ -143,7 +143,7 @@ def _optimize_curr_only(st, view_id, init_with_outliers):
     if n == 0:
         return None
     P, inl, stats = geom.ba_optimize(np.asarray(st.cam_poses[view_id])[None, :3], np.zeros(1, np.uint8), np.full(n, -1, np.int32), np.zeros(n, np.int32),
-                                     np.asarray(cam_k), np.asarray(p), np.asarray(uv), np.asarray(info), np.ones(n), [10, 10, 10, 10],
+                                     np.asarray(cam_k), np.asarray(p), np.asarray(uv), np.asarray(info), np.ones(n), list(its),
                                      init_with_outliers=init_with_outliers)
     st.cam_poses[view_id] = P[0]
     for (o, k), v in zip(owner, inl):
@@ -252,7 +252,8 @@ def _optimize_global(st, its=(10, 10, 40, 40)):
 
 
 def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, model_masks, is_sym, diameters, res=256,
-                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, global_opt_every=None, cam_pose=None):
+                 kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, global_opt_every=None, cam_pose=None,
+                 sfm_mode=False):
     """process_view (:327-451), SLAM mode, no external camera pose, bbox_inflate = 0.  Symmetric crops get the prior heat maps.
     global_opt_every: the periodic full optimize() of :443-451 (None: never, as on sequences shorter than ObjectSLAM's default of 10)."""
     obj_ids, bboxes = list(obj_ids), np.asarray(bboxes, np.float32)
@@ -278,11 +279,12 @@ def process_view(st: State, sd, view_id, img_u8, K, obj_ids, bboxes, model_kps, 
             backup = _backup_estimate_camera_pose(st, view_id, obj_ids, bboxes, K, seed)
     if len(sym):
         _process_objects(st, sd, True, view_id, img_u8, K, sym, *args)
-    reinit, counts, _ = slam_oracle.maybe_reinit_objects(st.obj_poses, st.cam_poses, st.detections, st.view_ids, view_id, 15, manual_kp_std)
+    reinit, counts, _ = slam_oracle.maybe_reinit_objects(st.obj_poses, st.cam_poses, st.detections, st.view_ids, view_id,
+                                                          len(st.view_ids) if sfm_mode else 15, manual_kp_std)          # :417
     for o, T in reinit.items():                                  # :683-690
         st.obj_poses[o] = T
-    stats = _optimize_curr_only(st, view_id, init_with_outliers)
+    stats = _optimize_curr_only(st, view_id, init_with_outliers, (10, 10, 40, 40) if sfm_mode else (10, 10, 10, 10))       # :843-846
     glob = None
-    if global_opt_every and len(st.view_ids) > 1 and len(st.view_ids) % global_opt_every == 0:      # :443-451
+    if sfm_mode or (global_opt_every and len(st.view_ids) > 1 and len(st.view_ids) % global_opt_every == 0):      # :443-451
         glob = _optimize_global(st)
     return dict(cam_ok=True, reinit=sorted(reinit), reinit_counts=counts, ba_stats=stats, global_stats=glob, backup=backup)

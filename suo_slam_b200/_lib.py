@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsuo_b200.so")
 
 SUO_OPT_CONV_BACKEND, SUO_OPT_TF32_PASSES, SUO_OPT_USE_GRAPH, SUO_OPT_CONV_PERSISTENT, SUO_OPT_MULTISTREAM, SUO_OPT_CONV_MATH, SUO_OPT_CONV_FUSE, SUO_OPT_CONV_PAIR, SUO_OPT_PDL, SUO_OPT_CONV_HALO, SUO_OPT_BA_BLOCK_DIAGONAL, SUO_OPT_PNP_MAX_POINTS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
+SUO_OPT_SLAM_SFM = 13
 
 _lib = None
 vp = C.c_void_p

@@ -507,6 +507,7 @@ int suo_set_option(suo_ctx* ctx, int option, int value) {
     case SUO_OPT_CONV_HALO: ctx->opt_halo = value ? 1 : 0; return SUO_OK;
     case SUO_OPT_PNP_MAX_POINTS: if (value < 4 || value > 4096) return SUO_E_INVALID; ctx->opt_pnp_max_pts = value; return SUO_OK;
     case SUO_OPT_BA_BLOCK_DIAGONAL: if (value < 0 || value > 2) return SUO_E_INVALID; ctx->opt_ba_blockdiag = value; return SUO_OK;
+    case SUO_OPT_SLAM_SFM: ctx->opt_slam_sfm = value ? 1 : 0; return SUO_OK;
     default: return SUO_E_INVALID;
   }
 }
@@ -1815,8 +1816,8 @@ int suo_slam_frame(suo_ctx* ctx, const uint8_t* image_hwc, int H, int W, const d
   rc = launch_slam_ba_assemble(ctx, L, K, o_st, o_cam, o_mv, o_To, w_cnt, w_kpi, w_xs, o_uv, o_cov, o_kb, b_poses, b_fixed, b_pv, b_vc, b_pe, b_ec, b_eo, b_ecam,
                                b_ck, b_p, b_uv, b_info, b_inl, b_src, s);
   if (rc) return rc;
-  static const int32_t its_host[4] = {10, 10, 10, 10};   // curr_only (object_slam.py:845-846)
-  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b_its, its_host, sizeof(its_host), cudaMemcpyHostToDevice, s));
+  static const int32_t its_host[2][4] = {{10, 10, 10, 10}, {10, 10, 40, 40}};   // curr_only in SLAM mode / in sfm_mode (object_slam.py:843-846)
+  SUO_CUDA_TRY(ctx, cudaMemcpyAsync(b_its, its_host[ctx->opt_slam_sfm], sizeof(its_host[0]), cudaMemcpyHostToDevice, s));
   SUO_CUDA_TRY(ctx, cudaMemsetAsync(b_st, 0, 3 * sizeof(int32_t), s));
   rc = launch_ba_batch_scratch(ctx, 1, b_pv, b_pe, b_poses, b_fixed, b_eo, b_ecam, b_ck, b_p, b_uv, b_info, b_inl, b_its, 4, 2.4476519768340177 /* sqrt(5.991) */,
                                5.991, init_with_outliers, b_st, b_err, b_lvl, b_fv, s, b_vc, b_ec, 1 /* one camera vertex: warp kernel */);

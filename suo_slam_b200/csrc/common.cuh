@@ -191,6 +191,7 @@ struct suo_ctx {
   int opt_pnp_max_pts = 64;  // SUO_OPT_PNP_MAX_POINTS: shared-memory point capacity per object of DEVICE-pointer suo_pnp_batch calls
   int opt_act_reuse = 1;     // activation buffers with disjoint live ranges share one allocation (SUO_ACT_REUSE=0: one allocation per buffer, needed by SUO_OPT_MULTISTREAM)
   int opt_ba_blockdiag = 0;  // SUO_OPT_BA_BLOCK_DIAGONAL: device-pointer suo_ba_batch calls skip the host-side structure check
+  int opt_slam_sfm = 0;      // SUO_OPT_SLAM_SFM: its = [10, 10, 40, 40] for suo_slam_frame's curr_only solve
   unsigned long long* trace = nullptr;       // SUO_TRACE: device launch trace of the persistent conv kernels (dumped by suo_destroy)
   int opt_grid_cap = 0;                      // > 0: persistent conv kernels use at most this many CTAs (SUO_GRID_CAP; concurrent-stream experiments)   // developer switches (SUO_EPI_TMA / SUO_MMA_MERGE): TMA-store epilogue, merged hi|lo' weight MMA
   void* net = nullptr;  // NetState (net_exec.cu)

@@ -125,8 +125,11 @@ class SlamTracker:
     tests/test_gpu_slam.py replays seven sequences whose states the UNMODIFIED reference class produced (tests/golden/slam_seq.npz)."""
 
     def __init__(self, model, kp_var_thresh=0.2, bbox_thresh=0.9, manual_kp_std=0.005, init_with_outliers=False, seed=0, check_n_views=15,
-                 global_opt_every=10):
+                 global_opt_every=10, sfm_mode=False):
+        """sfm_mode (ObjectSLAM(sfm_mode=True)): the re-initialisation test looks at ALL earlier views (:417), the per-view solve runs
+        its = [10, 10, 40, 40] (:843-846, SUO_OPT_SLAM_SFM) and the full graph is optimised after EVERY view, the first included (:443)."""
         self.model = model
+        self.sfm_mode = bool(sfm_mode)
         self.kp_var_thresh, self.bbox_thresh, self.manual_kp_std = kp_var_thresh, bbox_thresh, manual_kp_std
         self.init_with_outliers, self.seed, self.check_n_views = init_with_outliers, seed, check_n_views
         self.global_opt_every = global_opt_every
@@ -158,7 +161,8 @@ class SlamTracker:
                 T_map[q] = np.asarray(self.obj_poses[o])[:3]
         # the objects' detections in the last check_n_views - 1 earlier views (__maybe_reinit_objects, :627-650)
         hc, hT, hK, hoff, hmk, huv, hcov = [], [], [], [0], [], [], []
-        for v in [self.view_ids[-(i + 1)] for i in range(min(len(self.view_ids), self.check_n_views - 1))]:
+        n_check = len(self.view_ids) if self.sfm_mode else min(len(self.view_ids), self.check_n_views - 1)
+        for v in [self.view_ids[-(i + 1)] for i in range(n_check)]:
             for q, o in enumerate(ids):
                 d = self.detections[v].get(o)
                 if d is None:
@@ -180,6 +184,8 @@ class SlamTracker:
         if self.record is not None:
             self.record.append(dict(img=img, K=c(K, np.float64), boxes=boxes, L=L, n1=n1, mk=mk, mm=mm, diam=diam, map_valid=map_valid,
                                     T_map=c(T_map, np.float64), n_views=n_views, hist=h))
+
+        ctx.set_option(_lib.SUO_OPT_SLAM_SFM, int(self.sfm_mode))
 
         def call(T_init, mode):
             T_init = None if T_init is None else c(np.asarray(T_init)[:3], np.float64)
@@ -231,7 +237,7 @@ class SlamTracker:
         res["backup"] = backup
         res["culled"] = self._cull_objects() if cam_ok and out["status"][3] >= 3 else []       # optimize(curr_only=True) ran to its end
         res["global_stats"] = None
-        if cam_ok and self.global_opt_every and len(self.view_ids) > 1 and len(self.view_ids) % self.global_opt_every == 0:      # :443-451
+        if cam_ok and (self.sfm_mode or (self.global_opt_every and len(self.view_ids) > 1 and len(self.view_ids) % self.global_opt_every == 0)):      # :443-451
             res["global_stats"] = self.optimize_global()
         return res
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import slam_frame_oracle as sfo
-from suo_slam_b200 import slam, synth
+from suo_slam_b200 import _lib, slam, synth
 from suo_slam_b200.pkpnet import PkpNet
 
 pytestmark = pytest.mark.gpu
@@ -134,6 +134,30 @@ def test_slam_sequence_with_the_periodic_global_optimisation(marker_model, golde
         for o in st.obj_poses:
             assert _rel(trk.obj_poses[o], st.obj_poses[o]) < 1e-3, o
         _check_vs_reference_fixture(G, "glob", i, trk, vid)
+
+
+def test_slam_sequence_in_sfm_mode(marker_model, golden_dir):
+    """ObjectSLAM(sfm_mode=True): re-initialisation test over all views (:417), its = [10, 10, 40, 40] for the per-view solve too (:843-846,
+    SUO_OPT_SLAM_SFM) and the full graph after EVERY view, the first included (:443) — tracker vs oracle vs the unmodified reference (sfm_*)."""
+    sd = synth.make_marker_state_dict(0)
+    seq = synth.make_slam_sequence(3, n_views=3, n_obj=6)
+    G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
+    trk = slam.SlamTracker(marker_model, sfm_mode=True)
+    st = sfo.State()
+    try:
+        for i, v in enumerate(seq["views"]):
+            a = _view_args(seq, v)
+            out = trk.process_view(*a)
+            ref = sfo.process_view(st, sd, *a, sfm_mode=True)
+            vid = v["view_id"]
+            assert out["global_stats"] is not None and ref["global_stats"] is not None
+            print(f"[slam sfm view {i}] curr_only status {out['status'][:6].tolist()} (oracle {ref['ba_stats']}), global {out['global_stats']} (oracle {ref['global_stats']})")
+            for w in trk.cam_poses:
+                assert _rel(trk.cam_poses[w], st.cam_poses[w]) < 1e-3
+            assert set(trk.obj_poses) == set(st.obj_poses)
+            _check_vs_reference_fixture(G, "sfm", i, trk, vid)
+    finally:
+        marker_model.context().set_option(_lib.SUO_OPT_SLAM_SFM, 0)          # (the model fixture is shared by the module's tests)
 
 
 @pytest.mark.parametrize("name", ["allsym", "newnon", "cv"])

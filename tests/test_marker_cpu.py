@@ -227,7 +227,8 @@ def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
     """(a) One object's map pose is pushed away after the first view: the reference's camera-pose vote rejects it and __maybe_reinit_objects
     (lib/object_slam.py:595-697) replaces it in view 1 — the restatement takes the same decisions and reaches the same state.
     (b) 512x512 crops with the T-LESS thresholds and opt_init_with_outliers (evaluate.py:68-76), BASELINE configs[4]'s shape.
-    (c) the periodic global optimize() (cameras and objects free) of a run with global_opt_every = 2."""
+    (c) the periodic global optimize() (cameras and objects free) of a run with global_opt_every = 2.
+    (d) sfm_mode."""
     from oracle import slam_frame_oracle as sfo
     torch.set_num_threads(max(1, min(8, torch.get_num_threads())))
     G = np.load(os.path.join(golden_dir, "slam_seq.npz"))
@@ -248,6 +249,13 @@ def test_slam_frame_oracle_vs_the_reference_reinit_and_512(golden_dir):
         assert (r["global_stats"] is not None) == (i == 1)
         _check_view_against_reference(G, "glob", i, st, v["view_id"], r)
     assert np.abs(G["clean_v1_cam"] - G["glob_v1_cam"]).max() > 0.5          # (the global step moved the camera by ~1 mm in the reference)
+    # (d) sfm_mode: re-initialisation test over ALL views (:417), its = [10, 10, 40, 40] for the per-view solve too (:843-846), global optimize()
+    #     after EVERY view, the first included (:443)
+    st, seq3 = sfo.State(), synth.make_slam_sequence(3, n_views=3, n_obj=6)
+    for i, v in enumerate(seq3["views"]):
+        r = sfo.process_view(st, sd, *_slam_args(seq3, v), sfm_mode=True)
+        assert r["global_stats"] is not None
+        _check_view_against_reference(G, "sfm", i, st, v["view_id"], r)
     seq5 = synth.make_slam_sequence(11, n_views=2, n_obj=4, res=512, n_sym=2, radius=2 * synth.MARKER_RADIUS)
     st = sfo.State()
     for i, v in enumerate(seq5["views"]):
